@@ -1,0 +1,112 @@
+"""TEST INFRASTRUCTURE — build-container only.
+
+Generates `tests/golden/*.npz` by running the UNMODIFIED reference (`/root/reference/easykv`)
+on the 4.36-shaped scaffold via `oracle/ref_harness.py`.  Each file freezes, for one
+(model shape, mode, policy) case: the densely prefilled K/V, then for every later forward and
+layer the post-RoPE q, the new k/v and the attention output entering o_proj, every eviction
+event the reference issued (victim ids exactly as passed to `truncate_kv_cache_*`), the final
+cache and the console line with the retained-cache ratio.
+
+    python -m oracle.gen_golden            # regenerate everything (≈1 min, CPU)
+
+Reproducible within this image (torch 2.11.0 CPU); victim ids are what the parity tests pin.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness, scaffold  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "c1_llama_enc_roco_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=256, dtype="float32",
+                                   mode="encoding", stride=8, max_new_tokens=4,
+                                   gen=dict(budget=0.5, kv_policy="roco")),
+    "gqa_mistral_auto_roco_fp32": dict(arch="mistral", L=2, H=8, Hkv=2, d=128, seq=160, dtype="float32",
+                                       mode="auto", stride=8, max_new_tokens=24,
+                                       gen=dict(budget=64, kv_policy="roco")),
+    "llama_decoding_roco_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=32, dtype="float32",
+                                     mode="decoding", stride=1, max_new_tokens=72,
+                                     gen=dict(budget=40, kv_policy="roco")),
+    "llama_decoding_h2o_fp32": dict(arch="llama", L=1, H=4, Hkv=2, d=128, seq=24, dtype="float32",
+                                    mode="decoding", stride=1, max_new_tokens=40,
+                                    gen=dict(budget=16, kv_policy="h2o_head")),
+    "gqa_mistral_enc_h2o_fp32": dict(arch="mistral", L=2, H=8, Hkv=2, d=128, seq=132, dtype="float32",
+                                     mode="encoding", stride=4, max_new_tokens=3,
+                                     gen=dict(budget=0.5, kv_policy="h2o_head")),
+    "llama_enc_tova_fp32": dict(arch="llama", L=2, H=4, Hkv=2, d=128, seq=120, dtype="float32",
+                                mode="encoding", stride=8, max_new_tokens=3,
+                                gen=dict(budget=0.5, kv_policy="tova")),
+    "llama_auto_tova_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=96, dtype="float32",
+                                 mode="auto", stride=8, max_new_tokens=20,
+                                 gen=dict(budget=40, kv_policy="tova")),
+    "llama_auto_recency_fp32": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=64, dtype="float32",
+                                    mode="auto", stride=4, max_new_tokens=8,
+                                    gen=dict(budget=32, kv_policy="recency")),
+    "llama_ppl_roco_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=144, dtype="float32",
+                                mode="ppl", stride=8, max_new_tokens=0,
+                                gen=dict(budget=0.4, kv_policy="roco")),
+    # 16-bit rounding points
+    "gqa_mistral_auto_roco_fp16": dict(arch="mistral", L=2, H=8, Hkv=2, d=128, seq=160, dtype="float16",
+                                       mode="auto", stride=8, max_new_tokens=24,
+                                       gen=dict(budget=64, kv_policy="roco")),
+    "llama_enc_roco_fp16": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=128, dtype="float16",
+                                mode="encoding", stride=8, max_new_tokens=2,
+                                gen=dict(budget=0.5, kv_policy="roco")),
+}
+
+
+def run_case(name, c):
+    dtype = getattr(torch, c["dtype"])
+    model = scaffold.build(c["arch"], seed=0, dtype=dtype, L=c["L"], H=c["H"], Hkv=c["Hkv"], d=c["d"], vocab=512)
+    ids = torch.randint(3, 512, (1, c["seq"]), generator=torch.Generator().manual_seed(1))
+    gen = dict(temperature=1e-9, top_p=1.0, max_new_tokens=c["max_new_tokens"], **c["gen"])
+    ppl = c["mode"] == "ppl"
+    tr = ref_harness.run_reference(model, ids, gen, mode="encoding" if ppl else c["mode"], stride=c["stride"], ppl=ppl)
+    arrs = {}
+    npdt = np.float32 if dtype == torch.float32 else np.float16
+    for l, (k, v) in enumerate(tr.prefill_cache):
+        arrs[f"prefill_K_{l}"], arrs[f"prefill_V_{l}"] = k.numpy().astype(npdt), v.numpy().astype(npdt)
+    fmeta = []
+    for f, fw in enumerate(tr.forwards):
+        fmeta.append(dict(q_len=fw["q_len"], recorded=len(fw["layers"]) > 0 and f > 0,
+                          pos0=None if fw["position_ids"] is None else int(fw["position_ids"][0])))
+        if f == 0:
+            continue
+        for l, rec in enumerate(fw["layers"]):
+            for key in "qkvo":
+                arrs[f"f{f}_l{l}_{key}"] = rec[key].numpy().astype(npdt)
+    emeta = []
+    for e, ev in enumerate(tr.events):
+        arrs[f"ev{e}_ids"] = ev["ids"].numpy().astype(np.int64)
+        emeta.append(dict(kind=ev["kind"], fwd=ev["fwd"], n_before=ev["n_before"]))
+    for l, kv in enumerate(tr.final_cache):
+        arrs[f"final_K_{l}"], arrs[f"final_V_{l}"] = kv[0][0].numpy().astype(npdt), kv[1][0].numpy().astype(npdt)
+    meta = dict(name=name, case=c, forwards=fmeta, events=emeta, printed=tr.printed, tokens=tr.tokens,
+                result=tr.result if isinstance(tr.result, float) else str(tr.result),
+                torch=torch.__version__, reference_commit="a1d71cae3b562d9a709dda3741bd63e46a09ad31")
+    arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    return tr
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    only = sys.argv[1:]
+    for name, c in CASES.items():
+        if only and name not in only:
+            continue
+        tr = run_case(name, c)
+        sz = os.path.getsize(os.path.join(OUT, name + ".npz")) / 1e6
+        print(f"{name}: {len(tr.forwards)} forwards, {len(tr.events)} eviction events, {sz:.2f} MB | "
+              + tr.printed.strip().splitlines()[-1])

@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+Teacher-forced replay of a golden trace (`tests/golden/*.npz`, produced from the unmodified
+reference by `oracle/gen_golden.py`) through any *engine* exposing
+
+    engine.load_prefill(layer, K[Hkv,n,d], V[Hkv,n,d], n_scored, C_init or None)
+    engine.forward(layer, step: restate.Step, q[H,ql,d], k[Hkv,ql,d], v[Hkv,ql,d], force=None)
+        -> (out[H,ql,d], victims[Hkv,evict] int64 or None)
+       (`force`: victim ids to APPLY instead of the engine's own choice — the engine still
+        reports its own choice; used to re-synchronise after a tie-ambiguous reference step)
+    engine.export(layer) -> (K[Hkv,n,d], V[Hkv,n,d]) in the reference's logical order
+
+Every forward gets the reference's own q/k/v, so each eviction decision
+is tested on identical inputs; victims are compared as sorted sets per (layer, head)
+(SURVEY A.5 "What to compare").
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import restate
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def list_golden():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    return meta, z
+
+
+class OracleEngine:
+    """The CPU restatement behind the engine interface."""
+
+    def __init__(self, L, H, Hkv, d, dtype, scale_mul=False):
+        self.layers = [restate.LayerOracle(Hkv, d, dtype) for _ in range(L)]
+        self.scale_mul = scale_mul
+
+    def load_prefill(self, l, K, V, n_scored, C_init):
+        self.layers[l].load_prefill(K, V, n_scored, C_init)
+
+    def forward(self, l, st, q, k, v, force=None):
+        return self.layers[l].forward(st, q, k, v, self.scale_mul, force=force)
+
+    def export(self, l):
+        return self.layers[l].K, self.layers[l].V
+
+    def margin(self, l):
+        return self.layers[l].last_margin
+
+
+@dataclass
+class Report:
+    name: str
+    n_forwards: int = 0
+    n_events: int = 0
+    victim_mismatch: list = field(default_factory=list)   # (fwd, layer, ref ids, got ids, margin)
+    tie_ambiguous: list = field(default_factory=list)     # same, but the reference's margin was 0
+    max_out_err: float = 0.0
+    final_cache_equal: bool = True
+    min_margin: tuple = (float("inf"), float("inf"))
+    retained: int = 0
+
+    @property
+    def ok(self):
+        return not self.victim_mismatch and self.final_cache_equal
+
+
+def case_plan(meta):
+    c = meta["case"]
+    gen = c["gen"]
+    mode = c["mode"]
+    plan = restate.resolve_plan(mode, c["seq"], gen["budget"], c["stride"],
+                                gen.get("recent_ratio", 0.1), gen.get("temp_length", 4))
+    return plan, gen["kv_policy"], c["max_new_tokens"]
+
+
+def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0) -> Report:
+    """`resync`: after comparing, apply the REFERENCE's victims so every later step is again
+    tested on identical state.  `shadow`: an OracleEngine factory run in lock-step (always
+    forced to the reference's victims) whose decision margins classify a mismatch as
+    tie-ambiguous (margin <= tie_eps) or real."""
+    meta, z = load_golden(name)
+    c = meta["case"]
+    dtype = getattr(torch, c["dtype"])
+    L, H, Hkv, d = c["L"], c["H"], c["Hkv"], c["d"]
+    plan, policy, max_new = case_plan(meta)
+    eng = engine_factory(L, H, Hkv, d, dtype)
+    sh = shadow(L, H, Hkv, d, dtype) if shadow is not None else None
+    rep = Report(name)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+    C0 = restate.initial_counter(plan)
+    for l in range(L):
+        K, V = T(z[f"prefill_K_{l}"]), T(z[f"prefill_V_{l}"])
+        n_scored = 0 if plan.mode == "decoding" else K.shape[1]
+        eng.load_prefill(l, K, V, n_scored, C0)
+        if sh is not None:
+            sh.load_prefill(l, K, V, n_scored, C0)
+    events = {}
+    for e, ev in enumerate(meta["events"]):
+        events[ev["fwd"]] = (ev, z[f"ev{e}_ids"])
+    sched = list(restate.schedule(plan, policy, max_new))
+    fwds = meta["forwards"][1:]
+    assert len(sched) == len(fwds), (len(sched), len(fwds))
+    for f, ((kind, ql, st), fm) in enumerate(zip(sched, fwds), start=1):
+        assert ql == fm["q_len"]
+        rep.n_forwards += 1
+        ev = events.get(f)
+        assert (ev is not None) == bool(st.evict), (f, st)
+        for l in range(L):
+            if not fm["recorded"]:
+                raise AssertionError("golden forward without tensors")
+            q, k, v, o = (T(z[f"f{f}_l{l}_{key}"]) for key in "qkvo")
+            ref_ids = None
+            if ev is not None:
+                kindname, ids = ev[0]["kind"], torch.from_numpy(ev[1])
+                if kindname == "range":
+                    ref_ids = torch.arange(int(ids[0]), int(ids[1])).repeat(Hkv, 1)
+                else:
+                    ref_ids = ids[l].reshape(Hkv, -1)
+            force = ref_ids if resync else None
+            out, vic = eng.forward(l, st, q, k, v, force=force)
+            o_ref = o.view(ql, H, d).transpose(0, 1).float()
+            rep.max_out_err = max(rep.max_out_err, (out.float().cpu() - o_ref).abs().max().item())
+            margin = None
+            meng = sh if sh is not None else (eng if hasattr(eng, "margin") else None)
+            if sh is not None:
+                sh.forward(l, st, q, k, v, force=ref_ids)
+            if meng is not None and st.evict:
+                margin = meng.margin(l)
+                rep.min_margin = (min(rep.min_margin[0], margin[0]), min(rep.min_margin[1], margin[1]))
+            if ev is not None:
+                got = torch.sort(vic.cpu().long(), dim=-1)[0]
+                ref_sorted = torch.sort(ref_ids, dim=-1)[0]
+                if not torch.equal(got, ref_sorted):
+                    rec = (f, l, ref_sorted, got, margin)
+                    if margin is not None and min(margin) <= tie_eps:
+                        rep.tie_ambiguous.append(rec)
+                    else:
+                        rep.victim_mismatch.append(rec)
+        if ev is not None:
+            rep.n_events += 1
+        if (rep.victim_mismatch or rep.tie_ambiguous) and not resync:
+            rep.final_cache_equal = False
+            return rep
+    for l in range(L):
+        K, V = eng.export(l)
+        Kr, Vr = T(z[f"final_K_{l}"]), T(z[f"final_V_{l}"])
+        rep.retained = K.shape[1]
+        if K.shape != Kr.shape or not (torch.equal(K.cpu(), Kr) and torch.equal(V.cpu(), Vr)):
+            rep.final_cache_equal = False
+    return rep
