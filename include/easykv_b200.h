@@ -1,0 +1,149 @@
+/*
+ * easykv_b200 — C ABI of the B200-native KV-budgeted attention + eviction path.
+ *
+ * Drop-in boundary.  The reference (DRSY/EasyKV) has no FFI: its hot path is
+ * PyTorch called from Python.  Each entry point below replaces a *group of reference call
+ * sites*; the Python host code in `easykv_b200/` binds them with ctypes (see INTEGRATION.md
+ * for the stub a maintainer of the reference would add).  All paths are relative to the
+ * reference repository root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer into caller-owned
+ *     (e.g. torch-allocated) memory unless stated otherwise.  The library owns nothing.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *     nothing, never synchronises, and is CUDA-graph capturable.
+ *   - return value: 0 = ok, negative = error (EKV_ERR_*); `ekv_last_error()` gives a
+ *     thread-local human-readable message.  Nothing throws.
+ *   - dtype: the element type of q/k/v/K/V/out (EKV_F16, EKV_BF16, EKV_F32).  Policy state is
+ *     always fp32, slot maps int32.
+ *
+ * HBM layout (per layer; B sequences, Hkv KV heads, `cap` physical slots, head dim d)
+ *   K, V        [B, Hkv, cap, d]   dtype      physical slot order — rows NEVER move
+ *   S, SQ, C    [B, Hkv, cap]      fp32       per-slot policy state (sum p, sum p^2, counter)
+ *   lidx        [B, Hkv, cap]      int32      physical slot -> logical index in the reference's
+ *                                             arrival-ordered cache, -1 = free slot
+ *   The reference deletes victims order-preservingly (two full cache copies per step,
+ *   easykv/easykv.py:56-82); here eviction renumbers `lidx` and the next token overwrites the
+ *   victim's physical slot.  K is cached post-RoPE (easykv/llama_patch.py:190-196) so attention
+ *   is invariant to physical order.  K/V buffers must be initialised (e.g. zeros): free slots
+ *   are streamed and masked, never skipped.
+ */
+#ifndef EASYKV_B200_H
+#define EASYKV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EKV_ABI_VERSION 1
+
+enum { EKV_F16 = 0, EKV_BF16 = 1, EKV_F32 = 2 };
+
+/* kv_policy of easykv/easykv.py:205.  'recency' and 'random' evict a host-chosen contiguous
+ * logical range (easykv.py:343-362,491-499,741-747) => EKV_POLICY_RANGE. */
+enum {
+  EKV_POLICY_NONE = 0,  /* 'full' / plain attention over the retained cache            */
+  EKV_POLICY_ROCO = 1,  /* easykv.py:292-296 accumulate, :319-324 / :470-476 select      */
+  EKV_POLICY_H2O  = 2,  /* 'h2o_head': :288-291, :310-311 / :462-463                     */
+  EKV_POLICY_TOVA = 3,  /* :297-300, :334-335 / :484-485                                 */
+  EKV_POLICY_RANGE = 4  /* recency / random: evict logical [range_start, +evict)         */
+};
+
+enum {
+  EKV_OK = 0,
+  EKV_ERR_INVALID = -1,      /* bad argument / unsupported shape  (reference: ValueError, llama_patch.py:204-228) */
+  EKV_ERR_UNSUPPORTED = -2,  /* valid request this build cannot serve                                           */
+  EKV_ERR_CUDA = -3          /* CUDA runtime error on launch                                                    */
+};
+
+/* What the reference's mode loops (easykv.py:257-363, 426-500, 587-748, 816-892) decide for ONE
+ * forward.  Field-for-field the same as oracle/restate.py:Step. */
+typedef struct ekv_step {
+  int32_t policy;        /* EKV_POLICY_*                                                          */
+  int32_t accumulate;    /* update S/SQ from this forward's probabilities (easykv.py:443)          */
+  int32_t evict;         /* victims per (sequence, kv head): 0, 1 (decode) or stride (chunk)       */
+  int32_t apply;         /* 1: perform the eviction in place; 0: only report the victims           */
+  int32_t score_offset;  /* 'decoding' mode: the first P logical slots carry no state (:294,:324)  */
+  float   counter_add;   /* C += counter_add on scored slots before select (:304,:460,:708)        */
+  float   c_new0;        /* C of the i-th appended slot = c_new0 - i*c_new_step (:244-245,:416,:469)*/
+  float   c_new_step;
+  int32_t k_feasible;    /* roco: size of the low-std candidate set (:322,:474)                    */
+  int32_t protect_last;  /* roco: std[-10:] = 1e9 (:321)                                           */
+  int32_t sink_protect;  /* roco strided: std[:sink] = 1e9 (:473)                                  */
+  int32_t win_lo;        /* h2o/tova: candidates are state[win_lo : n_s - win_recent] (:311,:463)  */
+  int32_t win_recent;
+  int32_t range_start;   /* RANGE: first logical index (relative to score_offset) to evict         */
+  int32_t scale_mode;    /* 0: logits / sqrt(d) (ATen CPU);  1: logits * (1/sqrt(d)) (ATen CUDA)   */
+  int32_t reserved;
+} ekv_step;
+
+/* One layer's tensors for one forward.  Replaces the body of llama_forward / mistral_forward
+ * between the projections and o_proj (easykv/llama_patch.py:193-230, mistral_patch.py:137-170)
+ * AND the per-layer slice of the score/evict block of generate() (easykv/easykv.py:271-362). */
+typedef struct ekv_layer_io {
+  const void* q;        /* [B, H,   q_len, d] post-RoPE queries                                   */
+  const void* k_new;    /* [B, Hkv, q_len, d] post-RoPE keys of the q_len appended tokens          */
+  const void* v_new;    /* [B, Hkv, q_len, d]                                                      */
+  void*       out;      /* [B, H,   q_len, d] softmax(QK^T/sqrt(d)) V  (input of o_proj)           */
+  void*       K;        /* [B, Hkv, cap, d]   in/out: the appended rows are written here           */
+  void*       V;
+  float*      S;        /* [B, Hkv, cap]      in/out                                               */
+  float*      SQ;
+  float*      C;
+  int32_t*    lidx;     /* [B, Hkv, cap]      in/out                                               */
+  const int32_t* new_slots;  /* [B, Hkv, q_len] physical slots the appended tokens go to           */
+  int32_t*    victim_slots;  /* [B, Hkv, evict] out: physical slots freed (may alias new_slots)    */
+  int32_t*    victim_lidx;   /* [B, Hkv, evict] out: the reference's eviction ids, ascending       */
+  void*       scratch;       /* chunk path only: >= ekv_scratch_bytes() bytes, else NULL           */
+} ekv_layer_io;
+
+typedef struct ekv_shape {
+  int32_t dtype;     /* EKV_F16 | EKV_BF16 | EKV_F32                                              */
+  int32_t B, H, Hkv, d;
+  int32_t q_len;     /* 1 = decode step, >1 = strided prefill chunk (causal inside the chunk)     */
+  int32_t cap;       /* physical slots per (sequence, kv head)                                    */
+  int32_t n_before;  /* valid slots before this forward's append (same for all sequences/heads)   */
+  int32_t n_phys;    /* physical slots [0, n_phys) are streamed; must cover every valid/new slot  */
+} ekv_shape;
+
+int         ekv_abi_version(void);
+const char* ekv_last_error(void);
+
+/* Bytes of `scratch` a call with this shape needs (0 for decode). */
+int64_t ekv_scratch_bytes(const ekv_shape* shape);
+
+/* Fused forward for one layer: append -> QK^T/sqrt(d) -> softmax -> PV -> GQA fold ->
+ * policy accumulate -> budgeted victim select -> in-place eviction.
+ * Replaces: llama_patch.py:193-230 (cache append, repeat_kv, matmul, mask, softmax, matmul),
+ * easykv.py:188-196 (GQA fold), :288-300/:443-457 (accumulate), :303-362/:459-499 (select),
+ * :56-82 (KV compaction) and :315-333/:465-483 (state compaction). */
+int ekv_attend_evict(const ekv_shape* shape, const ekv_layer_io* io, const ekv_step* step, void* stream);
+
+/* Standalone select over existing state (no attention).  Same victim semantics as the fused
+ * call; used when attention ran elsewhere and by the unit tests.  `io` needs S, SQ, C, lidx,
+ * victim_slots, victim_lidx.  shape.q_len is ignored; n = shape.n_before valid slots.
+ * Replaces easykv.py:310-347 / :462-493 in isolation. */
+int ekv_select(const ekv_shape* shape, const ekv_layer_io* io, const ekv_step* step, void* stream);
+
+/* Evict an explicit victim list.  `victims` [B, Hkv, evict] holds logical ids (any order).
+ * Renumbers lidx, frees the slots and writes victim_slots.  Replaces truncate_kv_cache_silo /
+ * _liso / truncate_kv_cache (easykv.py:56-82,105-112) plus the matching state compaction. */
+int ekv_evict_explicit(const ekv_shape* shape, const ekv_layer_io* io, const int32_t* victims,
+                       int32_t evict, void* stream);
+
+/* Materialise the reference's arrival-ordered view: rows with lidx >= 0 are copied to
+ * K_out/V_out[B, Hkv, n, d] (and S/SQ/C_out[B, Hkv, n] if non-NULL) at index lidx.
+ * For export of a legacy `[layer][0|1] -> [B,Hkv,n,d]` cache (easykv.py:251,302) and parity. */
+int ekv_export_logical(const ekv_shape* shape, const ekv_layer_io* io, void* K_out, void* V_out,
+                       float* S_out, float* SQ_out, float* C_out, void* stream);
+
+/* Number of kernels launched by this library in the calling thread since load (bench.py's
+ * gpu_launches claim). */
+int64_t ekv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EASYKV_B200_H */
