@@ -1,0 +1,179 @@
+"""Device-resident budgeted KV cache of one model (all layers) and the per-forward call into the
+CUDA library.
+
+HBM layout per layer (include/easykv_b200.h): K, V `[B, Hkv, cap, d]` in *physical* slot order —
+rows never move; eviction frees a slot that the next appended token overwrites — plus fp32 policy
+state S, SQ, C `[B, Hkv, cap]` and the int32 map `lidx` physical slot -> logical (arrival-order)
+index that carries the reference's order-dependent semantics (protected last-10 / sink / recent
+windows, tie order, reported eviction ids).  torch is used for allocation and streams only.
+
+Replaces, together with the kernels: HF `DynamicCache.update` as called from
+easykv/llama_patch.py:193-196, `truncate_kv_cache_silo/_liso/truncate_kv_cache`
+(easykv/easykv.py:56-82,105-112) and the state tensors of easykv.py:242-247, :412-418.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .plan import StepParams
+
+_DTYPES = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BudgetedKVCache:
+    def __init__(self, num_layers, batch, num_heads, num_kv_heads, head_dim, capacity, dtype=torch.float16,
+                 device="cuda", arith=0):
+        if dtype not in _DTYPES:
+            raise ValueError(f"unsupported dtype {dtype}")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("easykv_b200 runs on CUDA devices only (no CPU path)")
+        self.lib = _lib.load()
+        self.L, self.B, self.H, self.Hkv, self.d, self.cap = num_layers, batch, num_heads, num_kv_heads, head_dim, capacity
+        self.dtype, self.device, self.arith = dtype, dev, arith
+        kv = dict(dtype=dtype, device=dev)
+        st = dict(dtype=torch.float32, device=dev)
+        self.K = [torch.zeros(batch, num_kv_heads, capacity, head_dim, **kv) for _ in range(num_layers)]
+        self.V = [torch.zeros(batch, num_kv_heads, capacity, head_dim, **kv) for _ in range(num_layers)]
+        self.S = [torch.zeros(batch, num_kv_heads, capacity, **st) for _ in range(num_layers)]
+        self.SQ = [torch.zeros(batch, num_kv_heads, capacity, **st) for _ in range(num_layers)]
+        self.Cn = [torch.zeros(batch, num_kv_heads, capacity, **st) for _ in range(num_layers)]
+        self.lidx = [torch.full((batch, num_kv_heads, capacity), -1, dtype=torch.int32, device=dev)
+                     for _ in range(num_layers)]
+        self.n = [0] * num_layers          # valid slots
+        self.n_phys = [0] * num_layers     # streamed physical extent
+        self.free = [None] * num_layers    # int32 [B, Hkv, f]: free physical slots inside [0, n_phys)
+        self.scratch = None
+
+    # ------------------------------------------------------------------------------------------
+    def _shape(self, l, q_len):
+        return _lib.Shape(dtype=_DTYPES[self.dtype], B=self.B, H=self.H, Hkv=self.Hkv, d=self.d, q_len=q_len,
+                          cap=self.cap, n_before=self.n[l], n_phys=self.n_phys[l])
+
+    def _io(self, l, **kw):
+        io = _lib.LayerIO(K=_ptr(self.K[l]), V=_ptr(self.V[l]), S=_ptr(self.S[l]), SQ=_ptr(self.SQ[l]),
+                          C=_ptr(self.Cn[l]), lidx=_ptr(self.lidx[l]))
+        for k, v in kw.items():
+            setattr(io, k, _ptr(v))
+        return io
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def free_count(self, l):
+        return 0 if self.free[l] is None else self.free[l].shape[-1]
+
+    # ------------------------------------------------------------------------------------------
+    def load_prefill(self, l, K, V, n_scored=None, C_init=None):
+        """Start layer `l` from a densely prefilled cache K, V `[B, Hkv, n, d]` (or `[Hkv, n, d]`).
+        Policy state is zero; C of the last `n_scored` slots is `C_init` (sequence of length
+        n_scored) or zero."""
+        if K.dim() == 3:
+            K, V = K[None], V[None]
+        n = K.shape[2]
+        if n > self.cap:
+            raise ValueError(f"prefill of {n} slots exceeds capacity {self.cap}")
+        self.K[l][:, :, :n].copy_(K)
+        self.V[l][:, :, :n].copy_(V)
+        self.S[l].zero_(); self.SQ[l].zero_(); self.Cn[l].zero_()
+        if C_init is not None and len(C_init):
+            c = torch.as_tensor(C_init, dtype=torch.float32, device=self.device)
+            self.Cn[l][:, :, n - c.numel():n] = c
+        self.lidx[l].fill_(-1)
+        self.lidx[l][:, :, :n] = torch.arange(n, dtype=torch.int32, device=self.device)
+        self.n[l] = self.n_phys[l] = n
+        self.free[l] = None
+
+    def step(self, l, sp: StepParams, q, k_new, v_new, apply=True, kernel=0):
+        """One forward of layer `l`: q `[B, H, q_len, d]`, k_new / v_new `[B, Hkv, q_len, d]`
+        (post-RoPE).  Returns (out `[B, H, q_len, d]`, victim_lidx `[B, Hkv, evict]` int32 or None).
+        With `apply=False` the victims are only reported (the caller may `evict()` others)."""
+        q_len = q.shape[2]
+        q, k_new, v_new = q.contiguous(), k_new.contiguous(), v_new.contiguous()
+        if self.free_count(l) > q_len or 0 < self.free_count(l) < q_len:
+            self.defragment(l)
+        new_slots = self.free[l] if self.free_count(l) == q_len else None
+        if new_slots is None and self.n_phys[l] + q_len > self.cap:
+            raise ValueError(f"cache capacity {self.cap} exceeded")
+        out = torch.empty_like(q)
+        evict = int(sp.evict)
+        vs = vl = None
+        if evict:
+            vs = torch.empty(self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
+            vl = torch.empty(self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
+        shape = self._shape(l, q_len)
+        cstep = sp.to_c(apply=apply, arith=self.arith)
+        need = self.lib.ekv_scratch_bytes(C.byref(shape), C.byref(cstep))
+        if need and (self.scratch is None or self.scratch.numel() < need):
+            self.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        io = self._io(l, q=q, k_new=k_new, v_new=v_new, out=out, new_slots=new_slots, victim_slots=vs,
+                      victim_lidx=vl, scratch=self.scratch if need else None)
+        _lib.check(self.lib.ekv_attend_evict(C.byref(shape), C.byref(io), C.byref(cstep), kernel, self._stream()))
+        self.n[l] += q_len
+        if new_slots is None:
+            self.n_phys[l] += q_len
+        self.free[l] = None
+        if evict and apply:
+            self.n[l] -= evict
+            self.free[l] = vs
+        return out, vl
+
+    def evict(self, l, victims):
+        """Delete logical ids `victims` `[B, Hkv, e]` (what truncate_kv_cache_* did)."""
+        victims = victims.to(device=self.device, dtype=torch.int32).contiguous()
+        if victims.dim() == 2:
+            victims = victims[None]
+        e = victims.shape[-1]
+        vs = torch.empty(self.B, self.Hkv, e, dtype=torch.int32, device=self.device)
+        shape = self._shape(l, 0)
+        io = self._io(l, victim_slots=vs)
+        _lib.check(self.lib.ekv_evict_explicit(C.byref(shape), C.byref(io), _ptr(victims), e, self._stream()))
+        self.n[l] -= e
+        self.free[l] = vs if self.free[l] is None else torch.cat([self.free[l], vs], dim=-1)
+
+    def select(self, l, sp: StepParams, apply=False):
+        """Victims for the current state without a forward (ekv_select)."""
+        evict = int(sp.evict)
+        vs = torch.empty(self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
+        vl = torch.empty(self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
+        shape = self._shape(l, 0)
+        cstep = sp.to_c(apply=apply, arith=self.arith)
+        io = self._io(l, victim_slots=vs, victim_lidx=vl)
+        _lib.check(self.lib.ekv_select(C.byref(shape), C.byref(io), C.byref(cstep), self._stream()))
+        if apply:
+            self.n[l] -= evict
+            self.free[l] = vs if self.free[l] is None else torch.cat([self.free[l], vs], dim=-1)
+        return vl
+
+    def export(self, l, with_state=False):
+        """K, V `[B, Hkv, n, d]` in the reference's logical (arrival) order."""
+        n = self.n[l]
+        Ko = torch.empty(self.B, self.Hkv, n, self.d, dtype=self.dtype, device=self.device)
+        Vo = torch.empty_like(Ko)
+        st = [torch.empty(self.B, self.Hkv, n, dtype=torch.float32, device=self.device) for _ in range(3)] if with_state else [None] * 3
+        shape = self._shape(l, 0)
+        io = self._io(l)
+        _lib.check(self.lib.ekv_export_logical(C.byref(shape), C.byref(io), _ptr(Ko), _ptr(Vo), _ptr(st[0]),
+                                               _ptr(st[1]), _ptr(st[2]), self._stream()))
+        return (Ko, Vo, *st) if with_state else (Ko, Vo)
+
+    def defragment(self, l):
+        """Make the physical layout dense again (valid slots at [0, n) in logical order).  Used at
+        mode transitions (e.g. after the strided phase of encoding_decoding leaves stride-1 free
+        slots that a one-token-per-step decode loop would otherwise stream forever)."""
+        n = self.n[l]
+        Ko, Vo, S, SQ, Cn = self.export(l, with_state=True)
+        self.K[l][:, :, :n].copy_(Ko); self.V[l][:, :, :n].copy_(Vo)
+        self.S[l][:, :, :n].copy_(S); self.SQ[l][:, :, :n].copy_(SQ); self.Cn[l][:, :, :n].copy_(Cn)
+        self.lidx[l].fill_(-1)
+        self.lidx[l][:, :, :n] = torch.arange(n, dtype=torch.int32, device=self.device)
+        self.n_phys[l] = n
+        self.free[l] = None

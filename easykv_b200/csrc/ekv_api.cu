@@ -1,0 +1,158 @@
+// extern "C" boundary of libeasykv_b200.so (see include/easykv_b200.h).  Validation, dispatch and
+// error reporting only; no allocation, no synchronisation, no global mutable state besides the
+// launch counter and the thread-local error string.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+
+#include "ekv_kernels.h"
+
+namespace ekv {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int set_cuda_error(const char* what, cudaError_t err) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(err));
+  return EKV_ERR_CUDA;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int build_args(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, KernelArgs& a) {
+  if (!sh || !io) return set_error(EKV_ERR_INVALID, "null shape/io");
+  if (sh->B <= 0 || sh->H <= 0 || sh->Hkv <= 0 || sh->d <= 0 || sh->cap <= 0)
+    return set_error(EKV_ERR_INVALID, "non-positive dimension (B=%d H=%d Hkv=%d d=%d cap=%d)", sh->B, sh->H, sh->Hkv, sh->d, sh->cap);
+  if (sh->H % sh->Hkv) return set_error(EKV_ERR_INVALID, "H=%d is not a multiple of Hkv=%d", sh->H, sh->Hkv);
+  if (sh->dtype != EKV_F16 && sh->dtype != EKV_BF16 && sh->dtype != EKV_F32) return set_error(EKV_ERR_INVALID, "dtype %d", sh->dtype);
+  if (sh->n_before < 0 || sh->n_phys < sh->n_before || sh->n_phys > sh->cap)
+    return set_error(EKV_ERR_INVALID, "need 0 <= n_before (%d) <= n_phys (%d) <= cap (%d)", sh->n_before, sh->n_phys, sh->cap);
+  a.q = io->q; a.k_new = io->k_new; a.v_new = io->v_new; a.out = io->out;
+  a.K = io->K; a.V = io->V; a.S = io->S; a.SQ = io->SQ; a.C = io->C; a.lidx = io->lidx;
+  a.new_slots = io->new_slots; a.victim_slots = io->victim_slots; a.victim_lidx = io->victim_lidx; a.scratch = io->scratch;
+  a.dtype = sh->dtype; a.B = sh->B; a.H = sh->H; a.Hkv = sh->Hkv; a.d = sh->d; a.q_len = sh->q_len; a.cap = sh->cap;
+  a.n_before = sh->n_before; a.n_phys = sh->n_phys;
+  a.scale_div = (float)std::sqrt((double)sh->d);
+  a.scale_mul = 1.0f / a.scale_div;
+  if (st) a.st = *st;
+  else {
+    a.st = ekv_step{};
+    a.st.policy = EKV_POLICY_NONE;
+  }
+  return EKV_OK;
+}
+
+// the reference would raise / mis-index on these (SURVEY A.5 "Edge"); here they are errors
+static int check_step(const KernelArgs& a, int n_after) {
+  const ekv_step& s = a.st;
+  if (s.policy < EKV_POLICY_NONE || s.policy > EKV_POLICY_RANGE) return set_error(EKV_ERR_INVALID, "policy %d", s.policy);
+  if (s.evict < 0) return set_error(EKV_ERR_INVALID, "evict %d", s.evict);
+  if (s.evict == 0 || s.policy == EKV_POLICY_NONE) return EKV_OK;
+  const int n_s = n_after - s.score_offset;
+  if (n_s <= 0) return set_error(EKV_ERR_INVALID, "no scored slots (n=%d, score_offset=%d)", n_after, s.score_offset);
+  if (s.policy == EKV_POLICY_ROCO) {
+    if (s.k_feasible < s.evict || s.k_feasible > n_s)
+      return set_error(EKV_ERR_INVALID, "roco: need evict (%d) <= k_feasible (%d) <= scored slots (%d)", s.evict, s.k_feasible, n_s);
+  } else if (s.policy == EKV_POLICY_H2O || s.policy == EKV_POLICY_TOVA) {
+    if (n_s - s.win_recent - s.win_lo < s.evict)
+      return set_error(EKV_ERR_INVALID, "window [%d, %d) holds fewer than %d candidates", s.win_lo, n_s - s.win_recent, s.evict);
+  } else if (s.policy == EKV_POLICY_RANGE) {
+    if (s.range_start < 0 || s.range_start + s.evict > n_s)
+      return set_error(EKV_ERR_INVALID, "range [%d, %d) outside the %d scored slots", s.range_start, s.range_start + s.evict, n_s);
+  }
+  if (s.evict > 0 && (!a.victim_lidx || !a.victim_slots)) return set_error(EKV_ERR_INVALID, "victim_slots / victim_lidx are required when evict > 0");
+  return EKV_OK;
+}
+
+}  // namespace ekv
+
+using namespace ekv;
+
+extern "C" {
+
+int ekv_abi_version(void) { return EKV_ABI_VERSION; }
+const char* ekv_last_error(void) { return g_err; }
+int64_t ekv_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+int64_t ekv_scratch_bytes(const ekv_shape* sh, const ekv_step* st) {
+  if (!sh || !st || !st->tova_head_mean || st->policy != EKV_POLICY_TOVA) return 0;
+  return (int64_t)sh->B * sh->Hkv * (sh->n_before + sh->q_len) * 4;
+}
+
+int ekv_attend_evict(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, int32_t kernel, void* stream) {
+  KernelArgs a;
+  int rc = build_args(sh, io, st, a);
+  if (rc) return rc;
+  if (sh->q_len < 1) return set_error(EKV_ERR_INVALID, "q_len %d", sh->q_len);
+  if (!io->q || !io->k_new || !io->v_new || !io->out || !io->K || !io->V || !io->S || !io->SQ || !io->C || !io->lidx)
+    return set_error(EKV_ERR_INVALID, "null tensor pointer");
+  if (!io->new_slots && sh->n_phys + sh->q_len > sh->cap)
+    return set_error(EKV_ERR_INVALID, "appending %d rows at %d overflows cap %d", sh->q_len, sh->n_phys, sh->cap);
+  rc = check_step(a, sh->n_before + sh->q_len);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool defer = a.st.policy == EKV_POLICY_TOVA && a.st.tova_head_mean && a.st.accumulate;
+  if (defer) {
+    // per-head accumulate inside the fused kernel, then the cross-head mean, then the select
+    if (!io->scratch) return set_error(EKV_ERR_INVALID, "tova_head_mean needs scratch (ekv_scratch_bytes)");
+    const ekv_step full = a.st;
+    a.st.evict = 0;
+    rc = launch_general(a, s);
+    if (rc) return rc;
+    KernelArgs b = a;
+    b.n_before = sh->n_before + sh->q_len;
+    b.n_phys = io->new_slots ? sh->n_phys : sh->n_phys + sh->q_len;
+    b.q_len = 0;
+    b.new_slots = nullptr;
+    b.st = full;
+    rc = launch_tova_head_mean(b, s);
+    if (rc || full.evict == 0) return rc;
+    return launch_select(b, s);
+  }
+  if (kernel == 0 && sh->q_len == 1) {
+    rc = launch_decode(a, s);
+    if (rc != EKV_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_general(a, s);
+}
+
+int ekv_select(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, void* stream) {
+  KernelArgs a;
+  int rc = build_args(sh, io, st, a);
+  if (rc) return rc;
+  if (!st) return set_error(EKV_ERR_INVALID, "null step");
+  if (!io->S || !io->SQ || !io->C || !io->lidx) return set_error(EKV_ERR_INVALID, "null tensor pointer");
+  a.q_len = 0;
+  a.new_slots = nullptr;
+  rc = check_step(a, sh->n_before);
+  if (rc) return rc;
+  return launch_select(a, (cudaStream_t)stream);
+}
+
+int ekv_evict_explicit(const ekv_shape* sh, const ekv_layer_io* io, const int32_t* victims, int32_t evict, void* stream) {
+  KernelArgs a;
+  int rc = build_args(sh, io, nullptr, a);
+  if (rc) return rc;
+  if (!io->lidx || (evict > 0 && !victims)) return set_error(EKV_ERR_INVALID, "null tensor pointer");
+  if (evict < 0 || evict > sh->n_before) return set_error(EKV_ERR_INVALID, "evict %d of %d", evict, sh->n_before);
+  return launch_evict_explicit(a, victims, evict, (cudaStream_t)stream);
+}
+
+int ekv_export_logical(const ekv_shape* sh, const ekv_layer_io* io, void* K_out, void* V_out, float* S_out,
+                       float* SQ_out, float* C_out, void* stream) {
+  KernelArgs a;
+  int rc = build_args(sh, io, nullptr, a);
+  if (rc) return rc;
+  if (!io->K || !io->V || !io->lidx || !K_out || !V_out) return set_error(EKV_ERR_INVALID, "null tensor pointer");
+  if ((S_out && !io->S) || (SQ_out && !io->SQ) || (C_out && !io->C)) return set_error(EKV_ERR_INVALID, "state export without state");
+  return launch_export(a, K_out, V_out, S_out, SQ_out, C_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

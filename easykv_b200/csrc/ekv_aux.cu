@@ -1,0 +1,179 @@
+// Stand-alone pieces of the path: select over existing state, explicit eviction, tova's
+// cross-head mean, and the export of the reference's arrival-ordered view.
+#include "ekv_select.cuh"
+#include "ekv_kernels.h"
+
+namespace ekv {
+
+constexpr int AUX_NT = 256;
+
+struct AuxSmem {
+  int off_lj, off_pool, total;
+  __host__ __device__ AuxSmem(int NE, int evict) {
+    off_lj = 0;
+    off_pool = ((NE * 4 + 15) / 16 * 16 + 127) / 128 * 128;
+    total = off_pool + (int)SelScratch::bytes(NE, evict);
+  }
+};
+
+// ---- ekv_select: easykv.py:310-347 / :462-493 in isolation ---------------------------------------
+__global__ void __launch_bounds__(AUX_NT) select_kernel(const KernelArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int unit = blockIdx.x;
+  const AuxSmem L(a.n_phys, a.st.evict);
+  SelScratch sc;
+  sc.lj = reinterpret_cast<int32_t*>(smem + L.off_lj);
+  sc.carve(smem + L.off_pool, a.n_phys, a.st.evict);
+  UnitState u;
+  u.S = a.S + (size_t)unit * a.cap; u.SQ = a.SQ + (size_t)unit * a.cap; u.C = a.C + (size_t)unit * a.cap;
+  u.lidx = a.lidx + (size_t)unit * a.cap;
+  u.new_slots = nullptr;
+  u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
+  u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
+  const Grp grp{(int)threadIdx.x, AUX_NT, 0};
+  ekv_step st = a.st;
+  st.accumulate = 0;
+  auto none = [](int, float& ds, float& dsq) { ds = 0.f; dsq = 0.f; };
+  state_select_apply(st, u, a.n_before, a.n_phys, 0, false, none, sc, grp);
+}
+
+int launch_select(const KernelArgs& a, cudaStream_t stream) {
+  const AuxSmem L(a.n_phys, a.st.evict);
+  if (L.total > 227 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "select: %d bytes of shared memory needed", L.total);
+  static thread_local int configured[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t err;
+  if (dev < 16 && !configured[dev]) {
+    err = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(select)", err);
+    configured[dev] = 1;
+  }
+  select_kernel<<<a.B * a.Hkv, AUX_NT, L.total, stream>>>(a);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("select_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+// ---- explicit eviction: truncate_kv_cache_silo/_liso/truncate_kv_cache (easykv.py:56-82,105-112) ---
+__global__ void __launch_bounds__(AUX_NT) evict_explicit_kernel(const KernelArgs a, const int32_t* victims, int evict) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  int32_t* vsorted = reinterpret_cast<int32_t*>(smem);          // [evict]
+  const int unit = blockIdx.x, tid = threadIdx.x;
+  const int32_t* vin = victims + (size_t)unit * evict;
+  int32_t* lidx = a.lidx + (size_t)unit * a.cap;
+  for (int t = tid; t < evict; t += AUX_NT) {
+    const int l = vin[t];
+    int rank = 0;
+    for (int k = 0; k < evict; ++k) rank += vin[k] < l;
+    vsorted[rank] = l;
+  }
+  __syncthreads();
+  for (int e = tid; e < a.n_phys; e += AUX_NT) {
+    const int l = lidx[e];
+    if (l < 0) continue;
+    int lo = 0, hi = evict;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (vsorted[mid] < l) lo = mid + 1; else hi = mid; }
+    if (lo < evict && vsorted[lo] == l) {
+      lidx[e] = -1;
+      if (a.victim_slots) a.victim_slots[(size_t)unit * evict + lo] = e;
+      if (a.victim_lidx) a.victim_lidx[(size_t)unit * evict + lo] = l;
+    } else if (lo > 0) {
+      lidx[e] = l - lo;
+    }
+  }
+}
+
+int launch_evict_explicit(const KernelArgs& a, const int32_t* victims, int evict, cudaStream_t stream) {
+  if (evict <= 0) return EKV_OK;
+  if (evict * 4 > 48 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "evict_explicit: too many victims (%d)", evict);
+  evict_explicit_kernel<<<a.B * a.Hkv, AUX_NT, evict * 4, stream>>>(a, victims, evict);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("evict_explicit_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+// ---- tova in 'encoding'/'ppl': S = mean over KV heads of the last row's folded probabilities ----------
+// (easykv.py:454-457, :845-848).  Logical index l lives in a different physical slot in every head, so
+// the per-head values are first laid out by logical index in `scratch` [B, Hkv, n] fp32.
+__global__ void tova_gather_kernel(const KernelArgs a, int n) {
+  const int unit = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_phys) return;
+  const int l = a.lidx[(size_t)unit * a.cap + e];
+  if (l >= 0 && l < n) reinterpret_cast<float*>(a.scratch)[(size_t)unit * n + l] = a.S[(size_t)unit * a.cap + e];
+}
+template <typename T> __global__ void tova_mean_scatter_kernel(const KernelArgs a, int n) {
+  const int unit = blockIdx.y, b = unit / a.Hkv;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_phys) return;
+  const int l = a.lidx[(size_t)unit * a.cap + e];
+  if (l < 0 || l >= n) return;
+  const float* tmp = reinterpret_cast<const float*>(a.scratch) + (size_t)b * a.Hkv * n + l;
+  float s = 0.f;
+  for (int hh = 0; hh < a.Hkv; ++hh) s += tmp[(size_t)hh * n];
+  a.S[(size_t)unit * a.cap + e] = Tr<T>::round_f(__fmul_rn(s, 1.0f / (float)a.Hkv));   // fp16 mean over heads
+}
+
+int launch_tova_head_mean(const KernelArgs& a, cudaStream_t stream) {
+  const int n = a.n_before;     // valid slots (the caller passes the post-append count)
+  dim3 grid((a.n_phys + 255) / 256, a.B * a.Hkv);
+  tova_gather_kernel<<<grid, 256, 0, stream>>>(a, n);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("tova_gather_kernel launch", err);
+  count_launch();
+  switch (a.dtype) {
+    case EKV_F16: tova_mean_scatter_kernel<__half><<<grid, 256, 0, stream>>>(a, n); break;
+    case EKV_BF16: tova_mean_scatter_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a, n); break;
+    default: tova_mean_scatter_kernel<float><<<grid, 256, 0, stream>>>(a, n); break;
+  }
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("tova_mean_scatter_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+// ---- export of the arrival-ordered view -----------------------------------------------------------------
+template <typename T>
+__global__ void export_kernel(const KernelArgs a, T* K_out, T* V_out, float* S_out, float* SQ_out, float* C_out) {
+  const int unit = blockIdx.y, n = a.n_before, D = a.d;
+  const int rows_per_block = blockDim.x / 16;                 // 16 threads per row
+  const int e = blockIdx.x * rows_per_block + threadIdx.x / 16;
+  if (e >= a.n_phys) return;
+  const int l = a.lidx[(size_t)unit * a.cap + e];
+  if (l < 0 || l >= n) return;
+  const int t16 = threadIdx.x % 16;
+  const T* ks = reinterpret_cast<const T*>(a.K) + ((size_t)unit * a.cap + e) * D;
+  const T* vs = reinterpret_cast<const T*>(a.V) + ((size_t)unit * a.cap + e) * D;
+  T* kd = K_out + ((size_t)unit * n + l) * D;
+  T* vd = V_out + ((size_t)unit * n + l) * D;
+  for (int c = t16; c < D; c += 16) { kd[c] = ks[c]; vd[c] = vs[c]; }
+  if (t16 == 0) {
+    if (S_out) S_out[(size_t)unit * n + l] = a.S[(size_t)unit * a.cap + e];
+    if (SQ_out) SQ_out[(size_t)unit * n + l] = a.SQ[(size_t)unit * a.cap + e];
+    if (C_out) C_out[(size_t)unit * n + l] = a.C[(size_t)unit * a.cap + e];
+  }
+}
+
+int launch_export(const KernelArgs& a, void* K_out, void* V_out, float* S_out, float* SQ_out, float* C_out,
+                  cudaStream_t stream) {
+  if (a.n_phys <= 0) return EKV_OK;
+  dim3 grid((a.n_phys + 15) / 16, a.B * a.Hkv);
+  switch (a.dtype) {
+    case EKV_F16:
+      export_kernel<__half><<<grid, 256, 0, stream>>>(a, (__half*)K_out, (__half*)V_out, S_out, SQ_out, C_out); break;
+    case EKV_BF16:
+      export_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a, (__nv_bfloat16*)K_out, (__nv_bfloat16*)V_out, S_out, SQ_out, C_out); break;
+    case EKV_F32:
+      export_kernel<float><<<grid, 256, 0, stream>>>(a, (float*)K_out, (float*)V_out, S_out, SQ_out, C_out); break;
+    default: return set_error(EKV_ERR_INVALID, "dtype %d", a.dtype);
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("export_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+}  // namespace ekv

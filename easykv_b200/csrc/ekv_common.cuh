@@ -125,6 +125,62 @@ __device__ __forceinline__ uint32_t order_key(float x) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// a subset of the CTA's warps synchronising on a named barrier (the TMA producer warp of the
+// decode kernel never joins the consumers' barriers)
+struct Grp {
+  int tid, n, bar;
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory");
+  }
+};
+
+// 8 consecutive-dimension elements owned by lane `l16` of a 16-lane group reading one row of
+// D=128 elements: 16-bit types own dims [8*l16, 8*l16+8) (one 128-bit access); fp32 owns
+// [4*l16, 4*l16+4) and [64+4*l16, 64+4*l16+4) (two 128-bit accesses, each conflict-free).
+template <typename T> __device__ __forceinline__ int dim_of(int l16, int i) {
+  if (sizeof(T) == 2) return 8 * l16 + i;
+  return (i < 4) ? 4 * l16 + i : 64 + 4 * l16 + (i - 4);
+}
+template <typename T> __device__ __forceinline__ void load_row8(const T* row, int l16, float (&x)[8]);
+template <> __device__ __forceinline__ void load_row8<__half>(const __half* row, int l16, float (&x)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(row + 8 * l16);
+  float2 a = Tr<__half>::to_f2(u.x), b = Tr<__half>::to_f2(u.y), c = Tr<__half>::to_f2(u.z), d = Tr<__half>::to_f2(u.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+template <> __device__ __forceinline__ void load_row8<__nv_bfloat16>(const __nv_bfloat16* row, int l16, float (&x)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(row + 8 * l16);
+  float2 a = Tr<__nv_bfloat16>::to_f2(u.x), b = Tr<__nv_bfloat16>::to_f2(u.y), c = Tr<__nv_bfloat16>::to_f2(u.z),
+         d = Tr<__nv_bfloat16>::to_f2(u.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+template <> __device__ __forceinline__ void load_row8<float>(const float* row, int l16, float (&x)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(row + 4 * l16);
+  float4 b = *reinterpret_cast<const float4*>(row + 64 + 4 * l16);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void store_row8(T* row, int l16, const float (&x)[8]);
+template <> __device__ __forceinline__ void store_row8<__half>(__half* row, int l16, const float (&x)[8]) {
+  __half2 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+  *reinterpret_cast<uint4*>(row + 8 * l16) = *reinterpret_cast<uint4*>(h);
+}
+template <> __device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloat16* row, int l16, const float (&x)[8]) {
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+  *reinterpret_cast<uint4*>(row + 8 * l16) = *reinterpret_cast<uint4*>(h);
+}
+template <> __device__ __forceinline__ void store_row8<float>(float* row, int l16, const float (&x)[8]) {
+  *reinterpret_cast<float4*>(row + 4 * l16) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(row + 64 + 4 * l16) = make_float4(x[4], x[5], x[6], x[7]);
+}
+
+template <typename T> __device__ __forceinline__ T neg_inf();
+template <> __device__ __forceinline__ __half neg_inf<__half>() { return __ushort_as_half(0xfc00); }
+template <> __device__ __forceinline__ __nv_bfloat16 neg_inf<__nv_bfloat16>() { return __ushort_as_bfloat16(0xff80); }
+template <> __device__ __forceinline__ float neg_inf<float>() { return __uint_as_float(0xff800000u); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -1,0 +1,35 @@
+// Internal: flattened kernel arguments + launcher prototypes shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/easykv_b200.h"
+
+namespace ekv {
+
+struct KernelArgs {
+  // ekv_layer_io
+  const void* q; const void* k_new; const void* v_new; void* out;
+  void* K; void* V; float* S; float* SQ; float* C; int32_t* lidx;
+  const int32_t* new_slots; int32_t* victim_slots; int32_t* victim_lidx; void* scratch;
+  // ekv_shape
+  int32_t dtype, B, H, Hkv, d, q_len, cap, n_before, n_phys;
+  // derived
+  float scale_div;   // (float)sqrt(d)
+  float scale_mul;   // 1.0f / scale_div
+  ekv_step st;
+};
+
+int set_cuda_error(const char* what, cudaError_t err);
+int set_error(int code, const char* fmt, ...);
+void count_launch();
+
+int launch_decode(const KernelArgs& a, cudaStream_t stream);      // ekv_decode.cu
+int launch_general(const KernelArgs& a, cudaStream_t stream);     // ekv_chunk.cu
+int launch_select(const KernelArgs& a, cudaStream_t stream);      // ekv_aux.cu
+int launch_tova_head_mean(const KernelArgs& a, cudaStream_t stream);
+int launch_evict_explicit(const KernelArgs& a, const int32_t* victims, int evict, cudaStream_t stream);
+int launch_export(const KernelArgs& a, void* K_out, void* V_out, float* S_out, float* SQ_out, float* C_out,
+                  cudaStream_t stream);
+
+}  // namespace ekv

@@ -26,7 +26,7 @@
  *   easykv/easykv.py:56-82); here eviction renumbers `lidx` and the next token overwrites the
  *   victim's physical slot.  K is cached post-RoPE (easykv/llama_patch.py:190-196) so attention
  *   is invariant to physical order.  K/V buffers must be initialised (e.g. zeros): free slots
- *   are streamed and masked, never skipped.
+ *   inside [0, n_phys) are streamed and masked, never skipped.
  */
 #ifndef EASYKV_B200_H
 #define EASYKV_B200_H
@@ -37,7 +37,13 @@
 extern "C" {
 #endif
 
-#define EKV_ABI_VERSION 1
+#define EKV_ABI_VERSION 2
+
+#if defined(__GNUC__)
+#define EKV_API __attribute__((visibility("default")))
+#else
+#define EKV_API
+#endif
 
 enum { EKV_F16 = 0, EKV_BF16 = 1, EKV_F32 = 2 };
 
@@ -59,14 +65,15 @@ enum {
 };
 
 /* What the reference's mode loops (easykv.py:257-363, 426-500, 587-748, 816-892) decide for ONE
- * forward.  Field-for-field the same as oracle/restate.py:Step. */
+ * forward. */
 typedef struct ekv_step {
   int32_t policy;        /* EKV_POLICY_*                                                          */
   int32_t accumulate;    /* update S/SQ from this forward's probabilities (easykv.py:443)          */
   int32_t evict;         /* victims per (sequence, kv head): 0, 1 (decode) or stride (chunk)       */
   int32_t apply;         /* 1: perform the eviction in place; 0: only report the victims           */
   int32_t score_offset;  /* 'decoding' mode: the first P logical slots carry no state (:294,:324)  */
-  float   counter_add;   /* C += counter_add on scored slots before select (:304,:460,:708)        */
+  float   counter_add;   /* C += counter_add on scored slots before select (:304,:460,:708);
+                            applied only when evict > 0                                           */
   float   c_new0;        /* C of the i-th appended slot = c_new0 - i*c_new_step (:244-245,:416,:469)*/
   float   c_new_step;
   int32_t k_feasible;    /* roco: size of the low-std candidate set (:322,:474)                    */
@@ -75,8 +82,11 @@ typedef struct ekv_step {
   int32_t win_lo;        /* h2o/tova: candidates are state[win_lo : n_s - win_recent] (:311,:463)  */
   int32_t win_recent;
   int32_t range_start;   /* RANGE: first logical index (relative to score_offset) to evict         */
-  int32_t scale_mode;    /* 0: logits / sqrt(d) (ATen CPU);  1: logits * (1/sqrt(d)) (ATen CUDA)   */
-  int32_t reserved;
+  int32_t arith;         /* which ATen kernels' arithmetic to reproduce at the two places they
+                            differ: 0 = CPU (logits / sqrt(d); exp * (1/sum)),
+                                    1 = CUDA (logits * (1/sqrt(d)); exp / sum)                    */
+  int32_t tova_head_mean;/* tova in 'encoding'/'ppl': state = mean over KV heads of the last
+                            query row, broadcast to all heads (:454-457,:845-848)                 */
 } ekv_step;
 
 /* One layer's tensors for one forward.  Replaces the body of llama_forward / mistral_forward
@@ -93,10 +103,12 @@ typedef struct ekv_layer_io {
   float*      SQ;
   float*      C;
   int32_t*    lidx;     /* [B, Hkv, cap]      in/out                                               */
-  const int32_t* new_slots;  /* [B, Hkv, q_len] physical slots the appended tokens go to           */
-  int32_t*    victim_slots;  /* [B, Hkv, evict] out: physical slots freed (may alias new_slots)    */
+  const int32_t* new_slots;  /* [B, Hkv, q_len] physical slots the appended tokens go to; they must
+                                be free (lidx == -1 or >= n_phys).  NULL: slot n_phys + i.          */
+  int32_t*    victim_slots;  /* [B, Hkv, evict] out: physical slots freed (may alias new_slots),
+                                ordered like victim_lidx                                          */
   int32_t*    victim_lidx;   /* [B, Hkv, evict] out: the reference's eviction ids, ascending       */
-  void*       scratch;       /* chunk path only: >= ekv_scratch_bytes() bytes, else NULL           */
+  void*       scratch;       /* >= ekv_scratch_bytes() bytes (only tova_head_mean needs any)       */
 } ekv_layer_io;
 
 typedef struct ekv_shape {
@@ -105,43 +117,49 @@ typedef struct ekv_shape {
   int32_t q_len;     /* 1 = decode step, >1 = strided prefill chunk (causal inside the chunk)     */
   int32_t cap;       /* physical slots per (sequence, kv head)                                    */
   int32_t n_before;  /* valid slots before this forward's append (same for all sequences/heads)   */
-  int32_t n_phys;    /* physical slots [0, n_phys) are streamed; must cover every valid/new slot  */
+  int32_t n_phys;    /* physical slots [0, n_phys) hold every valid slot and are streamed         */
 } ekv_shape;
 
-int         ekv_abi_version(void);
-const char* ekv_last_error(void);
+EKV_API int         ekv_abi_version(void);
+EKV_API const char* ekv_last_error(void);
 
-/* Bytes of `scratch` a call with this shape needs (0 for decode). */
-int64_t ekv_scratch_bytes(const ekv_shape* shape);
+/* Bytes of `scratch` a call with this shape/step needs (0 unless step->tova_head_mean). */
+EKV_API int64_t ekv_scratch_bytes(const ekv_shape* shape, const ekv_step* step);
 
 /* Fused forward for one layer: append -> QK^T/sqrt(d) -> softmax -> PV -> GQA fold ->
  * policy accumulate -> budgeted victim select -> in-place eviction.
  * Replaces: llama_patch.py:193-230 (cache append, repeat_kv, matmul, mask, softmax, matmul),
  * easykv.py:188-196 (GQA fold), :288-300/:443-457 (accumulate), :303-362/:459-499 (select),
- * :56-82 (KV compaction) and :315-333/:465-483 (state compaction). */
-int ekv_attend_evict(const ekv_shape* shape, const ekv_layer_io* io, const ekv_step* step, void* stream);
+ * :56-82 (KV compaction) and :315-333/:465-483 (state compaction).
+ * `kernel`: 0 = automatic (the TMA-pipelined decode kernel when q_len == 1 and the shape is
+ * supported, else the general kernel); 1 = force the general kernel. */
+EKV_API int ekv_attend_evict(const ekv_shape* shape, const ekv_layer_io* io, const ekv_step* step,
+                     int32_t kernel, void* stream);
 
-/* Standalone select over existing state (no attention).  Same victim semantics as the fused
- * call; used when attention ran elsewhere and by the unit tests.  `io` needs S, SQ, C, lidx,
- * victim_slots, victim_lidx.  shape.q_len is ignored; n = shape.n_before valid slots.
+/* Standalone select over existing state (no attention, no append).  Same victim semantics as
+ * the fused call (step->accumulate is ignored, counter_add IS applied); used when attention ran
+ * elsewhere and by the unit tests.  `io` needs S, SQ, C, lidx, victim_slots, victim_lidx.
+ * n = shape.n_before valid slots inside [0, n_phys); shape.q_len is ignored.
  * Replaces easykv.py:310-347 / :462-493 in isolation. */
-int ekv_select(const ekv_shape* shape, const ekv_layer_io* io, const ekv_step* step, void* stream);
+EKV_API int ekv_select(const ekv_shape* shape, const ekv_layer_io* io, const ekv_step* step, void* stream);
 
-/* Evict an explicit victim list.  `victims` [B, Hkv, evict] holds logical ids (any order).
- * Renumbers lidx, frees the slots and writes victim_slots.  Replaces truncate_kv_cache_silo /
- * _liso / truncate_kv_cache (easykv.py:56-82,105-112) plus the matching state compaction. */
-int ekv_evict_explicit(const ekv_shape* shape, const ekv_layer_io* io, const int32_t* victims,
+/* Evict an explicit victim list.  `victims` [B, Hkv, evict] holds logical ids (any order, no
+ * duplicates).  Renumbers lidx, frees the slots and writes victim_slots / victim_lidx
+ * (ascending).  Replaces truncate_kv_cache_silo / _liso / truncate_kv_cache
+ * (easykv.py:56-82,105-112) plus the matching state compaction. */
+EKV_API int ekv_evict_explicit(const ekv_shape* shape, const ekv_layer_io* io, const int32_t* victims,
                        int32_t evict, void* stream);
 
 /* Materialise the reference's arrival-ordered view: rows with lidx >= 0 are copied to
- * K_out/V_out[B, Hkv, n, d] (and S/SQ/C_out[B, Hkv, n] if non-NULL) at index lidx.
- * For export of a legacy `[layer][0|1] -> [B,Hkv,n,d]` cache (easykv.py:251,302) and parity. */
-int ekv_export_logical(const ekv_shape* shape, const ekv_layer_io* io, void* K_out, void* V_out,
+ * K_out/V_out[B, Hkv, n, d] (and S/SQ/C_out[B, Hkv, n] if non-NULL) at index lidx
+ * (n = shape.n_before).  For export of a legacy `[layer][0|1] -> [B,Hkv,n,d]` cache
+ * (easykv.py:251,302), for re-densifying the physical layout, and for parity checks. */
+EKV_API int ekv_export_logical(const ekv_shape* shape, const ekv_layer_io* io, void* K_out, void* V_out,
                        float* S_out, float* SQ_out, float* C_out, void* stream);
 
-/* Number of kernels launched by this library in the calling thread since load (bench.py's
+/* Number of kernels launched by this library in the calling process since load (bench.py's
  * gpu_launches claim). */
-int64_t ekv_launch_count(void);
+EKV_API int64_t ekv_launch_count(void);
 
 #ifdef __cplusplus
 }

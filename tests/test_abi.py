@@ -1,0 +1,50 @@
+"""The C-ABI library builds, loads, and exports exactly what include/easykv_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "easykv_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ekv_[a-z_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(ekv_lib):
+    from easykv_b200 import _lib
+    names = _declared()
+    assert set(names) == set(_lib.EXPORTS)
+    for n in names:
+        assert getattr(ekv_lib, n) is not None
+
+
+def test_abi_version_and_struct_layout(ekv_lib):
+    from easykv_b200 import _lib
+    assert ekv_lib.ekv_abi_version() == _lib.ABI_VERSION
+    assert ctypes.sizeof(_lib.Step) == 16 * 4
+    assert ctypes.sizeof(_lib.Shape) == 9 * 4
+    assert ctypes.sizeof(_lib.LayerIO) == 14 * 8
+
+
+def test_argument_validation_without_gpu(ekv_lib):
+    """Bad shapes are rejected before any CUDA call (reference: ValueError, llama_patch.py:204-228)."""
+    from easykv_b200 import _lib
+    sh = _lib.Shape(dtype=_lib.F16, B=1, H=6, Hkv=4, d=128, q_len=1, cap=16, n_before=0, n_phys=0)
+    io = _lib.LayerIO()
+    st = _lib.Step()
+    assert ekv_lib.ekv_attend_evict(ctypes.byref(sh), ctypes.byref(io), ctypes.byref(st), 0, None) == _lib.ERR_INVALID
+    assert b"multiple" in ekv_lib.ekv_last_error()
+    sh.H = 4
+    sh.n_phys = 32
+    assert ekv_lib.ekv_select(ctypes.byref(sh), ctypes.byref(io), ctypes.byref(st), None) == _lib.ERR_INVALID
+    assert ekv_lib.ekv_launch_count() == 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "easykv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("test oracle", ""), f
