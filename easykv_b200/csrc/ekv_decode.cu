@@ -204,9 +204,10 @@ decode_kernel(const KernelArgs a) {
       }
     }
   }
-  // the appended token's own key (the reference attends it: llama_patch.py:193-196)
-  if (hw == 0) {
-    float v[G < 16 ? (G < 1 ? 1 : G) : 16];
+  // the appended token's own key (the reference attends it: llama_patch.py:193-196).  Every
+  // half-warp computes it (the shuffles need all 32 lanes); half-warp 0 stores it.
+  {
+    float v[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       float acc = 0.f;
@@ -215,7 +216,7 @@ decode_kernel(const KernelArgs a) {
       v[g] = acc;
     }
     const float r = transpose_reduce16<G>(v, l16);
-    if (l16 < G) plog[bitrev_idx<G>(l16) * nep + n_phys] = finish_logit(r, true);
+    if (hw == 0 && l16 < G) plog[bitrev_idx<G>(l16) * nep + n_phys] = finish_logit(r, true);
   }
   grp.sync();
 
