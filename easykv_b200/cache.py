@@ -177,3 +177,55 @@ class BudgetedKVCache:
         self.lidx[l][:, :, :n] = torch.arange(n, dtype=torch.int32, device=self.device)
         self.n_phys[l] = n
         self.free[l] = None
+
+
+class SteadyDecode:
+    """The steady-state decode step of `encoding_decoding` / `decoding` (easykv.py:670-748, :257-363
+    once the budget is reached): every step appends one token per sequence and evicts one per
+    (sequence, layer, kv head), so shapes never change.  All C-ABI arguments are built once; the
+    per-layer victim buffer of step t is the new-slot buffer of step t+1 (no host round trip), and the
+    whole L-layer step can be captured into one CUDA graph."""
+
+    def __init__(self, cache: BudgetedKVCache, sp: StepParams, q, k_new, v_new, out=None):
+        """q `[L, B, H, 1, d]`, k_new / v_new `[L, B, Hkv, 1, d]`: device buffers the caller refills
+        before each `run()` (e.g. the projections' outputs)."""
+        assert sp.evict == 1
+        c = self.cache = cache
+        self.q, self.k_new, self.v_new = q, k_new, v_new
+        self.out = torch.empty_like(q) if out is None else out
+        self.victim_lidx = torch.empty(c.L, c.B, c.Hkv, 1, dtype=torch.int32, device=c.device)
+        self.slots = torch.empty(c.L, c.B, c.Hkv, 1, dtype=torch.int32, device=c.device)
+        self.cstep = sp.to_c(apply=True, arith=c.arith)
+        self.calls = []
+        for l in range(c.L):
+            if c.free_count(l) != 1:
+                # bring the layer into the steady state: one append-mode evicting step
+                o, _ = c.step(l, sp, q[l], k_new[l], v_new[l])
+                self.out[l].copy_(o)
+            self.slots[l].copy_(c.free[l])
+            c.free[l] = self.slots[l]
+            shape = c._shape(l, 1)
+            io = c._io(l, q=q[l], k_new=k_new[l], v_new=v_new[l], out=self.out[l], new_slots=self.slots[l],
+                       victim_slots=self.slots[l], victim_lidx=self.victim_lidx[l])
+            self.calls.append((shape, io))
+        self.graph = None
+
+    def run(self, stream=None):
+        lib, cs = self.cache.lib, self.cstep
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        for shape, io in self.calls:
+            rc = lib.ekv_attend_evict(C.byref(shape), C.byref(io), C.byref(cs), 0, s)
+            if rc:
+                _lib.check(rc)
+
+    def capture(self):
+        """Capture one whole step (L launches) into a CUDA graph; `replay()` then costs one launch."""
+        self.run()                                   # warm: function attributes are set outside capture
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.run()
+        return self
+
+    def replay(self):
+        self.graph.replay()
