@@ -36,6 +36,7 @@ class BudgetedKVCache:
         if dev.type != "cuda":
             raise RuntimeError("easykv_b200 runs on CUDA devices only (no CPU path)")
         self.lib = _lib.load()
+        capacity = (int(capacity) + 7) // 8 * 8      # 16-byte aligned per-head rows of the int32/fp32 arrays
         self.L, self.B, self.H, self.Hkv, self.d, self.cap = num_layers, batch, num_heads, num_kv_heads, head_dim, capacity
         self.dtype, self.device, self.arith = dtype, dev, arith
         kv = dict(dtype=dtype, device=dev)

@@ -24,6 +24,8 @@ int set_cuda_error(const char* what, cudaError_t err) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(err));
   return EKV_ERR_CUDA;
 }
+static std::atomic<unsigned long long*> g_timeline{nullptr};
+unsigned long long* debug_timeline() { return g_timeline.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static int build_args(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, KernelArgs& a) {
@@ -41,6 +43,7 @@ static int build_args(const ekv_shape* sh, const ekv_layer_io* io, const ekv_ste
   a.n_before = sh->n_before; a.n_phys = sh->n_phys;
   a.scale_div = (float)std::sqrt((double)sh->d);
   a.scale_mul = 1.0f / a.scale_div;
+  a.timeline = debug_timeline();
   if (st) a.st = *st;
   else {
     a.st = ekv_step{};
@@ -80,6 +83,7 @@ extern "C" {
 int ekv_abi_version(void) { return EKV_ABI_VERSION; }
 const char* ekv_last_error(void) { return g_err; }
 int64_t ekv_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+void ekv_debug_set_timeline(void* device_buffer) { g_timeline.store((unsigned long long*)device_buffer, std::memory_order_relaxed); }
 
 int64_t ekv_scratch_bytes(const ekv_shape* sh, const ekv_step* st) {
   if (!sh || !st || !st->tova_head_mean || st->policy != EKV_POLICY_TOVA) return 0;

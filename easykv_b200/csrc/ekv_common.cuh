@@ -89,6 +89,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Ampere-style per-thread async copies (SASS LDGSTS) for the small per-unit headers
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // thread-block cluster primitives (DSMEM)
 // ---------------------------------------------------------------------------------------
@@ -174,6 +186,76 @@ template <> __device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloa
 template <> __device__ __forceinline__ void store_row8<float>(float* row, int l16, const float (&x)[8]) {
   *reinterpret_cast<float4*>(row + 4 * l16) = make_float4(x[0], x[1], x[2], x[3]);
   *reinterpret_cast<float4*>(row + 64 + 4 * l16) = make_float4(x[4], x[5], x[6], x[7]);
+}
+
+// ---------------------------------------------------------------------------------------
+// Row8<T>: the 8 elements of a D=128 row owned by one lane of a 16-lane group, kept in the
+// storage format.  16-bit types are never converted: the products go through the sm_100
+// mixed-precision FMA (PTX fma.rn.f32.f16 / .bf16 -> SASS FHFMA with .H0/.H1 operand selectors),
+// which multiplies two 16-bit values exactly and adds into fp32 with one rounding — bit-identical
+// to fmaf(float(a), float(b), c) at a third of the instructions.
+// ---------------------------------------------------------------------------------------
+template <typename T> struct Row8;
+template <> struct Row8<float> {
+  float x[8];
+  __device__ __forceinline__ void load(const float* row, int l16) { load_row8<float>(row, l16, x); }
+};
+template <> struct Row8<__half> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __half* row, int l16) { u = *reinterpret_cast<const uint4*>(row + 8 * l16); }
+};
+template <> struct Row8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* row, int l16) { u = *reinterpret_cast<const uint4*>(row + 8 * l16); }
+};
+__device__ __forceinline__ float fma2_f16(uint32_t a, uint32_t b, float acc) {      // acc += a.lo*b.lo; acc += a.hi*b.hi
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.f16 %0, al, bl, %0;\n\tfma.rn.f32.f16 %0, ah, bh, %0;\n\t}" : "+f"(acc) : "r"(a), "r"(b));
+  return acc;
+}
+__device__ __forceinline__ float fma2_bf16(uint32_t a, uint32_t b, float acc) {
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %0, ah, bh, %0;\n\t}" : "+f"(acc) : "r"(a), "r"(b));
+  return acc;
+}
+__device__ __forceinline__ void axpy2_f16(uint16_t p, uint32_t v, float& o0, float& o1) {   // o0 += p*v.lo; o1 += p*v.hi
+  asm("{\n\t.reg .b16 vl, vh;\n\tmov.b32 {vl, vh}, %3;\n\t"
+      "fma.rn.f32.f16 %0, %2, vl, %0;\n\tfma.rn.f32.f16 %1, %2, vh, %1;\n\t}" : "+f"(o0), "+f"(o1) : "h"(p), "r"(v));
+}
+__device__ __forceinline__ void axpy2_bf16(uint16_t p, uint32_t v, float& o0, float& o1) {
+  asm("{\n\t.reg .b16 vl, vh;\n\tmov.b32 {vl, vh}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, %2, vl, %0;\n\tfma.rn.f32.bf16 %1, %2, vh, %1;\n\t}" : "+f"(o0), "+f"(o1) : "h"(p), "r"(v));
+}
+// dot of two lanes' 8 elements, accumulated sequentially j = 0..7 into acc
+__device__ __forceinline__ float dot8(const Row8<float>& a, const Row8<float>& b, float acc) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc = fmaf(a.x[j], b.x[j], acc);
+  return acc;
+}
+__device__ __forceinline__ float dot8(const Row8<__half>& a, const Row8<__half>& b, float acc) {
+  acc = fma2_f16(a.u.x, b.u.x, acc); acc = fma2_f16(a.u.y, b.u.y, acc);
+  acc = fma2_f16(a.u.z, b.u.z, acc); acc = fma2_f16(a.u.w, b.u.w, acc);
+  return acc;
+}
+__device__ __forceinline__ float dot8(const Row8<__nv_bfloat16>& a, const Row8<__nv_bfloat16>& b, float acc) {
+  acc = fma2_bf16(a.u.x, b.u.x, acc); acc = fma2_bf16(a.u.y, b.u.y, acc);
+  acc = fma2_bf16(a.u.z, b.u.z, acc); acc = fma2_bf16(a.u.w, b.u.w, acc);
+  return acc;
+}
+// o[j] += p * v[j] with p a model-dtype probability
+__device__ __forceinline__ void axpy8(float p, const Row8<float>& v, float (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(p, v.x[j], o[j]);
+}
+__device__ __forceinline__ void axpy8(__half p, const Row8<__half>& v, float (&o)[8]) {
+  const uint16_t pb = __half_as_ushort(p);
+  axpy2_f16(pb, v.u.x, o[0], o[1]); axpy2_f16(pb, v.u.y, o[2], o[3]);
+  axpy2_f16(pb, v.u.z, o[4], o[5]); axpy2_f16(pb, v.u.w, o[6], o[7]);
+}
+__device__ __forceinline__ void axpy8(__nv_bfloat16 p, const Row8<__nv_bfloat16>& v, float (&o)[8]) {
+  const uint16_t pb = __bfloat16_as_ushort(p);
+  axpy2_bf16(pb, v.u.x, o[0], o[1]); axpy2_bf16(pb, v.u.y, o[2], o[3]);
+  axpy2_bf16(pb, v.u.z, o[4], o[5]); axpy2_bf16(pb, v.u.w, o[6], o[7]);
 }
 
 template <typename T> __device__ __forceinline__ T neg_inf();

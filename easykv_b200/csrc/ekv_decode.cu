@@ -1,16 +1,23 @@
-// Fused decode step (q_len == 1) for one layer: one CTA per (sequence, kv head).
+// Fused decode step (q_len == 1) for one layer.  One persistent, warp-specialised CTA per SM that
+// loops over (sequence, kv head) units:
 //
-//   TMA producer warp : streams the head's K rows, then its V rows, HBM -> shared memory, as 8 KB
-//                       cp.async.bulk tiles through a STAGES-deep mbarrier ring (each K/V byte is
-//                       read from HBM exactly once; the g query heads of a GQA group share it).
-//   4 consumer warps  : K phase  — 16 lanes per row, 128-bit shared-memory reads, fp32 FMA dot
-//                                  products, transposing warp-shuffle reduction, logits rounded
-//                                  at the reference's rounding points;
+//   TMA producer warp : streams each unit's K rows, then its V rows, HBM -> shared memory, as 16 KB
+//                       cp.async.bulk tiles through one deep mbarrier ring (all shared memory that the
+//                       consumers do not need: ~11 tiles = 176 KB in flight per SM).  The stream is
+//                       continuous across unit boundaries.  Each K/V byte is read from HBM exactly
+//                       once; the g query heads of a GQA group share the stream.
+//   2 consumer groups : of 8 warps each, alternating units (ping-pong): while one group runs the
+//                       select tail of unit k, the other already consumes the tiles of unit k+1, so the
+//                       tail never idles HBM.  Per unit a group does
+//                       header   — q, the new K/V row, the slot map -> shared memory (while idle);
+//                       K phase  — 16 lanes per row, 128-bit shared-memory reads, fp32 FMA dot
+//                                  products, transposing warp-shuffle reduction, logits rounded and
+//                                  masked at the reference's rounding points;
 //                       softmax  — fp32, warp-shuffle + named-barrier reductions, probabilities
 //                                  rounded to the model dtype;
 //                       V phase  — fp32 FMA accumulate of p·V, cross-warp reduction, out;
-//                       tail     — GQA fold, policy accumulate, victim select, in-place
-//                                  eviction (ekv_select.cuh) and the append of the new K/V row.
+//                       tail     — GQA fold, policy accumulate, victim select, in-place eviction
+//                                  (ekv_select.cuh) and the append of the new K/V row.
 //
 // Replaces (reference paths): llama_patch.py:193-230 / mistral_patch.py:137-170 (cache append,
 // repeat_kv, QK^T, mask, softmax, PV) and easykv.py:271-362 / :683-748 (fold, accumulate, select,
@@ -22,14 +29,15 @@ namespace ekv {
 
 template <typename T> struct DecodeCfg {
   static constexpr int D = 128;
-  static constexpr int NWARP = 4;                       // consumer warps
+  static constexpr int NWARP = 8;                       // consumer warps per group
   static constexpr int NCONS = NWARP * 32;
-  static constexpr int NTHREADS = NCONS + 32;           // + the TMA producer warp
+  static constexpr int NGROUPS = 2;
+  static constexpr int NTHREADS = NGROUPS * NCONS + 32; // + the TMA producer warp (the last warp)
   static constexpr int ROW_BYTES = D * (int)sizeof(T);
-  static constexpr int TILE_BYTES = 8192;
-  static constexpr int TILE_ROWS = TILE_BYTES / ROW_BYTES;   // 32 (16-bit) / 16 (fp32)
+  static constexpr int TILE_BYTES = 16384;
+  static constexpr int TILE_ROWS = TILE_BYTES / ROW_BYTES;   // 64 (16-bit) / 32 (fp32)
   static constexpr int RPT = TILE_ROWS / (NWARP * 2);        // rows per 16-lane group per tile
-  static constexpr int STAGES = 4;
+  static constexpr int MAX_STAGES = 12;
 };
 
 // sum over the 16 lanes of a half-warp of NV per-lane values; afterwards lane l (< NV) of the
@@ -60,313 +68,402 @@ template <int NV> __device__ __forceinline__ int bitrev_idx(int l) {
   return r;
 }
 
+
+static inline __host__ __device__ int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
 template <typename T> struct DecodeSmem {
-  // byte offsets inside dynamic shared memory
-  int off_bar, off_q, off_red, off_ns, off_lj, off_plog, off_pool, total;
-  int nep;   // padded entries per head in plog
-  __host__ __device__ DecodeSmem(int G, int n_phys, int evict) {
+  // byte offsets inside dynamic shared memory; g_* are relative to a consumer group's block
+  int off_bar, off_grp, grp_bytes, g_red, g_q, g_k, g_v, g_ns, g_lj, g_plog, g_scr, off_ring, fixed, nep;
+  __host__ __device__ DecodeSmem(int G, int n_phys, int evict, int ngroups) {
     using Cfg = DecodeCfg<T>;
     const int NE = n_phys + 1;
-    nep = (NE + 7) / 8 * 8;
+    nep = align_up(NE, 8);
     int o = 0;
-    off_bar = o; o += 2 * Cfg::STAGES * 8;
-    off_q = o; o += G * Cfg::D * 4;
-    off_red = o; o += 8 * Cfg::NWARP * 4 * 2;
-    off_ns = o; o += 16;
-    off_lj = o; o += (NE * 4 + 15) / 16 * 16;
-    off_plog = o; o += (G * nep * (int)sizeof(T) + 15) / 16 * 16;
-    o = (o + 127) / 128 * 128;
-    off_pool = o;
-    size_t pool = (size_t)Cfg::STAGES * Cfg::TILE_BYTES;
-    size_t sel = SelScratch::bytes(NE, evict);
-    size_t outp = (size_t)Cfg::NWARP * 2 * G * Cfg::D * 4;
-    if (sel > pool) pool = sel;
-    if (outp > pool) pool = outp;
-    total = o + (int)pool;
+    off_bar = o; o += (Cfg::NGROUPS + 1) * Cfg::MAX_STAGES * 8;   // full[group][stage], empty[stage]
+    o = align_up(o, 128);
+    off_grp = o;
+    int h = 0;
+    g_red = h; h += 2 * 8 * Cfg::NWARP * 4;
+    g_q = h; h += G * Cfg::D * (int)sizeof(T);
+    g_k = h; h += Cfg::ROW_BYTES;
+    g_v = h; h += Cfg::ROW_BYTES;
+    g_ns = h; h += 16;
+    g_lj = h; h += align_up(NE * 4, 16);
+    g_plog = h; h += align_up(G * nep * (int)sizeof(T), 16);
+    h = align_up(h, 128);
+    g_scr = h;
+    size_t scr = SelScratch::bytes(NE, evict);
+    size_t outp = (size_t)Cfg::NWARP * G * Cfg::D * 4;
+    h += (int)(scr > outp ? scr : outp);
+    grp_bytes = align_up(h, 128);
+    o += ngroups * grp_bytes;
+    off_ring = o;
+    fixed = o;
   }
 };
 
 template <typename T, int G>
-__global__ void __launch_bounds__(DecodeCfg<T>::NTHREADS)
-decode_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(DecodeCfg<T>::NTHREADS, 1)
+decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
   using Cfg = DecodeCfg<T>;
-  constexpr int D = Cfg::D, NWARP = Cfg::NWARP, NCONS = Cfg::NCONS, RPT = Cfg::RPT, STAGES = Cfg::STAGES;
+  constexpr int D = Cfg::D, NWARP = Cfg::NWARP, NCONS = Cfg::NCONS, RPT = Cfg::RPT;
   constexpr int TILE_ROWS = Cfg::TILE_ROWS;
   extern __shared__ __align__(128) unsigned char smem[];
-  const DecodeSmem<T> L(G, a.n_phys, a.st.evict);
+  const DecodeSmem<T> L(G, a.n_phys, a.st.evict, ngroups);
+  // full[g][s]: tile in ring slot s has landed, signalled to the consumer group g that owns the tile —
+  // one barrier per (group, slot) so that each waiter tracks the phase of a barrier only it consumes
+  // (a parity wait must never run ahead of the barrier's previous phase); empty[s]: slot s released.
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-  uint64_t* empty = full + STAGES;
-  float* qs = reinterpret_cast<float*>(smem + L.off_q);
-  float* red = reinterpret_cast<float*>(smem + L.off_red);
-  int32_t* ns = reinterpret_cast<int32_t*>(smem + L.off_ns);
-  int32_t* lj = reinterpret_cast<int32_t*>(smem + L.off_lj);
-  T* plog = reinterpret_cast<T*>(smem + L.off_plog);
-  unsigned char* pool = smem + L.off_pool;
+  uint64_t* empty = full + Cfg::NGROUPS * Cfg::MAX_STAGES;
+  unsigned char* ring = smem + L.off_ring;
 
-  const int unit = blockIdx.x;                 // b * Hkv + h
+  const int U = a.B * a.Hkv;
   const int n_phys = a.n_phys, NE = n_phys + 1, nep = L.nep;
   const int nt = (n_phys + TILE_ROWS - 1) / TILE_ROWS;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const T* Kg = reinterpret_cast<const T*>(a.K) + (size_t)unit * a.cap * D;
-  const T* Vg = reinterpret_cast<const T*>(a.V) + (size_t)unit * a.cap * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      for (int g = 0; g < Cfg::NGROUPS; ++g) mbar_init(&full[g * Cfg::MAX_STAGES + s], 1);
+      mbar_init(&empty[s], NWARP);
+    }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == NWARP) {
-    // ===== TMA producer ======================================================================
+  if (warp == Cfg::NGROUPS * NWARP) {
+    // ===== TMA producer: one continuous tile stream over all of this CTA's units ======================
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
-      for (int t = 0; t < 2 * nt; ++t) {
-        const int s = t % STAGES, use = t / STAGES;
-        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-        const int tt = t < nt ? t : t - nt;
-        const int rows = min(TILE_ROWS, n_phys - tt * TILE_ROWS);
-        const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
-        const T* src = (t < nt ? Kg : Vg) + (size_t)tt * TILE_ROWS * D;
-        mbar_arrive_expect_tx(&full[s], bytes);
-        tma_bulk_g2s(pool + (size_t)s * Cfg::TILE_BYTES, src, bytes, &full[s], pol);
+      int t = 0;                                   // tile counter of this CTA
+      int k_unit = 0;
+      for (int unit = blockIdx.x; unit < U; unit += gridDim.x, ++k_unit) {
+        uint64_t* gfull = full + (k_unit % ngroups) * Cfg::MAX_STAGES;
+        const T* Kg = reinterpret_cast<const T*>(a.K) + (size_t)unit * a.cap * D;
+        const T* Vg = reinterpret_cast<const T*>(a.V) + (size_t)unit * a.cap * D;
+        for (int i = 0; i < 2 * nt; ++i, ++t) {
+          const int s = t % stages, use = t / stages;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          const int tt = i < nt ? i : i - nt;
+          const int rows = min(TILE_ROWS, n_phys - tt * TILE_ROWS);
+          const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
+          const T* src = (i < nt ? Kg : Vg) + (size_t)tt * TILE_ROWS * D;
+          mbar_arrive_expect_tx(&gfull[s], bytes);
+          tma_bulk_g2s(ring + (size_t)s * Cfg::TILE_BYTES, src, bytes, &gfull[s], pol);
+        }
       }
     }
     return;
   }
 
   // ===== consumers ===============================================================================
-  const Grp grp{tid, NCONS, 1};
-  const int hw = tid >> 4, l16 = tid & 15;      // 8 half-warps
-  const size_t unit_q = (size_t)unit * G * D;   // q/out: [B, H, 1, D] with H = Hkv * G
-  const size_t unit_kv = (size_t)unit * D;      // k_new/v_new: [B, Hkv, 1, D]
-
-  // stage q (fp32), lidx, the new slot; preload the new token's K/V chunk
-  {
-    const T* qg = reinterpret_cast<const T*>(a.q) + unit_q;
-    for (int i = tid; i < G * D; i += NCONS) qs[i] = Tr<T>::to_f(qg[i]);
-    const int32_t* lg = a.lidx + (size_t)unit * a.cap;
-    for (int e = tid; e < n_phys; e += NCONS) lj[e] = lg[e];
-    if (tid == 0) {
-      ns[0] = a.new_slots ? a.new_slots[unit] : n_phys;
-      lj[n_phys] = a.n_before;
-    }
-  }
-  float knew[8], vnew[8];
-  load_row8<T>(reinterpret_cast<const T*>(a.k_new) + unit_kv, l16, knew);
-  load_row8<T>(reinterpret_cast<const T*>(a.v_new) + unit_kv, l16, vnew);
-  grp.sync();
-  float qr[G][8];
-#pragma unroll
-  for (int g = 0; g < G; ++g)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qr[g][i] = qs[g * D + dim_of<T>(l16, i)];
+  const int gid = warp / NWARP;                 // consumer group
+  if (gid >= ngroups) return;
+  const int tid = threadIdx.x - gid * NCONS, gw = warp - gid * NWARP;
+  const Grp grp{tid, NCONS, 1 + gid};
+  const int hw = tid >> 4, l16 = tid & 15;      // 16 half-warps per group
+  unsigned char* gb = smem + L.off_grp + gid * L.grp_bytes;
+  float* red = reinterpret_cast<float*>(gb + L.g_red);
+  T* qh = reinterpret_cast<T*>(gb + L.g_q);
+  T* kh = reinterpret_cast<T*>(gb + L.g_k);
+  T* vh = reinterpret_cast<T*>(gb + L.g_v);
+  int32_t* ns = reinterpret_cast<int32_t*>(gb + L.g_ns);
+  int32_t* lj = reinterpret_cast<int32_t*>(gb + L.g_lj);
+  T* plog = reinterpret_cast<T*>(gb + L.g_plog);
+  unsigned char* scr = gb + L.g_scr;
 
   auto finish_logit = [&](float dot, bool valid) -> T {
     float x = Tr<T>::round_f(dot);                                           // llama_patch.py:201
     x = a.st.arith ? __fmul_rn(x, a.scale_mul) : __fdiv_rn(x, a.scale_div);  // :202
-    return valid ? Tr<T>::from_f(x) : neg_inf<T>();
+    return valid ? Tr<T>::from_f(x) : neg_inf<T>();                          // free slots are masked
   };
 
-  // ---- K phase ------------------------------------------------------------------------------------
-  constexpr int NVT = RPT * G;                       // values per half-warp per tile
-  constexpr int NV = NVT < 16 ? NVT : 16;            // values per transposing reduction
-  constexpr int NB = NVT / NV;
-  for (int t = 0; t < nt; ++t) {
-    const int s = t % STAGES;
-    mbar_wait(&full[s], (t / STAGES) & 1);
-    const T* tile = reinterpret_cast<const T*>(pool + (size_t)s * Cfg::TILE_BYTES);
-    float part[NVT];
-#pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      float x[8];
-      load_row8<T>(tile + (hw * RPT + k) * D, l16, x);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(x[i], qr[g][i], acc);
-        part[k * G + g] = acc;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      float v[NV];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = part[b * NV + i];
-      const float r = transpose_reduce16<NV>(v, l16);
-      if (l16 < NV) {
-        const int vi = b * NV + bitrev_idx<NV>(l16);
-        const int k = vi / G, g = vi % G;
-        const int e = t * TILE_ROWS + hw * RPT + k;
-        if (e < n_phys) plog[g * nep + e] = finish_logit(r, lj[e] >= 0);
-      }
-    }
+  // the k-th unit of this CTA is consumed by group k % ngroups; its tiles are [k*2nt, (k+1)*2nt)
+  uint64_t* gfull = full + gid * Cfg::MAX_STAGES;
+  uint32_t par = 0;                             // bit s: parity of this group's next wait on gfull[s]
+  int k_unit = gid;
+  unsigned long long* tl = a.timeline ? a.timeline + (size_t)blockIdx.x * 16 * 8 : nullptr;
+  auto stamp = [&](int k, int slot) {
+    if (tl && tid == 0 && k < 16) tl[k * 8 + slot] = clock64();
+  };
+  if (tl && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tl[15 * 8 + 7] = gt;
   }
-  // the appended token's own key (the reference attends it: llama_patch.py:193-196).  Every
-  // half-warp computes it (the shuffles need all 32 lanes); half-warp 0 stores it.
-  {
-    float v[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc = fmaf(knew[i], qr[g][i], acc);
-      v[g] = acc;
-    }
-    const float r = transpose_reduce16<G>(v, l16);
-    if (hw == 0 && l16 < G) plog[bitrev_idx<G>(l16) * nep + n_phys] = finish_logit(r, true);
-  }
-  grp.sync();
-
-  // ---- softmax (fp32 over the model-dtype logits; llama_patch.py:218-219) -------------------------
-  float mx[G], inv[G];
-  {
-    float m[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      m[g] = -INFINITY;
-      for (int e = tid; e < NE; e += NCONS) m[g] = fmaxf(m[g], Tr<T>::to_f(plog[g * nep + e]));
-      m[g] = warp_max(m[g]);
-      if (lane == 0) red[g * NWARP + warp] = m[g];
+  for (int unit = blockIdx.x + gid * gridDim.x; unit < U; unit += ngroups * gridDim.x, k_unit += ngroups) {
+    int t = k_unit * 2 * nt;
+    stamp(k_unit, 0);
+    // ---- header: q, new K/V row, slot map (this group is idle until its first tile lands) --------------
+    {
+      const uint4* qg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D);
+      const uint4* kg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_new) + (size_t)unit * D);
+      const uint4* vg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.v_new) + (size_t)unit * D);
+      constexpr int QCH = G * Cfg::ROW_BYTES / 16, RCH = Cfg::ROW_BYTES / 16;
+      for (int i = tid; i < QCH + 2 * RCH; i += NCONS) {
+        if (i < QCH) reinterpret_cast<uint4*>(qh)[i] = qg[i];
+        else if (i < QCH + RCH) reinterpret_cast<uint4*>(kh)[i - QCH] = kg[i - QCH];
+        else reinterpret_cast<uint4*>(vh)[i - QCH - RCH] = vg[i - QCH - RCH];
+      }
+      const int32_t* lg = a.lidx + (size_t)unit * a.cap;
+      for (int e = tid; e < n_phys; e += NCONS) lj[e] = lg[e];
+      if (tid == 0) {
+        ns[0] = a.new_slots ? a.new_slots[unit] : n_phys;
+        lj[n_phys] = a.n_before;
+      }
     }
     grp.sync();
+    stamp(k_unit, 1);
+    Row8<T> qr[G], knew;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float v = red[g * NWARP];
-#pragma unroll
-      for (int w = 1; w < NWARP; ++w) v = fmaxf(v, red[g * NWARP + w]);
-      mx[g] = v;
-    }
-    float* red2 = red + 8 * NWARP;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float sacc = 0.f;
-      for (int e = tid; e < NE; e += NCONS) sacc += expf(Tr<T>::to_f(plog[g * nep + e]) - mx[g]);
-      sacc = warp_sum(sacc);
-      if (lane == 0) red2[g * NWARP + warp] = sacc;
-    }
-    grp.sync();
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float v = red2[g * NWARP];
-#pragma unroll
-      for (int w = 1; w < NWARP; ++w) v += red2[g * NWARP + w];
-      inv[g] = a.st.arith ? v : __fdiv_rn(1.0f, v);
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      for (int e = tid; e < NE; e += NCONS) {
-        const float ex = expf(Tr<T>::to_f(plog[g * nep + e]) - mx[g]);
-        plog[g * nep + e] = Tr<T>::from_f(a.st.arith ? __fdiv_rn(ex, inv[g]) : __fmul_rn(ex, inv[g]));
-      }
-  }
-  grp.sync();
+    for (int g = 0; g < G; ++g) qr[g].load(qh + g * D, l16);
+    knew.load(kh, l16);
 
-  // ---- V phase ------------------------------------------------------------------------------------
-  float oacc[G][8];
+    // ---- K phase ----------------------------------------------------------------------------------
+    // Per tile a half-warp owns RPT rows -> NVT = RPT*G per-lane partial dots.  They are reduced across
+    // the 16 lanes 16 values at a time (over TB tiles when a tile yields fewer), so that afterwards
+    // every lane finishes exactly one logit.
+    constexpr int NVT = RPT * G;
+    constexpr int TB = NVT >= 16 ? 1 : 16 / NVT;       // tiles per batch
+    constexpr int NB = NVT >= 16 ? NVT / 16 : 1;       // 16-value reductions per batch
+    static_assert(NVT * TB == 16 * NB, "batch must be a whole number of 16-value reductions");
+    const int vi0 = bitrev_idx<16>(l16);               // value index this lane finishes in each reduction
+    float mloc = -INFINITY;                            // running max of the logits this lane stores
+    for (int i0 = 0; i0 < nt; i0 += TB) {
+      float part[NVT * TB];
 #pragma unroll
-  for (int g = 0; g < G; ++g)
+      for (int tb = 0; tb < TB; ++tb) {
+        if (i0 + tb < nt) {
+          const int s = t % stages;
+          mbar_wait(&gfull[s], (par >> s) & 1u);
+          par ^= 1u << s;
+          if (i0 + tb == 0) stamp(k_unit, 2);
+          const T* tile = reinterpret_cast<const T*>(ring + (size_t)s * Cfg::TILE_BYTES);
+          Row8<T> x[RPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) oacc[g][i] = 0.f;
-  for (int t = nt; t < 2 * nt; ++t) {
-    const int s = t % STAGES;
-    mbar_wait(&full[s], (t / STAGES) & 1);
-    const T* tile = reinterpret_cast<const T*>(pool + (size_t)s * Cfg::TILE_BYTES);
+          for (int k = 0; k < RPT; ++k) x[k].load(tile + (hw * RPT + k) * D, l16);
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      const int e = (t - nt) * TILE_ROWS + hw * RPT + k;
-      if (e < n_phys) {
-        float pv[G];
-        bool any = false;
+          for (int k = 0; k < RPT; ++k)
 #pragma unroll
-        for (int g = 0; g < G; ++g) { pv[g] = Tr<T>::to_f(plog[g * nep + e]); any |= pv[g] != 0.f; }
-        if (any) {
-          float x[8];
-          load_row8<T>(tile + (hw * RPT + k) * D, l16, x);
+            for (int g = 0; g < G; ++g) part[tb * NVT + k * G + g] = dot8(x[k], qr[g], 0.f);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+          ++t;
+        } else {
 #pragma unroll
-          for (int g = 0; g < G; ++g)
+          for (int j = 0; j < NVT; ++j) part[tb * NVT + j] = 0.f;
+        }
+      }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) oacc[g][i] = fmaf(pv[g], x[i], oacc[g][i]);
+      for (int b = 0; b < NB; ++b) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = part[b * 16 + j];
+        const float r = transpose_reduce16<16>(v, l16);
+        const int vi = b * 16 + vi0;                   // index into this batch's NVT*TB values
+        const int tb = vi / NVT, k = (vi % NVT) / G, g = vi % G;
+        const int e = (i0 + tb) * TILE_ROWS + hw * RPT + k;
+        if (e < n_phys) {
+          const T x = finish_logit(r, lj[e] >= 0);
+          plog[g * nep + e] = x;
+          mloc = fmaxf(mloc, Tr<T>::to_f(x));
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
-  if (hw == 0) {
+    // the appended token's own key (the reference attends it: llama_patch.py:193-196).  Every
+    // half-warp computes it (the shuffles need all 32 lanes); half-warp 0 stores it.
+    float xnew[G];
+    {
+      float v[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const float p = Tr<T>::to_f(plog[g * nep + n_phys]);
+      for (int g = 0; g < G; ++g) v[g] = dot8(knew, qr[g], 0.f);
+      const float r = transpose_reduce16<G>(v, l16);
+      const T x = finish_logit(r, true);          // lanes l16 < G: head bitrev_idx<G>(l16)
+      if (hw == 0 && l16 < G) plog[bitrev_idx<G>(l16) * nep + n_phys] = x;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) oacc[g][i] = fmaf(p, vnew[i], oacc[g][i]);
+      for (int g = 0; g < G; ++g)
+        xnew[g] = __shfl_sync(0xffffffffu, Tr<T>::to_f(x), (lane & 16) | bitrev_idx<G>(g));
     }
-  }
-  grp.sync();                                   // every stage buffer is consumed: the pool is free
-  {
-    float* part = reinterpret_cast<float*>(pool);          // [8 half-warps][G][D]
+
+    stamp(k_unit, 3);
+    // ---- softmax (fp32 over the model-dtype logits; llama_patch.py:210-219) ---------------------------
+    {
+      float mx[G], inv[G];
+      const int my_g = vi0 % G;                                  // head of the logits this lane stored
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float m = fmaxf(warp_max(my_g == g ? mloc : -INFINITY), xnew[g]);
+        if (lane == 0) red[g * NWARP + gw] = m;
+      }
+      grp.sync();
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float v = red[g * NWARP];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) v = fmaxf(v, red[g * NWARP + w]);
+        mx[g] = v;
+      }
+      float* red2 = red + 8 * NWARP;
+      float sacc[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) sacc[g] = 0.f;
+      for (int e = tid; e < NE; e += NCONS)
+#pragma unroll
+        for (int g = 0; g < G; ++g) sacc[g] += expf(Tr<T>::to_f(plog[g * nep + e]) - mx[g]);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        sacc[g] = warp_sum(sacc[g]);
+        if (lane == 0) red2[g * NWARP + gw] = sacc[g];
+      }
+      grp.sync();
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float v = red2[g * NWARP];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) v += red2[g * NWARP + w];
+        inv[g] = a.st.arith ? v : __fdiv_rn(1.0f, v);
+      }
+      for (int e = tid; e < NE; e += NCONS)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float ex = expf(Tr<T>::to_f(plog[g * nep + e]) - mx[g]);
+          plog[g * nep + e] = Tr<T>::from_f(a.st.arith ? __fdiv_rn(ex, inv[g]) : __fmul_rn(ex, inv[g]));
+        }
+    }
+    grp.sync();
+    stamp(k_unit, 4);
+
+    // ---- V phase ----------------------------------------------------------------------------------
+    float oacc[G][8];
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) part[(hw * G + g) * D + dim_of<T>(l16, i)] = oacc[g][i];
-    grp.sync();
-    T* og = reinterpret_cast<T*>(a.out) + unit_q;
-    for (int i = tid; i < G * D; i += NCONS) {
-      float v = part[i];
+      for (int j = 0; j < 8; ++j) oacc[g][j] = 0.f;
+    // free slots contribute p == 0 exactly; their rows are stale but finite (the cache buffers are
+    // zero-initialised and only ever hold rows that were valid), so no branch on p is needed
+    for (int i = 0; i < nt; ++i, ++t) {
+      const int s = t % stages;
+      mbar_wait(&gfull[s], (par >> s) & 1u);
+      par ^= 1u << s;
+      const T* tile = reinterpret_cast<const T*>(ring + (size_t)s * Cfg::TILE_BYTES);
+      const int e0 = i * TILE_ROWS + hw * RPT;
+      Row8<T> x[RPT];
+      T pv[RPT][G];
 #pragma unroll
-      for (int h = 1; h < NWARP * 2; ++h) v += part[h * G * D + i];
-      og[i] = Tr<T>::from_f(v);                                              // llama_patch.py:222
+      for (int k = 0; k < RPT; ++k) {
+        x[k].load(tile + (hw * RPT + k) * D, l16);
+#pragma unroll
+        for (int g = 0; g < G; ++g) pv[k][g] = plog[g * nep + min(e0 + k, n_phys)];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+      for (int k = 0; k < RPT; ++k)
+        if (e0 + k < n_phys) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) axpy8(pv[k][g], x[k], oacc[g]);
+        }
+    }
+    stamp(k_unit, 5);
+    if (hw == 0) {
+      Row8<T> vnew;
+      vnew.load(vh, l16);
+#pragma unroll
+      for (int g = 0; g < G; ++g) axpy8(plog[g * nep + n_phys], vnew, oacc[g]);
+    }
+    {
+      float* part = reinterpret_cast<float*>(scr);          // [NWARP][G][D]
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = oacc[g][j] + __shfl_xor_sync(0xffffffffu, oacc[g][j], 16);
+          if (lane < 16) part[(gw * G + g) * D + dim_of<T>(l16, j)] = v;
+        }
+      grp.sync();
+      T* og = reinterpret_cast<T*>(a.out) + (size_t)unit * G * D;
+      for (int i = tid; i < G * D; i += NCONS) {
+        float v = part[i];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) v += part[w * G * D + i];
+        og[i] = Tr<T>::from_f(v);                                              // llama_patch.py:222
+      }
     }
     grp.sync();
-  }
+    stamp(k_unit, 6);
 
-  // ---- tail: fold, accumulate, select, evict, append ------------------------------------------------
-  SelScratch sc;
-  sc.lj = lj;
-  sc.carve(pool, NE, a.st.evict);
-  UnitState u;
-  u.S = a.S + (size_t)unit * a.cap; u.SQ = a.SQ + (size_t)unit * a.cap; u.C = a.C + (size_t)unit * a.cap;
-  u.lidx = a.lidx + (size_t)unit * a.cap;
-  u.new_slots = ns;
-  u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
-  u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
-  const float inv_g = 1.0f / (float)G;
-  auto acc = [&](int e, float& ds, float& dsq) {
-    float pf;
-    if (G == 1) pf = Tr<T>::to_f(plog[e]);
-    else {                                                  // process_for_mqa_gqa, easykv.py:188-196
-      float sum = 0.f;
+    // ---- tail: fold, accumulate, select, evict, append ------------------------------------------------
+    SelScratch sc;
+    sc.lj = lj;
+    sc.carve(scr, NE, a.st.evict);
+    UnitState u;
+    u.S = a.S + (size_t)unit * a.cap; u.SQ = a.SQ + (size_t)unit * a.cap; u.C = a.C + (size_t)unit * a.cap;
+    u.lidx = a.lidx + (size_t)unit * a.cap;
+    u.new_slots = ns;
+    u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
+    u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
+    const float inv_g = 1.0f / (float)G;
+    auto acc = [&](int e, float& ds, float& dsq) {
+      float pf;
+      if (G == 1) pf = Tr<T>::to_f(plog[e]);
+      else {                                                  // process_for_mqa_gqa, easykv.py:188-196
+        float sum = 0.f;
 #pragma unroll
-      for (int g = 0; g < G; ++g) sum += Tr<T>::to_f(plog[g * nep + e]);
-      pf = Tr<T>::round_f(__fmul_rn(sum, inv_g));
+        for (int g = 0; g < G; ++g) sum += Tr<T>::to_f(plog[g * nep + e]);
+        pf = Tr<T>::round_f(__fmul_rn(sum, inv_g));
+      }
+      ds = pf;
+      dsq = Tr<T>::round_f(__fmul_rn(pf, pf));               // p**2 in the model dtype, easykv.py:296
+    };
+    // append the new row (this unit's K/V stream has been fully consumed)
+    if (hw == 0) {
+      const int slot = ns[0];
+      float x[8];
+      load_row8<T>(kh, l16, x);
+      store_row8<T>(reinterpret_cast<T*>(a.K) + ((size_t)unit * a.cap + slot) * D, l16, x);   // bit-exact round trip
+      load_row8<T>(vh, l16, x);
+      store_row8<T>(reinterpret_cast<T*>(a.V) + ((size_t)unit * a.cap + slot) * D, l16, x);
     }
-    ds = pf;
-    dsq = Tr<T>::round_f(__fmul_rn(pf, pf));               // p**2 in the model dtype, easykv.py:296
-  };
-  // append the new row (nobody reads K/V any more in this launch)
-  if (hw == 0) {
-    const int slot = ns[0];
-    store_row8<T>(reinterpret_cast<T*>(a.K) + ((size_t)unit * a.cap + slot) * D, l16, knew);
-    store_row8<T>(reinterpret_cast<T*>(a.V) + ((size_t)unit * a.cap + slot) * D, l16, vnew);
+    state_select_apply(a.st, u, a.n_before, n_phys, 1, /*lj_preloaded=*/true, acc, sc, grp);
+    grp.sync();                                   // the header / scratch are rewritten for the next unit
+    stamp(k_unit, 7);
   }
-  state_select_apply(a.st, u, a.n_before, n_phys, 1, /*lj_preloaded=*/true, acc, sc, grp);
 }
 
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int G> static int launch_decode_tg(const KernelArgs& a, cudaStream_t stream) {
-  const DecodeSmem<T> L(G, a.n_phys, a.st.evict);
-  if (L.total > 227 * 1024) return EKV_ERR_UNSUPPORTED;
+  using Cfg = DecodeCfg<T>;
+  static thread_local int sm_count[16] = {0};
   static thread_local int configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
   cudaError_t err;
-  if (dev < 16 && configured[dev] < L.total) {
-    err = cudaFuncSetAttribute(decode_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(decode)", err);
-    configured[dev] = 227 * 1024;
+  if (!sm_count[dev]) {
+    err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return set_cuda_error("cudaDeviceGetAttribute", err);
   }
-  decode_kernel<T, G><<<a.B * a.Hkv, DecodeCfg<T>::NTHREADS, L.total, stream>>>(a);
+  const int U = a.B * a.Hkv;
+  int grid = sm_count[dev] < U ? sm_count[dev] : U;
+  // two ping-pong consumer groups when a CTA gets more than one unit and both fit next to >= 4 ring stages
+  const int sm_total = 227 * 1024;
+  int ngroups = (U > grid) ? Cfg::NGROUPS : 1;
+  DecodeSmem<T> L(G, a.n_phys, a.st.evict, ngroups);
+  int stages = (sm_total - L.fixed) / Cfg::TILE_BYTES;
+  if (ngroups == 2 && stages < 4) {
+    ngroups = 1;
+    L = DecodeSmem<T>(G, a.n_phys, a.st.evict, 1);
+    stages = (sm_total - L.fixed) / Cfg::TILE_BYTES;
+  }
+  if (sm_total < L.fixed || stages < 2) return EKV_ERR_UNSUPPORTED;
+  if (stages > Cfg::MAX_STAGES) stages = Cfg::MAX_STAGES;
+  const int smem_bytes = L.fixed + stages * Cfg::TILE_BYTES;
+  if (!configured[dev]) {
+    err = cudaFuncSetAttribute(decode_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_total);
+    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(decode)", err);
+    configured[dev] = 1;
+  }
+  decode_kernel<T, G><<<grid, Cfg::NTHREADS, smem_bytes, stream>>>(a, stages, ngroups);
   err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error("decode_kernel launch", err);
   count_launch();

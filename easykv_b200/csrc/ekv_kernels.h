@@ -18,7 +18,10 @@ struct KernelArgs {
   float scale_div;   // (float)sqrt(d)
   float scale_mul;   // 1.0f / scale_div
   ekv_step st;
+  unsigned long long* timeline;   // profiling hook (ekv_debug_set_timeline), normally null
 };
+
+unsigned long long* debug_timeline();
 
 int set_cuda_error(const char* what, cudaError_t err);
 int set_error(int code, const char* fmt, ...);

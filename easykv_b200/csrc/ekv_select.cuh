@@ -25,6 +25,9 @@ struct UnitState {      // this (sequence, kv head)'s slices
   float* S;
   float* SQ;
   float* C;
+  const float* S_in = nullptr;   // optional staged copies (shared memory) of S/SQ/C[0, n_phys) to read from
+  const float* SQ_in = nullptr;
+  const float* C_in = nullptr;
   int32_t* lidx;
   const int32_t* new_slots;   // [q_len] or nullptr
   int32_t* victim_slots;      // [evict] or nullptr
@@ -63,7 +66,7 @@ struct SelScratch {     // shared memory, carved by the caller; NE = n_phys + q_
   }
 };
 
-enum { F_CAND = 1, F_FEAS = 2, F_CHOSEN = 4 };
+enum { F_CAND = 1, F_FEAS = 2, F_CHOSEN = 4, F_REJ = 8 };
 
 // m-th smallest (1-based) of key(e) over {e : pred(e)}: returns the threshold T, how many of the
 // entries equal to T belong to the m smallest (`need`), and how many entries equal T (`tcount`).
@@ -142,48 +145,70 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
   const int policy = st.policy;
 
   // ---- pass 1: state update + keys --------------------------------------------------------
-  for (int e = g.tid; e < NE; e += g.n) {
-    const bool is_new = e >= n_phys;
-    const int i_new = e - n_phys;
-    const int phys = is_new ? (u.new_slots ? u.new_slots[i_new] : n_phys + i_new) : e;
-    int l;
-    if (is_new) l = n_before + i_new;
-    else l = lj_preloaded ? c.lj[e] : u.lidx[e];
-    c.lj[e] = l;
-    uint8_t f = 0;
-    uint32_t ka = 0, kb = 0;
-    const int j = l - P;
-    if (l >= 0 && j >= 0) {
-      float s = 0.f, sq = 0.f, cc;
-      if (is_new) cc = __fsub_rn(st.c_new0, __fmul_rn((float)i_new, st.c_new_step));
-      else { s = u.S[phys]; sq = u.SQ[phys]; cc = u.C[phys]; }
-      bool dirty = is_new;
-      if (st.accumulate) {
-        float ds, dsq;
-        acc(e, ds, dsq);
-        if (policy == EKV_POLICY_ROCO) { s = __fadd_rn(s, ds); sq = __fadd_rn(sq, dsq); dirty = true; }
-        else if (policy == EKV_POLICY_H2O) { s = __fadd_rn(s, ds); dirty = true; }
-        else if (policy == EKV_POLICY_TOVA) { s = ds; dirty = true; }
-      }
-      if (evicting && st.counter_add != 0.f) { cc = __fadd_rn(cc, st.counter_add); dirty = true; }
-      if (dirty) { u.S[phys] = s; u.SQ[phys] = sq; u.C[phys] = cc; }
-      if (evicting) {
-        if (policy == EKV_POLICY_ROCO) {
-          const float mean = __fdiv_rn(s, cc);
-          float sd = __fsqrt_rn(__fsub_rn(__fdiv_rn(sq, cc), __fmul_rn(mean, mean)));
-          if (j >= n_s - st.protect_last || j < st.sink_protect) sd = 1e9f;
-          ka = order_key(sd);
-          kb = order_key(mean);
-          f = F_CAND;
-        } else if (policy == EKV_POLICY_H2O || policy == EKV_POLICY_TOVA) {
-          kb = order_key(s);
-          if (j >= st.win_lo && j < n_s - st.win_recent) f = F_CAND | F_FEAS;
-        } else if (policy == EKV_POLICY_RANGE) {
-          if (j >= st.range_start && j < st.range_start + st.evict) f = F_CAND | F_FEAS | F_CHOSEN;
+  // CH entries per thread and trip: all their state loads are issued before any of them is used
+  // (the loop otherwise serialises one DRAM round trip per entry behind the write-backs)
+  constexpr int CH = 4;
+  for (int base = 0; base < NE; base += CH * g.n) {
+    int l[CH];
+    float s[CH], sq[CH], cc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int e = base + k * g.n + g.tid;
+      l[k] = -1; s[k] = 0.f; sq[k] = 0.f; cc[k] = 0.f;
+      if (e < NE) {
+        const bool is_new = e >= n_phys;
+        if (is_new) {
+          l[k] = n_before + (e - n_phys);
+          cc[k] = __fsub_rn(st.c_new0, __fmul_rn((float)(e - n_phys), st.c_new_step));
+        } else {
+          l[k] = lj_preloaded ? c.lj[e] : u.lidx[e];
+          if (!lj_preloaded || l[k] >= P) {
+            if (u.S_in) { s[k] = u.S_in[e]; sq[k] = u.SQ_in[e]; cc[k] = u.C_in[e]; }
+            else { s[k] = u.S[e]; sq[k] = u.SQ[e]; cc[k] = u.C[e]; }
+          }
         }
       }
     }
-    c.keyA[e] = ka; c.keyB[e] = kb; c.flag[e] = f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int e = base + k * g.n + g.tid;
+      if (e >= NE) continue;
+      const bool is_new = e >= n_phys;
+      const int phys = is_new ? (u.new_slots ? u.new_slots[e - n_phys] : e) : e;
+      c.lj[e] = l[k];
+      uint8_t f = 0;
+      uint32_t ka = 0, kb = 0;
+      const int j = l[k] - P;
+      if (l[k] >= 0 && j >= 0) {
+        float sv = s[k], sqv = sq[k], cv = cc[k];
+        bool dirty = is_new;
+        if (st.accumulate) {
+          float ds, dsq;
+          acc(e, ds, dsq);
+          if (policy == EKV_POLICY_ROCO) { sv = __fadd_rn(sv, ds); sqv = __fadd_rn(sqv, dsq); dirty = true; }
+          else if (policy == EKV_POLICY_H2O) { sv = __fadd_rn(sv, ds); dirty = true; }
+          else if (policy == EKV_POLICY_TOVA) { sv = ds; dirty = true; }
+        }
+        if (evicting && st.counter_add != 0.f) { cv = __fadd_rn(cv, st.counter_add); dirty = true; }
+        if (dirty) { u.S[phys] = sv; u.SQ[phys] = sqv; u.C[phys] = cv; }
+        if (evicting) {
+          if (policy == EKV_POLICY_ROCO) {
+            const float mean = __fdiv_rn(sv, cv);
+            float sd = __fsqrt_rn(__fsub_rn(__fdiv_rn(sqv, cv), __fmul_rn(mean, mean)));
+            if (j >= n_s - st.protect_last || j < st.sink_protect) sd = 1e9f;
+            ka = order_key(sd);
+            kb = order_key(mean);
+            f = F_CAND;
+          } else if (policy == EKV_POLICY_H2O || policy == EKV_POLICY_TOVA) {
+            kb = order_key(sv);
+            if (j >= st.win_lo && j < n_s - st.win_recent) f = F_CAND | F_FEAS;
+          } else if (policy == EKV_POLICY_RANGE) {
+            if (j >= st.range_start && j < st.range_start + st.evict) f = F_CAND | F_FEAS | F_CHOSEN;
+          }
+        }
+      }
+      c.keyA[e] = ka; c.keyB[e] = kb; c.flag[e] = f;
+    }
   }
   g.sync();
   if (!evicting || policy == EKV_POLICY_NONE) {
@@ -195,8 +220,64 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
     return;
   }
 
+  // ---- roco, one victim (decode): walk the candidates in (mean, std, index) order and take the first
+  // whose std rank is below k_feasible — the same slot as argmin over the k smallest std, found with
+  // one block argmin + one counting pass per attempt (~1/0.7 attempts expected) instead of a full
+  // radix select.  Falls through to the general path after MAX_TRY rejected candidates.
+  bool done = false;
+  if (policy == EKV_POLICY_ROCO && st.evict == 1) {
+    constexpr int MAX_TRY = 6;
+    const int w = g.tid >> 5, nw = (g.n + 31) >> 5;
+    for (int attempt = 0; attempt < MAX_TRY && !done; ++attempt) {
+      Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
+      for (int e = g.tid; e < NE; e += g.n) {
+        if ((c.flag[e] & (F_CAND | F_REJ)) == F_CAND) {
+          Tuple128 t;
+          t.hi = ((unsigned long long)c.keyB[e] << 32) | c.keyA[e];
+          t.lo = ((unsigned long long)(uint32_t)c.lj[e] << 32) | (uint32_t)e;
+          if (tuple_less(t, best)) best = t;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Tuple128 t;
+        t.hi = __shfl_xor_sync(0xffffffffu, best.hi, o);
+        t.lo = __shfl_xor_sync(0xffffffffu, best.lo, o);
+        if (tuple_less(t, best)) best = t;
+      }
+      if ((g.tid & 31) == 0) { c.red[2 * w] = best.hi; c.red[2 * w + 1] = best.lo; }
+      g.sync();
+      for (int k = 0; k < nw; ++k) {
+        Tuple128 t; t.hi = c.red[2 * k]; t.lo = c.red[2 * k + 1];
+        if (tuple_less(t, best)) best = t;
+      }
+      if (best.lo == ~0ull) break;                                // no candidate left (uniform)
+      const uint32_t ka_c = (uint32_t)(best.hi & 0xffffffffu), l_c = (uint32_t)(best.lo >> 32);
+      const int e_c = (int)(best.lo & 0xffffffffu);
+      int cnt = 0;                                                // std rank of the candidate
+      for (int e = g.tid; e < NE; e += g.n) {
+        if (c.flag[e] & F_CAND) {
+          const uint32_t ka = c.keyA[e];
+          cnt += (ka < ka_c || (ka == ka_c && (uint32_t)c.lj[e] < l_c)) ? 1 : 0;
+        }
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if ((g.tid & 31) == 0) c.hist[(attempt & 1) * 32 + w] = (uint32_t)cnt;
+      g.sync();
+      int rank = 0;
+      for (int k = 0; k < nw; ++k) rank += (int)c.hist[(attempt & 1) * 32 + k];
+      if (rank < st.k_feasible) {
+        if (g.tid == 0) c.flag[e_c] |= F_FEAS | F_CHOSEN;
+        done = true;
+      } else if (g.tid == 0) {
+        c.flag[e_c] |= F_REJ;
+      }
+      g.sync();
+    }
+  }
+
   // ---- stage 1 (roco): the k_feasible smallest std ------------------------------------------
-  if (policy == EKV_POLICY_ROCO) {
+  if (policy == EKV_POLICY_ROCO && !done) {
     uint32_t T1; int need1, tc1;
     radix_select(NE, st.k_feasible,
                  [&](int e) { return c.keyA[e]; }, [&](int e) { return (c.flag[e] & F_CAND) != 0; }, c, g, T1, need1, tc1);
@@ -217,7 +298,7 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
   }
 
   // ---- stage 2: the `evict` smallest (keyB, keyA, logical index) among the feasible ------------
-  if (policy != EKV_POLICY_RANGE) {
+  if (policy != EKV_POLICY_RANGE && !done) {
     if (st.evict == 1) {
       Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
       for (int e = g.tid; e < NE; e += g.n) {

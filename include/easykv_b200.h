@@ -161,6 +161,12 @@ EKV_API int ekv_export_logical(const ekv_shape* shape, const ekv_layer_io* io, v
  * gpu_launches claim). */
 EKV_API int64_t ekv_launch_count(void);
 
+/* Profiling hook (development aid, not part of the data path): when set to a device buffer of
+ * uint64 [grid][16 units][8], the decode kernel's consumer groups record SM-clock timestamps at their
+ * phase boundaries (unit start, header, first tile, K phase, softmax, V phase, out, tail) plus the
+ * CTA's start %globaltimer in slot [cta][15][7].  NULL (the default) disables it. */
+EKV_API void ekv_debug_set_timeline(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

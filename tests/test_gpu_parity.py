@@ -68,7 +68,7 @@ def _random_state(Hkv, n, cap, seed, quant):
 def test_select_matches_oracle(ekv_lib, policy, evict, n, quant):
     from easykv_b200.cache import BudgetedKVCache
     from easykv_b200.plan import StepParams
-    Hkv, cap = 8, n + 37
+    Hkv, cap = 8, (n + 37 + 7) // 8 * 8
     S, SQ, C, perm = _random_state(Hkv, n, cap, seed=n + evict, quant=quant)
     budget = n - 1
     recent = int(budget * (0.3 if evict == 1 else 0.1))
@@ -142,7 +142,7 @@ def test_full_size_decode_properties(ekv_lib):
     with an fp32 torch attention over that cache, (d) the decode kernel and the general kernel agree."""
     from easykv_b200.cache import BudgetedKVCache
     from easykv_b200.plan import StepParams
-    B, H, Hkv, d, n, steps = 4, 32, 32, 128, 1088, 48
+    B, H, Hkv, d, n, steps = 12, 32, 32, 128, 1088, 48     # 384 units > 148 SMs: both consumer groups run
     torch.manual_seed(3)
     dev = "cuda"
     caches = [BudgetedKVCache(1, B, H, Hkv, d, n + 1, dtype=torch.float16) for _ in range(2)]
@@ -173,8 +173,8 @@ def test_full_size_decode_properties(ekv_lib):
     assert torch.equal(Ke, Kl) and torch.equal(Ve, Vl)
     lidx = caches[0].lidx[0]
     srt = torch.sort(lidx, dim=-1)[0]
-    assert torch.equal(srt[..., 1:], torch.arange(n, device=dev, dtype=torch.int32).expand(B, Hkv, n))
-    assert int(srt[..., 0].max()) == -1
+    assert torch.equal(srt[..., -n:], torch.arange(n, device=dev, dtype=torch.int32).expand(B, Hkv, n))
+    assert int(srt[..., :-n].max()) == -1
 
 
 def test_errors_are_python_exceptions(ekv_lib):
