@@ -211,6 +211,14 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
         ns[0] = a.new_slots ? a.new_slots[unit] : n_phys;
         lj[n_phys] = a.n_before;
       }
+      // the tail reads this unit's S / SQ / C once: pull the lines into L2 now
+      if (a.st.policy != EKV_POLICY_NONE && a.st.policy != EKV_POLICY_RANGE) {
+        const int lines = (n_phys * 4 + 127) / 128;
+        for (int i = tid; i < 3 * lines; i += NCONS) {
+          const float* base = (i < lines ? a.S : (i < 2 * lines ? a.SQ : a.C)) + (size_t)unit * a.cap;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + (size_t)(i % lines) * 128));
+        }
+      }
     }
     grp.sync();
     stamp(k_unit, 1);
@@ -307,6 +315,7 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
       float sacc[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) sacc[g] = 0.f;
+#pragma unroll 5
       for (int e = tid; e < NE; e += NCONS)
 #pragma unroll
         for (int g = 0; g < G; ++g) sacc[g] += expf(Tr<T>::to_f(plog[g * nep + e]) - mx[g]);
@@ -323,6 +332,7 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
         for (int w = 1; w < NWARP; ++w) v += red2[g * NWARP + w];
         inv[g] = a.st.arith ? v : __fdiv_rn(1.0f, v);
       }
+#pragma unroll 5
       for (int e = tid; e < NE; e += NCONS)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -396,6 +406,7 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
     SelScratch sc;
     sc.lj = lj;
     sc.carve(scr, NE, a.st.evict);
+    if (tl && k_unit < 7) sc.dbg = tl + (8 + k_unit) * 8;
     UnitState u;
     u.S = a.S + (size_t)unit * a.cap; u.SQ = a.SQ + (size_t)unit * a.cap; u.C = a.C + (size_t)unit * a.cap;
     u.lidx = a.lidx + (size_t)unit * a.cap;

@@ -44,6 +44,7 @@ struct SelScratch {     // shared memory, carved by the caller; NE = n_phys + q_
   int32_t* vs;          // [max(evict,1)]      victim physical slots (unsorted)
   int32_t* misc;        // [8]
   unsigned long long* red;  // [2 * 32]
+  unsigned long long* dbg = nullptr;   // profiling hook: 8 clock64 stamps of the tail's stages
   static __host__ __device__ size_t bytes(int NE, int evict) {
     int ev = evict > 0 ? evict : 1;
     size_t b = (size_t)NE * 4 * 2;                 // keyA, keyB   (lj is carved separately by callers that preload it)
@@ -143,74 +144,82 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
   const int n_s = n_after - P;
   const bool evicting = st.evict > 0;
   const int policy = st.policy;
+  auto stamp = [&](int i) { if (c.dbg && g.tid == 0) c.dbg[i] = clock64(); };
+  stamp(0);
 
   // ---- pass 1: state update + keys --------------------------------------------------------
-  // CH entries per thread and trip: all their state loads are issued before any of them is used
-  // (the loop otherwise serialises one DRAM round trip per entry behind the write-backs)
-  constexpr int CH = 4;
-  for (int base = 0; base < NE; base += CH * g.n) {
-    int l[CH];
-    float s[CH], sq[CH], cc[CH];
+  // FCH entries per thread and trip, in three stages — all loads, then all arithmetic, then all stores —
+  // so that one DRAM round trip covers the whole trip and the IEEE div/sqrt chains of the entries
+  // overlap.  When a single trip covers the unit (NE <= FCH * threads) the keys stay in registers for
+  // the single-victim fast path below.
+  constexpr int FCH = 5;
+  const bool one_trip = NE <= FCH * g.n;
+  int rl[FCH];
+  uint32_t rka[FCH], rkb[FCH];
+  uint8_t rf[FCH];
+  for (int base = 0; base < NE; base += FCH * g.n) {
+    float s[FCH], sq[FCH], cc[FCH], ds[FCH], dsq[FCH];
+    int ph[FCH];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
+    for (int k = 0; k < FCH; ++k) {
       const int e = base + k * g.n + g.tid;
-      l[k] = -1; s[k] = 0.f; sq[k] = 0.f; cc[k] = 0.f;
+      rl[k] = -1; s[k] = 0.f; sq[k] = 0.f; cc[k] = 1.f; ds[k] = 0.f; dsq[k] = 0.f; ph[k] = e;
       if (e < NE) {
-        const bool is_new = e >= n_phys;
-        if (is_new) {
-          l[k] = n_before + (e - n_phys);
+        if (e >= n_phys) {
+          rl[k] = n_before + (e - n_phys);
           cc[k] = __fsub_rn(st.c_new0, __fmul_rn((float)(e - n_phys), st.c_new_step));
+          ph[k] = u.new_slots ? u.new_slots[e - n_phys] : e;
         } else {
-          l[k] = lj_preloaded ? c.lj[e] : u.lidx[e];
-          if (!lj_preloaded || l[k] >= P) {
+          rl[k] = lj_preloaded ? c.lj[e] : u.lidx[e];
+          if (!lj_preloaded || rl[k] >= P) {
             if (u.S_in) { s[k] = u.S_in[e]; sq[k] = u.SQ_in[e]; cc[k] = u.C_in[e]; }
             else { s[k] = u.S[e]; sq[k] = u.SQ[e]; cc[k] = u.C[e]; }
           }
         }
+        if (st.accumulate) acc(e, ds[k], dsq[k]);
       }
     }
+    bool dirty[FCH];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
+    for (int k = 0; k < FCH; ++k) {
       const int e = base + k * g.n + g.tid;
-      if (e >= NE) continue;
-      const bool is_new = e >= n_phys;
-      const int phys = is_new ? (u.new_slots ? u.new_slots[e - n_phys] : e) : e;
-      c.lj[e] = l[k];
-      uint8_t f = 0;
-      uint32_t ka = 0, kb = 0;
-      const int j = l[k] - P;
-      if (l[k] >= 0 && j >= 0) {
-        float sv = s[k], sqv = sq[k], cv = cc[k];
-        bool dirty = is_new;
+      const int j = rl[k] - P;
+      rka[k] = 0; rkb[k] = 0; rf[k] = 0; dirty[k] = false;
+      if (e < NE && rl[k] >= 0 && j >= 0) {
+        dirty[k] = e >= n_phys;
         if (st.accumulate) {
-          float ds, dsq;
-          acc(e, ds, dsq);
-          if (policy == EKV_POLICY_ROCO) { sv = __fadd_rn(sv, ds); sqv = __fadd_rn(sqv, dsq); dirty = true; }
-          else if (policy == EKV_POLICY_H2O) { sv = __fadd_rn(sv, ds); dirty = true; }
-          else if (policy == EKV_POLICY_TOVA) { sv = ds; dirty = true; }
+          if (policy == EKV_POLICY_ROCO) { s[k] = __fadd_rn(s[k], ds[k]); sq[k] = __fadd_rn(sq[k], dsq[k]); dirty[k] = true; }
+          else if (policy == EKV_POLICY_H2O) { s[k] = __fadd_rn(s[k], ds[k]); dirty[k] = true; }
+          else if (policy == EKV_POLICY_TOVA) { s[k] = ds[k]; dirty[k] = true; }
         }
-        if (evicting && st.counter_add != 0.f) { cv = __fadd_rn(cv, st.counter_add); dirty = true; }
-        if (dirty) { u.S[phys] = sv; u.SQ[phys] = sqv; u.C[phys] = cv; }
+        if (evicting && st.counter_add != 0.f) { cc[k] = __fadd_rn(cc[k], st.counter_add); dirty[k] = true; }
         if (evicting) {
           if (policy == EKV_POLICY_ROCO) {
-            const float mean = __fdiv_rn(sv, cv);
-            float sd = __fsqrt_rn(__fsub_rn(__fdiv_rn(sqv, cv), __fmul_rn(mean, mean)));
+            const float mean = __fdiv_rn(s[k], cc[k]);
+            float sd = __fsqrt_rn(__fsub_rn(__fdiv_rn(sq[k], cc[k]), __fmul_rn(mean, mean)));
             if (j >= n_s - st.protect_last || j < st.sink_protect) sd = 1e9f;
-            ka = order_key(sd);
-            kb = order_key(mean);
-            f = F_CAND;
+            rka[k] = order_key(sd);
+            rkb[k] = order_key(mean);
+            rf[k] = F_CAND;
           } else if (policy == EKV_POLICY_H2O || policy == EKV_POLICY_TOVA) {
-            kb = order_key(sv);
-            if (j >= st.win_lo && j < n_s - st.win_recent) f = F_CAND | F_FEAS;
+            rkb[k] = order_key(s[k]);
+            if (j >= st.win_lo && j < n_s - st.win_recent) rf[k] = F_CAND | F_FEAS;
           } else if (policy == EKV_POLICY_RANGE) {
-            if (j >= st.range_start && j < st.range_start + st.evict) f = F_CAND | F_FEAS | F_CHOSEN;
+            if (j >= st.range_start && j < st.range_start + st.evict) rf[k] = F_CAND | F_FEAS | F_CHOSEN;
           }
         }
       }
-      c.keyA[e] = ka; c.keyB[e] = kb; c.flag[e] = f;
+    }
+#pragma unroll
+    for (int k = 0; k < FCH; ++k) {
+      const int e = base + k * g.n + g.tid;
+      if (e < NE) {
+        if (dirty[k]) { u.S[ph[k]] = s[k]; u.SQ[ph[k]] = sq[k]; u.C[ph[k]] = cc[k]; }
+        c.lj[e] = rl[k]; c.keyA[e] = rka[k]; c.keyB[e] = rkb[k]; c.flag[e] = rf[k];
+      }
     }
   }
-  g.sync();
+  stamp(1);
   if (!evicting || policy == EKV_POLICY_NONE) {
     for (int e = n_phys + g.tid; e < NE; e += g.n) {
       const int i_new = e - n_phys;
@@ -220,21 +229,28 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
     return;
   }
 
-  // ---- roco, one victim (decode): walk the candidates in (mean, std, index) order and take the first
-  // whose std rank is below k_feasible — the same slot as argmin over the k smallest std, found with
-  // one block argmin + one counting pass per attempt (~1/0.7 attempts expected) instead of a full
-  // radix select.  Falls through to the general path after MAX_TRY rejected candidates.
-  bool done = false;
-  if (policy == EKV_POLICY_ROCO && st.evict == 1) {
-    constexpr int MAX_TRY = 6;
+  // ---- single victim (decode), keys in registers -------------------------------------------------------
+  // roco: walk the candidates in (mean, std, index) order and take the first whose std rank is below
+  // k_feasible — the same slot as argmin over the k smallest std (easykv.py:322-324), found with one
+  // block argmin + one counting pass per attempt (the lowest-mean slot is usually among the 70 % lowest
+  // std) instead of a radix select.  h2o / tova: one block argmin over the window.  Victim bookkeeping
+  // and the renumbering also run from registers.  After MAX_TRY rejected candidates the general path
+  // below takes over.
+  if (one_trip && st.evict == 1 && policy != EKV_POLICY_RANGE) {
+    constexpr int MAX_TRY = 4;
     const int w = g.tid >> 5, nw = (g.n + 31) >> 5;
-    for (int attempt = 0; attempt < MAX_TRY && !done; ++attempt) {
+    const uint8_t need_flag = policy == EKV_POLICY_ROCO ? F_CAND : F_FEAS;
+    bool found = false;
+    int e_c = -1;
+    uint32_t l_c = 0;
+    for (int attempt = 0; attempt < MAX_TRY; ++attempt) {
       Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
-      for (int e = g.tid; e < NE; e += g.n) {
-        if ((c.flag[e] & (F_CAND | F_REJ)) == F_CAND) {
+#pragma unroll
+      for (int k = 0; k < FCH; ++k) {
+        if ((rf[k] & (need_flag | F_REJ)) == need_flag) {
           Tuple128 t;
-          t.hi = ((unsigned long long)c.keyB[e] << 32) | c.keyA[e];
-          t.lo = ((unsigned long long)(uint32_t)c.lj[e] << 32) | (uint32_t)e;
+          t.hi = ((unsigned long long)rkb[k] << 32) | rka[k];
+          t.lo = ((unsigned long long)(uint32_t)rl[k] << 32) | (uint32_t)(k * g.n + g.tid);
           if (tuple_less(t, best)) best = t;
         }
       }
@@ -252,30 +268,50 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
         if (tuple_less(t, best)) best = t;
       }
       if (best.lo == ~0ull) break;                                // no candidate left (uniform)
-      const uint32_t ka_c = (uint32_t)(best.hi & 0xffffffffu), l_c = (uint32_t)(best.lo >> 32);
-      const int e_c = (int)(best.lo & 0xffffffffu);
+      const uint32_t ka_c = (uint32_t)(best.hi & 0xffffffffu);
+      l_c = (uint32_t)(best.lo >> 32);
+      e_c = (int)(best.lo & 0xffffffffu);
+      if (policy != EKV_POLICY_ROCO) { found = true; break; }
       int cnt = 0;                                                // std rank of the candidate
-      for (int e = g.tid; e < NE; e += g.n) {
-        if (c.flag[e] & F_CAND) {
-          const uint32_t ka = c.keyA[e];
-          cnt += (ka < ka_c || (ka == ka_c && (uint32_t)c.lj[e] < l_c)) ? 1 : 0;
-        }
-      }
+#pragma unroll
+      for (int k = 0; k < FCH; ++k)
+        cnt += ((rf[k] & F_CAND) && (rka[k] < ka_c || (rka[k] == ka_c && (uint32_t)rl[k] < l_c))) ? 1 : 0;
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if ((g.tid & 31) == 0) c.hist[(attempt & 1) * 32 + w] = (uint32_t)cnt;
       g.sync();
       int rank = 0;
       for (int k = 0; k < nw; ++k) rank += (int)c.hist[(attempt & 1) * 32 + k];
-      if (rank < st.k_feasible) {
-        if (g.tid == 0) c.flag[e_c] |= F_FEAS | F_CHOSEN;
-        done = true;
-      } else if (g.tid == 0) {
-        c.flag[e_c] |= F_REJ;
+      if (rank < st.k_feasible) { found = true; break; }
+#pragma unroll
+      for (int k = 0; k < FCH; ++k)
+        if (k * g.n + g.tid == e_c) rf[k] |= F_REJ;
+    }
+    stamp(2);
+    if (found) {
+#pragma unroll
+      for (int k = 0; k < FCH; ++k) {
+        const int e = k * g.n + g.tid;
+        if (e >= NE || rl[k] < 0) continue;
+        const int phys = e >= n_phys ? (u.new_slots ? u.new_slots[e - n_phys] : e) : e;
+        if (e == e_c) {
+          if (u.victim_lidx) u.victim_lidx[0] = rl[k];
+          if (u.victim_slots) u.victim_slots[0] = phys;
+          if (st.apply) u.lidx[phys] = -1;
+          else if (e >= n_phys) u.lidx[phys] = rl[k];
+        } else if (st.apply && (uint32_t)rl[k] > l_c) {
+          u.lidx[phys] = rl[k] - 1;
+        } else if (e >= n_phys) {
+          u.lidx[phys] = rl[k];
+        }
       }
-      g.sync();
+      stamp(5);
+      return;
     }
   }
+  g.sync();
+  bool done = false;
 
+  stamp(2);
   // ---- stage 1 (roco): the k_feasible smallest std ------------------------------------------
   if (policy == EKV_POLICY_ROCO && !done) {
     uint32_t T1; int need1, tc1;
@@ -352,6 +388,7 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
     }
   }
 
+  stamp(3);
   // ---- gather victims, order them by logical index, renumber --------------------------------------
   if (g.tid == 0) c.misc[4] = 0;
   g.sync();
@@ -381,6 +418,7 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
     }
   }
   g.sync();
+  stamp(4);
   if (st.apply) {
     for (int e = g.tid; e < NE; e += g.n) {
       const int l = c.lj[e];
@@ -397,6 +435,7 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
       u.lidx[phys] = c.lj[e];
     }
   }
+  stamp(5);
 }
 
 }  // namespace ekv

@@ -32,3 +32,7 @@ for cta in (0, 1, 73, 147):
         rel = [(x.item() - base) for x in row]
         dif = [rel[0]] + [rel[i] - rel[i - 1] for i in range(1, 8)]
         print(f"  unit#{ku} g{ku%2}: start@{rel[0]:>7}  " + " ".join(f"{nm}+{dd}" for nm, dd in zip(names[1:], dif[1:])) + f"  end@{rel[7]}")
+        if ku < 7:
+            tr = [x.item() for x in tl[cta, 8 + ku][:6]]
+            print("      tail: pre+%d pass1+%d fast+%d radix+%d gather+%d apply+%d post+%d" % (
+                tr[0] - row[6].item(), tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], row[7].item() - tr[5]))
