@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--seqs-per-gpu", type=int, default=32)
+    ap.add_argument("--seqs-per-gpu", type=int, default=64)
     ap.add_argument("--layers", type=int, default=L_LAYERS)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")

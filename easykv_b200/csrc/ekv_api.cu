@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ekv_kernels.h"
 
@@ -26,6 +27,10 @@ int set_cuda_error(const char* what, cudaError_t err) {
 }
 static std::atomic<unsigned long long*> g_timeline{nullptr};
 unsigned long long* debug_timeline() { return g_timeline.load(std::memory_order_relaxed); }
+int decode_variant() {
+  static const int v = [] { const char* e = getenv("EKV_DECODE_VARIANT"); return e ? atoi(e) : 0; }();
+  return v;
+}
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static int build_args(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, KernelArgs& a) {

@@ -31,8 +31,7 @@ template <typename T> struct DecodeCfg {
   static constexpr int D = 128;
   static constexpr int NWARP = 8;                       // consumer warps per group
   static constexpr int NCONS = NWARP * 32;
-  static constexpr int NGROUPS = 2;
-  static constexpr int NTHREADS = NGROUPS * NCONS + 32; // + the TMA producer warp (the last warp)
+  static constexpr int MAX_GROUPS = 2;
   static constexpr int ROW_BYTES = D * (int)sizeof(T);
   static constexpr int TILE_BYTES = 16384;
   static constexpr int TILE_ROWS = TILE_BYTES / ROW_BYTES;   // 64 (16-bit) / 32 (fp32)
@@ -79,7 +78,7 @@ template <typename T> struct DecodeSmem {
     const int NE = n_phys + 1;
     nep = align_up(NE, 8);
     int o = 0;
-    off_bar = o; o += (Cfg::NGROUPS + 1) * Cfg::MAX_STAGES * 8;   // full[group][stage], empty[stage]
+    off_bar = o; o += (Cfg::MAX_GROUPS + 1) * Cfg::MAX_STAGES * 8;   // full[group][stage], empty[stage]
     o = align_up(o, 128);
     off_grp = o;
     int h = 0;
@@ -102,19 +101,22 @@ template <typename T> struct DecodeSmem {
   }
 };
 
-template <typename T, int G>
-__global__ void __launch_bounds__(DecodeCfg<T>::NTHREADS, 1)
-decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
+// NG consumer groups per CTA: 2 = one CTA per SM whose groups ping-pong over one shared ring;
+// 1 = a lighter CTA (one group, its own ring) of which two are resident per SM and stream independently.
+template <typename T, int G, int NG>
+__global__ void __launch_bounds__(NG * DecodeCfg<T>::NCONS + 32, NG == 1 ? 2 : 1)
+decode_kernel(const KernelArgs a, const int stages) {
+  constexpr int ngroups = NG;
   using Cfg = DecodeCfg<T>;
   constexpr int D = Cfg::D, NWARP = Cfg::NWARP, NCONS = Cfg::NCONS, RPT = Cfg::RPT;
   constexpr int TILE_ROWS = Cfg::TILE_ROWS;
   extern __shared__ __align__(128) unsigned char smem[];
-  const DecodeSmem<T> L(G, a.n_phys, a.st.evict, ngroups);
+  const DecodeSmem<T> L(G, a.n_phys, a.st.evict, NG);
   // full[g][s]: tile in ring slot s has landed, signalled to the consumer group g that owns the tile —
   // one barrier per (group, slot) so that each waiter tracks the phase of a barrier only it consumes
   // (a parity wait must never run ahead of the barrier's previous phase); empty[s]: slot s released.
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-  uint64_t* empty = full + Cfg::NGROUPS * Cfg::MAX_STAGES;
+  uint64_t* empty = full + Cfg::MAX_GROUPS * Cfg::MAX_STAGES;
   unsigned char* ring = smem + L.off_ring;
 
   const int U = a.B * a.Hkv;
@@ -124,33 +126,48 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      for (int g = 0; g < Cfg::NGROUPS; ++g) mbar_init(&full[g * Cfg::MAX_STAGES + s], 1);
+      for (int g = 0; g < NG; ++g) mbar_init(&full[g * Cfg::MAX_STAGES + s], 1);
       mbar_init(&empty[s], NWARP);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == Cfg::NGROUPS * NWARP) {
+  if (warp == NG * NWARP) {
     // ===== TMA producer: one continuous tile stream over all of this CTA's units ======================
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
-      int t = 0;                                   // tile counter of this CTA
+      int s = 0, use = 0;                          // ring slot and how often it has been used
       int k_unit = 0;
+      long long pwait = 0;
+      const long long pstart = clock64();
       for (int unit = blockIdx.x; unit < U; unit += gridDim.x, ++k_unit) {
         uint64_t* gfull = full + (k_unit % ngroups) * Cfg::MAX_STAGES;
         const T* Kg = reinterpret_cast<const T*>(a.K) + (size_t)unit * a.cap * D;
         const T* Vg = reinterpret_cast<const T*>(a.V) + (size_t)unit * a.cap * D;
-        for (int i = 0; i < 2 * nt; ++i, ++t) {
-          const int s = t % stages, use = t / stages;
-          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+        for (int i = 0; i < 2 * nt; ++i) {
+          if (use > 0) {
+            if (a.timeline) {
+              const long long c0 = clock64();
+              mbar_wait(&empty[s], (use - 1) & 1);
+              pwait += clock64() - c0;
+            } else {
+              mbar_wait(&empty[s], (use - 1) & 1);
+            }
+          }
           const int tt = i < nt ? i : i - nt;
           const int rows = min(TILE_ROWS, n_phys - tt * TILE_ROWS);
           const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
           const T* src = (i < nt ? Kg : Vg) + (size_t)tt * TILE_ROWS * D;
           mbar_arrive_expect_tx(&gfull[s], bytes);
           tma_bulk_g2s(ring + (size_t)s * Cfg::TILE_BYTES, src, bytes, &gfull[s], pol);
+          if (++s == stages) { s = 0; ++use; }
         }
+      }
+      if (a.timeline) {                            // profiling: cycles the ring was full (nothing to request)
+        unsigned long long* tlp = a.timeline + (size_t)blockIdx.x * 16 * 8 + 15 * 8;
+        tlp[0] = (unsigned long long)pwait;
+        tlp[1] = (unsigned long long)(clock64() - pstart);
       }
     }
     return;
@@ -158,7 +175,6 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
 
   // ===== consumers ===============================================================================
   const int gid = warp / NWARP;                 // consumer group
-  if (gid >= ngroups) return;
   const int tid = threadIdx.x - gid * NCONS, gw = warp - gid * NWARP;
   const Grp grp{tid, NCONS, 1 + gid};
   const int hw = tid >> 4, l16 = tid & 15;      // 16 half-warps per group
@@ -192,7 +208,7 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
     tl[15 * 8 + 7] = gt;
   }
   for (int unit = blockIdx.x + gid * gridDim.x; unit < U; unit += ngroups * gridDim.x, k_unit += ngroups) {
-    int t = k_unit * 2 * nt;
+    int s = (int)(((long long)k_unit * 2 * nt) % stages);   // ring slot of this unit's first tile
     stamp(k_unit, 0);
     // ---- header: q, new K/V row, slot map (this group is idle until its first tile lands) --------------
     {
@@ -242,7 +258,6 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
 #pragma unroll
       for (int tb = 0; tb < TB; ++tb) {
         if (i0 + tb < nt) {
-          const int s = t % stages;
           mbar_wait(&gfull[s], (par >> s) & 1u);
           par ^= 1u << s;
           if (i0 + tb == 0) stamp(k_unit, 2);
@@ -256,7 +271,7 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
             for (int g = 0; g < G; ++g) part[tb * NVT + k * G + g] = dot8(x[k], qr[g], 0.f);
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[s]);
-          ++t;
+          s = s + 1 == stages ? 0 : s + 1;
         } else {
 #pragma unroll
           for (int j = 0; j < NVT; ++j) part[tb * NVT + j] = 0.f;
@@ -351,8 +366,7 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
       for (int j = 0; j < 8; ++j) oacc[g][j] = 0.f;
     // free slots contribute p == 0 exactly; their rows are stale but finite (the cache buffers are
     // zero-initialised and only ever hold rows that were valid), so no branch on p is needed
-    for (int i = 0; i < nt; ++i, ++t) {
-      const int s = t % stages;
+    for (int i = 0; i < nt; ++i) {
       mbar_wait(&gfull[s], (par >> s) & 1u);
       par ^= 1u << s;
       const T* tile = reinterpret_cast<const T*>(ring + (size_t)s * Cfg::TILE_BYTES);
@@ -367,6 +381,7 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
+      s = s + 1 == stages ? 0 : s + 1;
 #pragma unroll
       for (int k = 0; k < RPT; ++k)
         if (e0 + k < n_phys) {
@@ -442,43 +457,64 @@ decode_kernel(const KernelArgs a, const int stages, const int ngroups) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int G> static int launch_decode_tg(const KernelArgs& a, cudaStream_t stream) {
-  using Cfg = DecodeCfg<T>;
-  static thread_local int sm_count[16] = {0};
+template <typename T, int G, int NG>
+static int launch_decode_cfg(const KernelArgs& a, int grid, int stages, int smem_bytes, int dev, cudaStream_t stream) {
   static thread_local int configured[16] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 16) dev = 15;
   cudaError_t err;
-  if (!sm_count[dev]) {
-    err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (err != cudaSuccess) return set_cuda_error("cudaDeviceGetAttribute", err);
-  }
-  const int U = a.B * a.Hkv;
-  int grid = sm_count[dev] < U ? sm_count[dev] : U;
-  // two ping-pong consumer groups when a CTA gets more than one unit and both fit next to >= 4 ring stages
-  const int sm_total = 227 * 1024;
-  int ngroups = (U > grid) ? Cfg::NGROUPS : 1;
-  DecodeSmem<T> L(G, a.n_phys, a.st.evict, ngroups);
-  int stages = (sm_total - L.fixed) / Cfg::TILE_BYTES;
-  if (ngroups == 2 && stages < 4) {
-    ngroups = 1;
-    L = DecodeSmem<T>(G, a.n_phys, a.st.evict, 1);
-    stages = (sm_total - L.fixed) / Cfg::TILE_BYTES;
-  }
-  if (sm_total < L.fixed || stages < 2) return EKV_ERR_UNSUPPORTED;
-  if (stages > Cfg::MAX_STAGES) stages = Cfg::MAX_STAGES;
-  const int smem_bytes = L.fixed + stages * Cfg::TILE_BYTES;
   if (!configured[dev]) {
-    err = cudaFuncSetAttribute(decode_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_total);
+    err = cudaFuncSetAttribute(decode_kernel<T, G, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(decode)", err);
     configured[dev] = 1;
   }
-  decode_kernel<T, G><<<grid, Cfg::NTHREADS, smem_bytes, stream>>>(a, stages, ngroups);
+  decode_kernel<T, G, NG><<<grid, NG * DecodeCfg<T>::NCONS + 32, smem_bytes, stream>>>(a, stages);
   err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error("decode_kernel launch", err);
   count_launch();
   return EKV_OK;
+}
+
+int decode_variant();   // ekv_api.cu (env EKV_DECODE_VARIANT): 0 = automatic, 1 = one group per CTA (2 CTAs/SM), 2 = ping-pong groups
+
+template <typename T, int G> static int launch_decode_tg(const KernelArgs& a, cudaStream_t stream) {
+  using Cfg = DecodeCfg<T>;
+  static thread_local int sm_count[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
+  if (!sm_count[dev]) {
+    cudaError_t err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return set_cuda_error("cudaDeviceGetAttribute", err);
+  }
+  const int U = a.B * a.Hkv, sms = sm_count[dev];
+  const int sm_total = 227 * 1024;
+  const int variant = decode_variant();
+  // automatic: more than one unit per SM -> one CTA per SM with two ping-pong consumer groups over a
+  // shared ring (measured best: 0.87-0.93 of the HBM roofline vs 0.79-0.89 for two independent CTAs per
+  // SM); otherwise one light CTA per unit.
+  bool pingpong = variant == 2 || (variant == 0 && U > sms);
+  if (pingpong) {
+    const DecodeSmem<T> L2(G, a.n_phys, a.st.evict, 2);
+    if (sm_total < L2.fixed || (sm_total - L2.fixed) / Cfg::TILE_BYTES < 4) pingpong = false;
+  }
+  if (!pingpong) {
+    // one consumer group per CTA; with variant 1 two CTAs per SM (each with its own ring) once there is
+    // more than one unit per SM and at least 3 ring stages fit in half an SM's shared memory
+    const DecodeSmem<T> L(G, a.n_phys, a.st.evict, 1);
+    int per_sm = (variant == 1 && U > sms) ? 2 : 1;
+    int budget = per_sm == 2 ? sm_total / 2 - 1024 : sm_total;
+    int stages = (budget - L.fixed) / Cfg::TILE_BYTES;
+    if (per_sm == 2 && stages < 3) { per_sm = 1; budget = sm_total; stages = (budget - L.fixed) / Cfg::TILE_BYTES; }
+    if (budget < L.fixed || stages < 2) return EKV_ERR_UNSUPPORTED;
+    if (stages > Cfg::MAX_STAGES) stages = Cfg::MAX_STAGES;
+    const int grid = U < sms * per_sm ? U : sms * per_sm;
+    return launch_decode_cfg<T, G, 1>(a, grid, stages, L.fixed + stages * Cfg::TILE_BYTES, dev, stream);
+  }
+  const DecodeSmem<T> L(G, a.n_phys, a.st.evict, 2);
+  int stages = (sm_total - L.fixed) / Cfg::TILE_BYTES;
+  if (sm_total < L.fixed || stages < 4) return EKV_ERR_UNSUPPORTED;
+  if (stages > Cfg::MAX_STAGES) stages = Cfg::MAX_STAGES;
+  const int grid = U < sms ? U : sms;
+  return launch_decode_cfg<T, G, 2>(a, grid, stages, L.fixed + stages * Cfg::TILE_BYTES, dev, stream);
 }
 
 template <typename T> static int launch_decode_t(const KernelArgs& a, cudaStream_t stream) {
