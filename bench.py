@@ -246,15 +246,13 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    from easykv_b200.shard import reduce_job
+    ms, tokens = reduce_job(ms, B * args.steps, device=dev)            # max over ranks, sum over ranks
+    ms_e2e, tokens_e2e = reduce_job(ms_e2e, B * e2e_steps, device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    tokens = B * world * args.steps
     value = tokens / (ms / 1e3)
     per_launch_s = ms / 1e3 / (args.steps * L)
     balg = bytes_alg_per_launch(B, n + 1)
@@ -275,10 +273,11 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 data, f32 accumulate/state", "data": "synthetic",
+        "dtype": "f16", "data": "synthetic",
         "config": {"workload": f"Llama-2-7B head layout (L={L},H={H},Hkv={HKV},d={D}), 4K prompt already reduced by mode=auto "
                                f"budget={BUDGET} stride={STRIDE} to {RETAINED} retained slots; decode phase: {RETAINED}+1 keys per step, "
                                f"roco, one eviction per (sequence, layer, kv head) per step",
+                   "arithmetic": "f16 K/V/q/probabilities, f32 accumulate and policy state",
                    "seqs_per_gpu": B, "global_seqs": B * world, "cuda_graph": use_graph,
                    "l2": f"inputs larger than L2: {L} layers x {B} seqs x {2*HKV*(n+1)*D*2/1e6:.1f} MB of K/V = "
                          f"{L*B*2*HKV*(n+1)*D*2/1e9:.1f} GB streamed per step, distinct buffers per layer",
@@ -287,7 +286,7 @@ def main():
                      "traffic": traffic, "peak_source": peak_src,
                      "bytes_alg_per_launch": balg, "avg_launch_us": per_launch_s * 1e6,
                      "kernel": "ekv::decode_kernel<__half,1>"},
-        "e2e": {"value": B * world * e2e_steps / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": tokens_e2e / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "note": "q,k_new,v_new from pinned host memory, out + victim ids back to host, every step; cache resident"},
         "gpu_launches": gpu_launches, "host_launch_calls_in_timed_region": host_launches,

@@ -93,6 +93,14 @@ class BudgetedKVCache:
         self.n[l] = self.n_phys[l] = n
         self.free[l] = None
 
+    def set_counter(self, l, values):
+        """C of the first len(values) logical slots (easykv.py:412-418).  Only valid while the layout is
+        still dense (right after a prefill: physical slot == logical index)."""
+        if self.free_count(l) or self.n[l] != self.n_phys[l]:
+            raise RuntimeError("set_counter needs a dense layout")
+        c = torch.as_tensor(values, dtype=torch.float32, device=self.device)
+        self.Cn[l][:, :, :c.numel()] = c
+
     def step(self, l, sp: StepParams, q, k_new, v_new, apply=True, kernel=0):
         """One forward of layer `l`: q `[B, H, q_len, d]`, k_new / v_new `[B, Hkv, q_len, d]`
         (post-RoPE).  Returns (out `[B, H, q_len, d]`, victim_lidx `[B, Hkv, evict]` int32 or None).

@@ -1,0 +1,211 @@
+"""User surface of the budgeted-KV path — same names, signatures, config keys and return types as the
+reference's `easykv/easykv.py`:
+
+    enable_fixed_kv(model, tokenizer, mode, stride=1, verbose=False)        easykv/easykv.py:903-908
+    model.easykv_generate(input_ids=LongTensor[1, len], generation_config=dict) -> str    :199-753
+    model.easykv_ppl(input_ids=..., generation_config=dict) -> float                      :754-901
+
+What is different underneath: the reference's loops call the HF model with `output_attentions=True`,
+pull `[1, H, q, n]` probability tensors back into Python, fold / accumulate / select with ~135 host
+syncs per token and rebuild the cache by boolean indexing (easykv.py:271-362).  Here every forward is ONE
+`ekv_attend_evict` launch per layer (issued from the attention seam, `attention.py`) driven by a
+`StepParams` computed on the host from integers only (`plan.py`); nothing is read back except the
+sampled token.
+
+Mode loops mirrored (control flow only — sequencing and sampling are host glue):
+  decoding           :228-366     encoding            :367-529
+  encoding_decoding  :530-753     ppl                 :754-901     auto dispatch :220-227
+Sampling (`logits_adapter`, torch.multinomial; :115-134, :258) stays in PyTorch.
+"""
+from __future__ import annotations
+
+import functools
+import math
+import statistics
+import time
+
+import torch
+
+from . import plan as P
+from .attention import find_attention_modules, geometry, patched_attention
+from .cache import BudgetedKVCache
+
+
+def logits_adapter(logits: torch.Tensor, temperature: float, top_p: float):
+    """Temperature scaling and top-p renormalisation; returns (sampling distribution, raw softmax).
+    Same arithmetic as easykv/easykv.py:115-134."""
+    shape = logits.shape
+    logits = logits.reshape(-1, shape[-1])
+    prob = torch.softmax(logits / temperature, dim=-1)
+    sorted_prob, sorted_idx = torch.sort(prob, descending=True, dim=-1)
+    cumsum = torch.cumsum(sorted_prob, dim=-1)
+    sorted_prob[(cumsum - sorted_prob) > top_p] = 0.0
+    sorted_prob.div_(sorted_prob.sum(dim=-1, keepdim=True))
+    final = torch.gather(sorted_prob, -1, torch.argsort(sorted_idx, dim=-1))
+    return final.reshape(shape), torch.softmax(logits, dim=-1).reshape(shape)
+
+
+class Session:
+    """State shared between the driver loop and the attention seam during one `generate` call."""
+
+    def __init__(self, model, cache: BudgetedKVCache, record=True):
+        self.config = getattr(model, "config", None)
+        self.cache = cache
+        self.step = P.StepParams()
+        self.pos0 = 0
+        self.q_len = 0
+        self.max_position = 0
+        self.two_tuple = False
+        self.fwd = 0
+        self.events = [] if record else None     # (forward index, int32 [L, B, Hkv, evict] victim ids)
+        self._cur = None
+
+    def begin(self, step: P.StepParams, pos0: int, q_len: int):
+        self.step, self.pos0, self.q_len = step, pos0, q_len
+        self.max_position = max(self.max_position, pos0 + q_len - 1)
+        self.fwd += 1
+        self._cur = [] if (self.events is not None and step.evict) else None
+
+    def position_ids(self, device):
+        return torch.arange(self.pos0, self.pos0 + self.q_len, device=device)[None]
+
+    def record(self, layer, victims):
+        if self._cur is not None and victims is not None:
+            self._cur.append(victims)
+
+    def end(self):
+        if self._cur:
+            self.events.append((self.fwd, torch.stack(self._cur)))
+        self._cur = None
+
+
+DENSE_CHUNK = 64      # tokens per forward of the dense (no-eviction) prefill
+
+
+@torch.inference_mode()
+def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, report_decoding_latency=False):
+    cfg = generation_config
+    temperature = cfg.get("temperature", 1.0)                 # easykv/easykv.py:201-210
+    top_p = cfg.get("top_p", 1.0)
+    max_new_tokens = cfg.get("max_new_tokens", 1024)
+    budget = cfg.get("budget", 0.5)
+    policy = cfg.get("kv_policy", "recency")
+    temp_length = cfg.get("temp_length", 4)
+    recent_ratio = cfg.get("recent_ratio", 0.1)
+    keep_attention = cfg.get("keep_attention", False)
+    eos_token_ids = cfg.get("eos_token_ids", [self.tokenizer.eos_token_id])
+    if cfg.get("streaming", False):
+        raise NotImplementedError("streaming=True (llama_forward_stream) is not part of this path yet (SURVEY §8f row 3)")
+    policy = P.canonical_policy(policy)
+    if policy == "random":
+        raise NotImplementedError("kv_policy='random' draws from torch's generator inside the reference's loop and is "
+                                  "not reproduced here")
+    if input_ids.dim() == 1:
+        input_ids = input_ids[None]
+    bsz, length = input_ids.shape
+    ppl_mode = kv_mode == "ppl"
+    plan = P.resolve_plan(kv_mode, length, budget, stride, recent_ratio, temp_length)
+    if keep_attention and plan.mode in ("encoding", "encoding_decoding", "ppl"):
+        raise NotImplementedError("keep_attention=True needs the dense-prefill column statistics (SURVEY §8f row 1)")
+
+    mods = find_attention_modules(self)
+    H, Hkv, d = geometry(mods[0], getattr(self, "config", None))
+    param = next(self.parameters())
+    device, dtype = param.device, param.dtype
+    input_ids = input_ids.to(device)
+    capacity = plan.capacity + (max_new_tokens if plan.mode in ("dense", "encoding") else 0) + 1
+    # "aten_arith": which ATen flavour's two non-associative spots to reproduce (include/easykv_b200.h,
+    # ekv_step.arith): the CUDA kernels' (default — what the reference does on a GPU) or the CPU kernels'
+    arith = {"cuda": 1, "cpu": 0}[cfg.get("aten_arith", "cuda")]
+    cache = BudgetedKVCache(len(mods), bsz, H, Hkv, d, capacity, dtype=dtype, device=device, arith=arith)
+    sess = Session(self, cache, record=cfg.get("record_evictions", True))
+    self.easykv_last = sess                                   # eviction trace / cache of the last call
+
+    def forward(ids, pos0, step):
+        sess.begin(step, pos0, ids.shape[1])
+        pos = torch.arange(pos0, pos0 + ids.shape[1], device=device)[None].expand(bsz, -1)
+        out = self(input_ids=ids, position_ids=pos, use_cache=False)
+        sess.end()
+        return out.logits
+
+    def dense_prefill(upto):
+        """Causal attention over tokens [0, upto) with no policy: the reference's unpatched / patched dense
+        forward (easykv.py:232, :396, :557).  Chunked so that every forward is one fused launch per layer."""
+        logits = None
+        for t0 in range(0, upto, DENSE_CHUNK):
+            logits = forward(input_ids[:, t0:min(t0 + DENSE_CHUNK, upto)], t0, P.StepParams())
+        return logits
+
+    def sample(prob):
+        return torch.multinomial(prob, num_samples=1)          # easykv.py:258
+
+    with patched_attention(self, sess):
+        sched = list(P.schedule(plan, policy, max_new_tokens, keep_attention))
+        chunks = [s for s in sched if s[0] == "chunk"]
+        decodes = [s for s in sched if s[0] == "decode"]
+        all_logits, all_ids = [], []
+        if ppl_mode and plan.mode == "dense":                 # easykv.py:759-765
+            logits = torch.cat([forward(input_ids[:, t0:t0 + DENSE_CHUNK], t0, P.StepParams())
+                                for t0 in range(0, length, DENSE_CHUNK)], dim=1).float()
+            lp = torch.nn.functional.cross_entropy(logits[0, :-1], input_ids[0, 1:], reduction="none")
+            return math.exp(statistics.mean(lp.cpu().numpy().tolist()))
+        # ---- prompt --------------------------------------------------------------------------------------
+        n_dense = length if plan.mode in ("decoding", "dense") else plan.r_idx
+        logits = dense_prefill(n_dense)
+        C0 = P.initial_counter(plan, keep_attention)
+        if C0 is not None:                                     # strided modes keep state for the prompt
+            for l in range(cache.L):
+                cache.set_counter(l, C0)
+        cur = n_dense
+        for _, q_len, st in chunks:                            # easykv.py:426-500 / :587-661 / :816-892
+            logits = forward(input_ids[:, cur:cur + q_len], cur, st)
+            if ppl_mode:
+                all_logits.append(logits[0].float())
+                all_ids.append(input_ids[0, cur:cur + q_len])
+            cur += q_len
+        retained = cache.n[0]
+        if plan.mode in ("encoding", "ppl"):
+            print(f"KV cache budget ratio: {retained / length * 100:.2f}%({retained}/{length})")
+        if ppl_mode:                                           # easykv.py:896-901
+            ids, lg = torch.cat(all_ids), torch.cat(all_logits, dim=0)
+            lp = torch.nn.functional.cross_entropy(lg[:-1], ids[1:], reduction="none")
+            return math.exp(statistics.mean(lp.cpu().numpy().tolist()))
+        # ---- generation ------------------------------------------------------------------------------------
+        prob, _ = logits_adapter(logits[:, -1, :].float(), temperature, top_p)
+        output_ids, times = [], []
+        cur_pos = length
+        for _, _, st in decodes:                               # easykv.py:257-363 / :508-526 / :670-748
+            nxt = sample(prob)
+            output_ids.append(nxt[:, 0].tolist())
+            if bsz == 1 and output_ids[-1][0] in eos_token_ids:
+                break
+            t0 = time.time()
+            logits = forward(nxt, cur_pos, st)
+            prob, _ = logits_adapter(logits[:, -1, :].float(), temperature, top_p)
+            if report_decoding_latency:
+                torch.cuda.synchronize(device)
+                times.append(time.time() - t0)
+            cur_pos += 1
+        n_out = len(output_ids)
+        size = cache.n[0]
+        if plan.mode == "decoding":
+            kept = size - length
+            print(f"KV cache budget ratio: {kept / max(n_out, 1) * 100:.2f}%({kept}/{n_out})")
+        elif plan.mode == "encoding_decoding":
+            print(f"KV Cache Budget ratio {size / (length + n_out) * 100:.2f}%[{size}/({length}+{n_out})]")
+        if report_decoding_latency and len(times) > 1:
+            print(f"Per-step decoding latency: {statistics.mean(times[1:]):.3f}")
+    texts = [self.tokenizer.decode([step[b] for step in output_ids], skip_special_tokens=True).strip()
+             for b in range(bsz)]
+    return texts[0] if bsz == 1 else texts
+
+
+def enable_fixed_kv(model, tokenizer, mode, stride=1, verbose=False):
+    """easykv/easykv.py:903-908."""
+    if mode not in ("decoding", "encoding", "auto", "ppl", "encoding_decoding"):
+        raise ValueError(f"unknown mode {mode!r}")
+    model.tokenizer = tokenizer
+    model.easykv_generate = functools.partial(generate, self=model, kv_mode=mode, stride=stride,
+                                              report_decoding_latency=verbose)
+    model.easykv_ppl = functools.partial(generate, self=model, kv_mode="ppl", stride=stride)
+    print(f"Fixed KV Cache for {mode} enabled")

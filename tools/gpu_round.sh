@@ -13,7 +13,7 @@ echo "== bench" ; timeout 600 python bench.py 2>&1 | tail -2 | tee $OUT/${TAG}_b
 echo "== bench 32 seqs" ; timeout 600 python bench.py --seqs-per-gpu 32 --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/${TAG}_bench_b32.json
 echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>&1 | tail -1 | tee $OUT/${TAG}_bench_ref.json
 echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'decode_kernel|general_kernel|select_kernel|export_kernel|evict_explicit|tova_' -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > $OUT/${TAG}_launches_cmd.log 2>&1
 echo "== ncu full capture of the decode kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 40 -c 3 -f -o $OUT/${TAG}_decode \

@@ -1,0 +1,98 @@
+"""Kernel-level sweep over the BASELINE configs' geometries (development aid; bench.py is the contract).
+Prints one JSON line per case: per-launch time, algorithmic GB/s (SURVEY §8d formula) and fraction of the
+measured HBM roofline.
+
+    python tools/sweep.py [decode|chunk|all]
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from easykv_b200.cache import BudgetedKVCache  # noqa: E402
+from easykv_b200.plan import StepParams  # noqa: E402
+
+PEAK = 6538.0
+pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    PEAK = float(json.load(open(pk))["hbm_gbs"])
+A_POL = {"roco": 6, "h2o_head": 2, "tova": 1, "recency": 0, "full": 0}
+
+
+def bytes_alg(B, H, Hkv, d, n, q, policy, evict, e=2):
+    return B * (2 * Hkv * n * d * e + 2 * Hkv * q * d * e + 2 * H * q * d * e + A_POL[policy] * Hkv * n * 4 + Hkv * evict * 4)
+
+
+def steady_state(cache, l, n, dev):
+    B, Hkv = cache.B, cache.Hkv
+    cache.S[l][:, :, :n] = torch.rand(B, Hkv, n, device=dev) * cache.Cn[l][:, :, :n] / n
+    cache.SQ[l][:, :, :n] = cache.S[l][:, :, :n] ** 2 / cache.Cn[l][:, :, :n] * 1.5
+
+
+def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float16, kernel=0):
+    d, dev = 128, "cuda"
+    torch.manual_seed(0)
+    cache = BudgetedKVCache(L, B, H, Hkv, d, n + q_len, dtype=dtype)
+    for l in range(L):
+        cache.load_prefill(l, torch.randn(B, Hkv, n, d, device=dev, dtype=dtype), torch.randn(B, Hkv, n, d, device=dev, dtype=dtype),
+                           n, [float(n - i) for i in range(n)])
+        steady_state(cache, l, n, dev)
+    budget = n
+    if q_len == 1:
+        recent = int(budget * 0.3)
+        sp = StepParams(policy=policy, accumulate=policy in ("roco", "h2o_head", "tova"), evict=0 if policy == "full" else 1,
+                        counter_add=1.0, k_feasible=budget - recent, win_recent=recent if policy == "h2o_head" else 0, range_start=4)
+    else:
+        recent = int(budget * 0.1)
+        sp = StepParams(policy=policy, accumulate=policy in ("roco", "h2o_head", "tova"), evict=0 if policy == "full" else q_len,
+                        counter_add=float(q_len), c_new_step=1.0, k_feasible=max(budget - recent - 4, q_len), sink_protect=4,
+                        win_lo=4, win_recent=recent, range_start=4)
+    q = torch.randn(L, B, H, q_len, d, device=dev, dtype=dtype) * 0.3
+    kn = torch.randn(L, B, Hkv, q_len, d, device=dev, dtype=dtype)
+    vn = torch.randn(L, B, Hkv, q_len, d, device=dev, dtype=dtype)
+    for _ in range(3):
+        for l in range(L):
+            cache.step(l, sp, q[l], kn[l], vn[l], kernel=kernel)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        for l in range(L):
+            cache.step(l, sp, q[l], kn[l], vn[l], kernel=kernel)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (steps * L)
+    ba = bytes_alg(B, H, Hkv, d, n + q_len, q_len, policy, sp.evict, e=torch.empty(0, dtype=dtype).element_size())
+    gbs = ba / us / 1e3
+    print(json.dumps(dict(case=name, B=B, H=H, Hkv=Hkv, n=n, q_len=q_len, policy=policy, dtype=str(dtype).split(".")[1], kernel=kernel,
+                          us_per_launch=round(us, 1), bytes_alg=ba, GBps=round(gbs, 1), frac_of_measured=round(gbs / PEAK, 3))), flush=True)
+    del cache
+    torch.cuda.empty_cache()
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("decode", "all"):
+        # (name, B, H, Hkv, n) — decode step, roco
+        for name, B, H, Hkv, n in [("7B b1", 1, 32, 32, 1088), ("7B b8", 8, 32, 32, 1088), ("7B b32", 32, 32, 32, 1088),
+                                   ("7B b64", 64, 32, 32, 1088), ("13B n2112 b32", 32, 40, 40, 2112),
+                                   ("mistral n8208 b16", 16, 32, 8, 8208), ("70B n8256 b8", 8, 64, 8, 8256),
+                                   ("70B n8256 b32", 32, 64, 8, 8256), ("7B literal n4352 b16", 16, 32, 32, 4352)]:
+            run_case(name, B, H, Hkv, n, 1, "roco")
+        for pol in ("h2o_head", "tova", "recency", "full"):
+            run_case("13B sweep " + pol, 32, 40, 40, 2112, 1, pol)
+        run_case("7B b64 bf16", 64, 32, 32, 1088, 1, "roco", dtype=torch.bfloat16)
+        run_case("7B b32 general-kernel", 32, 32, 32, 1088, 1, "roco", kernel=1, steps=3)
+    if what in ("chunk", "all"):
+        for name, B, H, Hkv, n, q in [("C3 mistral stride16", 1, 32, 8, 8208, 16), ("C3 mistral stride16 b8", 8, 32, 8, 8208, 16),
+                                      ("C2 7B stride64", 1, 32, 32, 1088, 64), ("C2 7B stride64 b8", 8, 32, 32, 1088, 64),
+                                      ("C5 70B stride64", 1, 64, 8, 8256, 64)]:
+            pol = "h2o_head" if "C3" in name else "roco"
+            run_case(name, B, H, Hkv, n, q, pol, L=2, steps=3)
+
+
+if __name__ == "__main__":
+    main()
