@@ -27,10 +27,11 @@ int set_cuda_error(const char* what, cudaError_t err) {
 }
 static std::atomic<unsigned long long*> g_timeline{nullptr};
 unsigned long long* debug_timeline() { return g_timeline.load(std::memory_order_relaxed); }
-int decode_variant() {
-  static const int v = [] { const char* e = getenv("EKV_DECODE_VARIANT"); return e ? atoi(e) : 0; }();
-  return v;
-}
+// kernel-selection overrides (development / test hook): environment at load, ekv_debug_set_dispatch later
+static std::atomic<int> g_variant{[] { const char* e = getenv("EKV_DECODE_VARIANT"); return e ? atoi(e) : 0; }()};
+static std::atomic<int> g_cluster{[] { const char* e = getenv("EKV_DECODE_CLUSTER"); return e ? atoi(e) : 0; }()};
+int decode_variant() { return g_variant.load(std::memory_order_relaxed); }
+int decode_cluster_size() { return g_cluster.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static int build_args(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, KernelArgs& a) {
@@ -88,6 +89,10 @@ extern "C" {
 int ekv_abi_version(void) { return EKV_ABI_VERSION; }
 const char* ekv_last_error(void) { return g_err; }
 int64_t ekv_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size) {
+  g_variant.store(decode_variant, std::memory_order_relaxed);
+  g_cluster.store(cluster_size, std::memory_order_relaxed);
+}
 void ekv_debug_set_timeline(void* device_buffer) { g_timeline.store((unsigned long long*)device_buffer, std::memory_order_relaxed); }
 
 int64_t ekv_scratch_bytes(const ekv_shape* sh, const ekv_step* st) {

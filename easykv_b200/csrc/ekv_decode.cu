@@ -22,53 +22,9 @@
 // Replaces (reference paths): llama_patch.py:193-230 / mistral_patch.py:137-170 (cache append,
 // repeat_kv, QK^T, mask, softmax, PV) and easykv.py:271-362 / :683-748 (fold, accumulate, select,
 // truncate_kv_cache_silo, state compaction) for one layer of one decode forward.
-#include "ekv_select.cuh"
-#include "ekv_kernels.h"
+#include "ekv_decode_common.cuh"
 
 namespace ekv {
-
-template <typename T> struct DecodeCfg {
-  static constexpr int D = 128;
-  static constexpr int NWARP = 8;                       // consumer warps per group
-  static constexpr int NCONS = NWARP * 32;
-  static constexpr int MAX_GROUPS = 2;
-  static constexpr int ROW_BYTES = D * (int)sizeof(T);
-  static constexpr int TILE_BYTES = 16384;
-  static constexpr int TILE_ROWS = TILE_BYTES / ROW_BYTES;   // 64 (16-bit) / 32 (fp32)
-  static constexpr int RPT = TILE_ROWS / (NWARP * 2);        // rows per 16-lane group per tile
-  static constexpr int MAX_STAGES = 12;
-};
-
-// sum over the 16 lanes of a half-warp of NV per-lane values; afterwards lane l (< NV) of the
-// group holds the total of value index bitrev_{log2 NV}(l).  NV-1 + log2(16/NV) shuffles instead
-// of 4*NV.
-template <int NV> __device__ __forceinline__ float transpose_reduce16(float (&v)[NV], int l16) {
-  int bit = 1;
-#pragma unroll
-  for (int w = NV / 2; w >= 1; w >>= 1) {
-    const bool up = (l16 & bit) != 0;
-#pragma unroll
-    for (int i = 0; i < w; ++i) {
-      const float send = up ? v[i] : v[i + w];
-      const float keep = up ? v[i + w] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-    }
-    bit <<= 1;
-  }
-  float r = v[0];
-#pragma unroll
-  for (; bit < 16; bit <<= 1) r += __shfl_xor_sync(0xffffffffu, r, bit);
-  return r;
-}
-template <int NV> __device__ __forceinline__ int bitrev_idx(int l) {
-  int r = 0;
-#pragma unroll
-  for (int w = NV / 2, b = 1; w >= 1; w >>= 1, b <<= 1) r += (l & b) ? w : 0;
-  return r;
-}
-
-
-static inline __host__ __device__ int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 template <typename T> struct DecodeSmem {
   // byte offsets inside dynamic shared memory; g_* are relative to a consumer group's block
@@ -527,14 +483,32 @@ template <typename T> static int launch_decode_t(const KernelArgs& a, cudaStream
   }
 }
 
-int launch_decode(const KernelArgs& a, cudaStream_t stream) {
-  if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean) return EKV_ERR_UNSUPPORTED;
+int decode_cluster_size();   // ekv_api.cu (env EKV_DECODE_CLUSTER)
+
+static int launch_decode_single(const KernelArgs& a, cudaStream_t stream) {
   switch (a.dtype) {
     case EKV_F16: return launch_decode_t<__half>(a, stream);
     case EKV_BF16: return launch_decode_t<__nv_bfloat16>(a, stream);
     case EKV_F32: return launch_decode_t<float>(a, stream);
     default: return EKV_ERR_INVALID;
   }
+}
+
+// Dispatch between the two decode kernels: fewer units than half the SMs -> split each unit over a
+// cluster (ekv_decode_cluster.cu) so the whole chip streams; otherwise the persistent kernel above; and
+// the cluster kernel again for units too large for one CTA's shared memory.
+int launch_decode(const KernelArgs& a, cudaStream_t stream) {
+  if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean) return EKV_ERR_UNSUPPORTED;
+  if (a.st.evict <= 1) {
+    if (decode_cluster_size() > 0) return launch_decode_cluster(a, false, stream);
+    if (decode_cluster_size() == 0 && a.B * a.Hkv * 2 <= 148) {
+      const int rc = launch_decode_cluster(a, true, stream);
+      if (rc != EKV_ERR_UNSUPPORTED) return rc;
+    }
+  }
+  const int rc = launch_decode_single(a, stream);
+  if (rc != EKV_ERR_UNSUPPORTED || a.st.evict > 1) return rc;
+  return launch_decode_cluster(a, false, stream);
 }
 
 }  // namespace ekv

@@ -1,0 +1,675 @@
+// Fused decode step (q_len == 1), cluster-split variant: the key range of ONE (sequence, kv head) unit is
+// divided over the C CTAs of a thread-block cluster.  Used when a whole unit does not fit one CTA's shared
+// memory (long retained caches with large GQA groups: Mistral / Llama-2-70B layouts at 8K slots) or when
+// there are fewer units than SMs (small batches), where one CTA per unit would leave most of the chip idle.
+//
+// Per CTA (rank r of C): a TMA producer warp streams the CTA's slice of K rows, then of V rows, through an
+// mbarrier ring exactly as in ekv_decode.cu; 8 consumer warps compute the slice's logits, probabilities and
+// partial P·V.  What crosses CTAs goes through distributed shared memory (st.shared::cluster) bracketed by
+// cluster barriers:
+//   1. per-head slice maxima               (C x G floats, all-to-all)
+//   2. per-head slice sums of exp(x - max) (C x G floats, all-to-all)
+//   3. partial outputs, reduce-scattered by output dimension (each CTA finishes D/C dims of every head),
+//      together with each slice's best victim candidate (one 128-bit tuple)
+//   4. per attempt: the candidate's std rank (one int per CTA)              — roco only
+// Sums across CTAs are always formed in rank order, so every CTA derives bit-identical softmax
+// denominators and the result does not depend on arrival order.
+//
+// The victim is found exactly as in the single-CTA fast path (ekv_select.cuh): candidates are visited in
+// (mean, std, logical index) order and the first whose std rank is below k_feasible is taken — the slot
+// argmin-over-the-k-smallest-std picks (easykv/easykv.py:322-324, :722-724).  h2o_head / tova need one
+// cluster argmin (:311, :335); recency is positional (:343-347, :741-742).  Eviction renumbers each slice's
+// share of the slot map locally; rank 0 appends the new token.
+//
+// Replaces the same reference lines as ekv_decode.cu.
+#include "ekv_decode_common.cuh"
+
+namespace ekv {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_unaligned() {      // for a single thread of a diverged warp
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+template <typename T> struct ClusterSmem {
+  int off_bar, off_red, off_q, off_k, off_v, off_ns, off_lj, off_plog, off_ka, off_kb, off_flag;
+  int off_xmax, off_xsum, off_xout, off_xbest, off_xcnt, off_ring, fixed, slp;
+  __host__ __device__ ClusterSmem(int G, int slice, int C) {
+    using Cfg = DecodeCfg<T>;
+    const int NEl = slice + 1;                    // rank 0 also owns the appended token's entry
+    slp = align_up(NEl, 8);
+    int o = 0;
+    off_bar = o; o += 2 * Cfg::MAX_STAGES * 8;
+    o = align_up(o, 128);
+    off_red = o; o += 2 * 8 * Cfg::NWARP * 4 + 64 * 8 + 64 * 4;     // float maxima/sums | u64 tuples | int counts
+    off_q = o; o += G * Cfg::ROW_BYTES;
+    off_k = o; o += Cfg::ROW_BYTES;
+    off_v = o; o += Cfg::ROW_BYTES;
+    off_ns = o; o += 16;
+    off_lj = o; o += align_up(NEl * 4, 16);
+    off_plog = o; o += align_up(G * slp * (int)sizeof(T), 16);
+    off_ka = o; o += align_up(NEl * 4, 16);
+    off_kb = o; o += align_up(NEl * 4, 16);
+    off_flag = o; o += align_up(NEl, 16);
+    off_xmax = o; o += C * G * 4;
+    off_xsum = o; o += C * G * 4;
+    off_xout = o; o += G * Cfg::D * 4;            // [C][G][D/C]
+    off_xbest = align_up(o, 16); o = off_xbest + 2 * C * 16;
+    off_xcnt = o; o += 2 * C * 4;
+    o = align_up(o, 128);
+    off_ring = o;                                 // the ring doubles as the cross-warp P·V scratch [NWARP][G][D] fp32
+    fixed = o;
+  }
+  static __host__ __device__ int min_ring(int G) { return DecodeCfg<T>::NWARP * G * DecodeCfg<T>::D * 4; }
+};
+
+template <typename T, int G>
+__global__ void __launch_bounds__(DecodeCfg<T>::NCONS + 32, 1)
+decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
+  using Cfg = DecodeCfg<T>;
+  constexpr int D = Cfg::D, NWARP = Cfg::NWARP, NCONS = Cfg::NCONS, RPT = Cfg::RPT, TILE_ROWS = Cfg::TILE_ROWS;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+  const ClusterSmem<T> L(G, slice, C);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  uint64_t* empty = full + Cfg::MAX_STAGES;
+  unsigned char* ring = smem + L.off_ring;
+
+  const int unit = blockIdx.x / C;
+  const int n_phys = a.n_phys;
+  const int lo = min(rank * slice, n_phys), hi = min(lo + slice, n_phys);
+  const int nloc = hi - lo;                                   // physical slots of this CTA
+  const int NEl = nloc + (rank == 0 ? 1 : 0);                 // + the appended token on rank 0 (local index nloc)
+  const int slp = L.slp;
+  const int nt = (nloc + TILE_ROWS - 1) / TILE_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == NWARP) {
+    // ===== TMA producer ==============================================================================
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      const T* Kg = reinterpret_cast<const T*>(a.K) + ((size_t)unit * a.cap + lo) * D;
+      const T* Vg = reinterpret_cast<const T*>(a.V) + ((size_t)unit * a.cap + lo) * D;
+      int s = 0, use = 0;
+      bool synced = false;
+      for (int i = 0; i < 2 * nt; ++i) {
+        if (use > 0) {
+          // A slot last filled with a V tile is only released after the consumers have passed the two
+          // softmax cluster barriers.  A cluster barrier completes when every NON-EXITED thread of the
+          // cluster has arrived, so this thread has to take part in those two phases before it may
+          // block on such a slot (it exits before the later ones; exited threads are not waited for).
+          if (!synced && i - stages >= nt) {
+            cluster_sync_unaligned();
+            cluster_sync_unaligned();
+            synced = true;
+          }
+          mbar_wait(&empty[s], (use - 1) & 1);
+        }
+        const int tt = i < nt ? i : i - nt;
+        const int rows = min(TILE_ROWS, nloc - tt * TILE_ROWS);
+        const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
+        const T* src = (i < nt ? Kg : Vg) + (size_t)tt * TILE_ROWS * D;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        tma_bulk_g2s(ring + (size_t)s * Cfg::TILE_BYTES, src, bytes, &full[s], pol);
+        if (++s == stages) { s = 0; ++use; }
+      }
+    }
+    return;     // exited threads do not take part in the cluster barriers below
+  }
+
+  // ===== consumers ===================================================================================
+  const int tid = threadIdx.x;
+  const Grp grp{tid, NCONS, 1};
+  const int hw = tid >> 4, l16 = tid & 15;
+  float* red = reinterpret_cast<float*>(smem + L.off_red);
+  unsigned long long* red64 = reinterpret_cast<unsigned long long*>(smem + L.off_red + 2 * 8 * NWARP * 4);
+  int* redi = reinterpret_cast<int*>(smem + L.off_red + 2 * 8 * NWARP * 4 + 64 * 8);
+  T* qh = reinterpret_cast<T*>(smem + L.off_q);
+  T* kh = reinterpret_cast<T*>(smem + L.off_k);
+  T* vh = reinterpret_cast<T*>(smem + L.off_v);
+  int32_t* ns = reinterpret_cast<int32_t*>(smem + L.off_ns);
+  int32_t* lj = reinterpret_cast<int32_t*>(smem + L.off_lj);
+  T* plog = reinterpret_cast<T*>(smem + L.off_plog);
+  uint32_t* keyA = reinterpret_cast<uint32_t*>(smem + L.off_ka);
+  uint32_t* keyB = reinterpret_cast<uint32_t*>(smem + L.off_kb);
+  uint8_t* flag = smem + L.off_flag;
+  float* xmax = reinterpret_cast<float*>(smem + L.off_xmax);
+  float* xsum = reinterpret_cast<float*>(smem + L.off_xsum);
+  float* xout = reinterpret_cast<float*>(smem + L.off_xout);
+  unsigned long long* xbest = reinterpret_cast<unsigned long long*>(smem + L.off_xbest);
+  int* xcnt = reinterpret_cast<int*>(smem + L.off_xcnt);
+
+  auto finish_logit = [&](float dot, bool valid) -> T {
+    float x = Tr<T>::round_f(dot);                                           // llama_patch.py:201
+    x = a.st.arith ? __fmul_rn(x, a.scale_mul) : __fdiv_rn(x, a.scale_div);  // :202
+    return valid ? Tr<T>::from_f(x) : neg_inf<T>();
+  };
+
+  // ---- header ----------------------------------------------------------------------------------------
+  {
+    const uint4* qg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D);
+    const uint4* kg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_new) + (size_t)unit * D);
+    const uint4* vg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.v_new) + (size_t)unit * D);
+    constexpr int QCH = G * Cfg::ROW_BYTES / 16, RCH = Cfg::ROW_BYTES / 16;
+    for (int i = tid; i < QCH + 2 * RCH; i += NCONS) {
+      if (i < QCH) reinterpret_cast<uint4*>(qh)[i] = qg[i];
+      else if (i < QCH + RCH) reinterpret_cast<uint4*>(kh)[i - QCH] = kg[i - QCH];
+      else reinterpret_cast<uint4*>(vh)[i - QCH - RCH] = vg[i - QCH - RCH];
+    }
+    const int32_t* lg = a.lidx + (size_t)unit * a.cap + lo;
+    for (int e = tid; e < nloc; e += NCONS) lj[e] = lg[e];
+    if (tid == 0) {
+      ns[0] = a.new_slots ? a.new_slots[unit] : n_phys;
+      if (rank == 0) lj[nloc] = a.n_before;
+    }
+    if (a.st.policy != EKV_POLICY_NONE && a.st.policy != EKV_POLICY_RANGE) {
+      const int lines = (nloc * 4 + 127) / 128;
+      for (int i = tid; i < 3 * lines; i += NCONS) {
+        const float* base = (i < lines ? a.S : (i < 2 * lines ? a.SQ : a.C)) + (size_t)unit * a.cap + lo;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + (size_t)(i % lines) * 128));
+      }
+    }
+  }
+  grp.sync();
+  Row8<T> qr[G], knew;
+#pragma unroll
+  for (int g = 0; g < G; ++g) qr[g].load(qh + g * D, l16);
+  knew.load(kh, l16);
+
+  // ---- K phase (same structure as ekv_decode.cu) -----------------------------------------------------------
+  constexpr int NVT = RPT * G;
+  constexpr int TB = NVT >= 16 ? 1 : 16 / NVT;
+  constexpr int NB = NVT >= 16 ? NVT / 16 : 1;
+  static_assert(NVT * TB == 16 * NB, "batch must be a whole number of 16-value reductions");
+  const int vi0 = bitrev_idx<16>(l16);
+  float mloc = -INFINITY;
+  int s = 0;
+  uint32_t par = 0;
+  for (int i0 = 0; i0 < nt; i0 += TB) {
+    float part[NVT * TB];
+#pragma unroll
+    for (int tb = 0; tb < TB; ++tb) {
+      if (i0 + tb < nt) {
+        mbar_wait(&full[s], (par >> s) & 1u);
+        par ^= 1u << s;
+        const T* tile = reinterpret_cast<const T*>(ring + (size_t)s * Cfg::TILE_BYTES);
+        Row8<T> x[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) x[k].load(tile + (hw * RPT + k) * D, l16);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k)
+#pragma unroll
+          for (int g = 0; g < G; ++g) part[tb * NVT + k * G + g] = dot8(x[k], qr[g], 0.f);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        s = s + 1 == stages ? 0 : s + 1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NVT; ++j) part[tb * NVT + j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = part[b * 16 + j];
+      const float r = transpose_reduce16<16>(v, l16);
+      const int vi = b * 16 + vi0;
+      const int tb = vi / NVT, k = (vi % NVT) / G, g = vi % G;
+      const int e = (i0 + tb) * TILE_ROWS + hw * RPT + k;
+      if (e < nloc) {
+        const T x = finish_logit(r, lj[e] >= 0);
+        plog[g * slp + e] = x;
+        mloc = fmaxf(mloc, Tr<T>::to_f(x));
+      }
+    }
+  }
+  // the appended token's own key: rank 0 owns it (every half-warp computes it, the shuffles need all lanes)
+  float xnew[G];
+  {
+    float v[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) v[g] = dot8(knew, qr[g], 0.f);
+    const float r = transpose_reduce16<G>(v, l16);
+    const T x = finish_logit(r, true);
+    if (rank == 0 && hw == 0 && l16 < G) plog[bitrev_idx<G>(l16) * slp + nloc] = x;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float xv = __shfl_sync(0xffffffffu, Tr<T>::to_f(x), (lane & 16) | bitrev_idx<G>(g));
+      xnew[g] = rank == 0 ? xv : -INFINITY;
+    }
+  }
+
+  // ---- softmax across the cluster ------------------------------------------------------------------------
+  const int gw = warp;
+  float mx[G], inv[G];
+  {
+    const int my_g = vi0 % G;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float m = fmaxf(warp_max(my_g == g ? mloc : -INFINITY), xnew[g]);
+      if (lane == 0) red[g * NWARP + gw] = m;
+    }
+    grp.sync();
+    if (tid < G * C) {                                        // thread (g, p): this slice's max of head g -> peer p
+      const int g = tid / C, p = tid % C;
+      float v = red[g * NWARP];
+#pragma unroll
+      for (int w = 1; w < NWARP; ++w) v = fmaxf(v, red[g * NWARP + w]);
+      st_cluster_f32(map_to_rank(&xmax[rank * G + g], p), v);
+    }
+    cluster_sync_all();                                                             // (1)
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float v = xmax[g];
+      for (int p = 1; p < C; ++p) v = fmaxf(v, xmax[p * G + g]);
+      mx[g] = v;
+    }
+    float* red2 = red + 8 * NWARP;
+    float sacc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) sacc[g] = 0.f;
+    for (int e = tid; e < NEl; e += NCONS)
+#pragma unroll
+      for (int g = 0; g < G; ++g) sacc[g] += expf(Tr<T>::to_f(plog[g * slp + e]) - mx[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      sacc[g] = warp_sum(sacc[g]);
+      if (lane == 0) red2[g * NWARP + gw] = sacc[g];
+    }
+    grp.sync();
+    if (tid < G * C) {
+      const int g = tid / C, p = tid % C;
+      float v = red2[g * NWARP];
+#pragma unroll
+      for (int w = 1; w < NWARP; ++w) v += red2[g * NWARP + w];
+      st_cluster_f32(map_to_rank(&xsum[rank * G + g], p), v);
+    }
+    cluster_sync_all();                                                             // (2)
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float v = xsum[g];
+      for (int p = 1; p < C; ++p) v += xsum[p * G + g];                            // rank order on every CTA
+      inv[g] = a.st.arith ? v : __fdiv_rn(1.0f, v);
+    }
+    for (int e = tid; e < NEl; e += NCONS)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float ex = expf(Tr<T>::to_f(plog[g * slp + e]) - mx[g]);
+        plog[g * slp + e] = Tr<T>::from_f(a.st.arith ? __fdiv_rn(ex, inv[g]) : __fmul_rn(ex, inv[g]));   // llama_patch.py:218-219
+      }
+  }
+  grp.sync();
+
+  // ---- V phase ---------------------------------------------------------------------------------------------
+  float oacc[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) oacc[g][j] = 0.f;
+  for (int i = 0; i < nt; ++i) {
+    mbar_wait(&full[s], (par >> s) & 1u);
+    par ^= 1u << s;
+    const T* tile = reinterpret_cast<const T*>(ring + (size_t)s * Cfg::TILE_BYTES);
+    const int e0 = i * TILE_ROWS + hw * RPT;
+    Row8<T> x[RPT];
+    T pv[RPT][G];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      x[k].load(tile + (hw * RPT + k) * D, l16);
+#pragma unroll
+      for (int g = 0; g < G; ++g) pv[k][g] = plog[g * slp + min(e0 + k, slp - 1)];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    s = s + 1 == stages ? 0 : s + 1;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k)
+      if (e0 + k < nloc) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) axpy8(pv[k][g], x[k], oacc[g]);
+      }
+  }
+  if (rank == 0 && hw == 0) {
+    Row8<T> vnew;
+    vnew.load(vh, l16);
+#pragma unroll
+    for (int g = 0; g < G; ++g) axpy8(plog[g * slp + nloc], vnew, oacc[g]);
+  }
+  grp.sync();                       // every tile of this CTA has been consumed: the ring is free scratch now
+  {
+    float* part = reinterpret_cast<float*>(ring);             // [NWARP][G][D]
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = oacc[g][j] + __shfl_xor_sync(0xffffffffu, oacc[g][j], 16);
+        if (lane < 16) part[(gw * G + g) * D + dim_of<T>(l16, j)] = v;
+      }
+    grp.sync();
+    const int DPC = D / C;                                    // output dims finished by each CTA
+    for (int i = tid; i < G * D; i += NCONS) {
+      float v = part[i];
+#pragma unroll
+      for (int w = 1; w < NWARP; ++w) v += part[w * G * D + i];
+      const int g = i / D, dim = i % D;
+      st_cluster_f32(map_to_rank(&xout[(rank * G + g) * DPC + dim % DPC], dim / DPC), v);
+    }
+  }
+
+  // ---- tail, pass 1: this slice's policy state and selection keys ------------------------------------------------
+  const ekv_step& st = a.st;
+  const int P = st.score_offset;
+  const int n_after = a.n_before + 1, n_s = n_after - P;
+  const bool evicting = st.evict > 0 && st.policy != EKV_POLICY_NONE;
+  float* Sg = a.S + (size_t)unit * a.cap;
+  float* SQg = a.SQ + (size_t)unit * a.cap;
+  float* Cg = a.C + (size_t)unit * a.cap;
+  int32_t* lidx_g = a.lidx + (size_t)unit * a.cap;
+  const float inv_g = 1.0f / (float)G;
+  auto phys_of = [&](int e) { return e >= nloc ? ns[0] : lo + e; };
+  {
+    constexpr int FCH = 5;
+    for (int base = 0; base < NEl; base += FCH * NCONS) {
+      float sv[FCH], sq[FCH], cc[FCH], ds[FCH], dsq[FCH];
+      int rl[FCH];
+#pragma unroll
+      for (int k = 0; k < FCH; ++k) {
+        const int e = base + k * NCONS + tid;
+        rl[k] = -1; sv[k] = 0.f; sq[k] = 0.f; cc[k] = 1.f; ds[k] = 0.f; dsq[k] = 0.f;
+        if (e < NEl) {
+          if (e >= nloc) {
+            rl[k] = a.n_before;
+            cc[k] = st.c_new0;
+          } else {
+            rl[k] = lj[e];
+            if (rl[k] >= P) { sv[k] = Sg[lo + e]; sq[k] = SQg[lo + e]; cc[k] = Cg[lo + e]; }
+          }
+          if (st.accumulate) {
+            float pf;
+            if (G == 1) pf = Tr<T>::to_f(plog[e]);
+            else {                                                  // process_for_mqa_gqa, easykv.py:188-196
+              float sum = 0.f;
+#pragma unroll
+              for (int g = 0; g < G; ++g) sum += Tr<T>::to_f(plog[g * slp + e]);
+              pf = Tr<T>::round_f(__fmul_rn(sum, inv_g));
+            }
+            ds[k] = pf;
+            dsq[k] = Tr<T>::round_f(__fmul_rn(pf, pf));             // p**2 in the model dtype, easykv.py:296
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < FCH; ++k) {
+        const int e = base + k * NCONS + tid;
+        if (e >= NEl) continue;
+        uint32_t ka = 0, kb = 0;
+        uint8_t f = 0;
+        bool dirty = false;
+        if (rl[k] >= 0 && rl[k] >= P)
+          entry_update(st, rl[k] - P, n_s, e >= nloc, ds[k], dsq[k], sv[k], sq[k], cc[k], ka, kb, f, dirty);
+        if (dirty) { const int ph = phys_of(e); Sg[ph] = sv[k]; SQg[ph] = sq[k]; Cg[ph] = cc[k]; }
+        keyA[e] = ka; keyB[e] = kb; flag[e] = f;
+      }
+    }
+  }
+  grp.sync();
+
+  // ---- select across the cluster ------------------------------------------------------------------------------------
+  const bool single = evicting && st.policy != EKV_POLICY_RANGE;
+  const uint8_t need_flag = st.policy == EKV_POLICY_ROCO ? F_CAND : F_FEAS;
+  bool found = false;
+  uint32_t l_c = 0;
+  int owner = -1, e_c = -1;
+  auto local_best = [&]() {
+    Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
+    for (int e = tid; e < NEl; e += NCONS) {
+      if ((flag[e] & (need_flag | F_REJ)) == need_flag) {
+        Tuple128 t;
+        t.hi = ((unsigned long long)keyB[e] << 32) | keyA[e];
+        t.lo = ((unsigned long long)(uint32_t)lj[e] << 32) | ((uint32_t)rank << 24) | (uint32_t)e;
+        if (tuple_less(t, best)) best = t;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Tuple128 t;
+      t.hi = __shfl_xor_sync(0xffffffffu, best.hi, o);
+      t.lo = __shfl_xor_sync(0xffffffffu, best.lo, o);
+      if (tuple_less(t, best)) best = t;
+    }
+    if (lane == 0) { red64[2 * gw] = best.hi; red64[2 * gw + 1] = best.lo; }
+    grp.sync();
+    if (tid < C) {                                            // thread p forwards the CTA's best to peer p
+      Tuple128 b; b.hi = red64[0]; b.lo = red64[1];
+      for (int w = 1; w < NWARP; ++w) {
+        Tuple128 t; t.hi = red64[2 * w]; t.lo = red64[2 * w + 1];
+        if (tuple_less(t, b)) b = t;
+      }
+      return b;
+    }
+    Tuple128 none; none.hi = ~0ull; none.lo = ~0ull;
+    return none;
+  };
+  int attempt = 0;
+  if (single) {
+    const Tuple128 b = local_best();
+    if (tid < C) {
+      const uint32_t dst = map_to_rank(&xbest[(0 * C + rank) * 2], tid);
+      st_cluster_u64(dst, b.hi);
+      st_cluster_u64(dst + 8, b.lo);
+    }
+  }
+  cluster_sync_all();                                                               // (3) partial outputs + candidates
+  {
+    // finish this CTA's share of the output: dims [rank*DPC, (rank+1)*DPC) of every head (llama_patch.py:222)
+    const int DPC = D / C;
+    T* og = reinterpret_cast<T*>(a.out) + (size_t)unit * G * D;
+    for (int i = tid; i < G * DPC; i += NCONS) {
+      const int g = i / DPC, dd = i % DPC;
+      float v = xout[(0 * G + g) * DPC + dd];
+      for (int p = 1; p < C; ++p) v += xout[(p * G + g) * DPC + dd];
+      og[g * D + rank * DPC + dd] = Tr<T>::from_f(v);
+    }
+    // rank 0 appends the new row: every CTA of the cluster is past its V stream
+    if (rank == 0 && hw == 0) {
+      const int slot = ns[0];
+      float x[8];
+      load_row8<T>(kh, l16, x);
+      store_row8<T>(reinterpret_cast<T*>(a.K) + ((size_t)unit * a.cap + slot) * D, l16, x);
+      load_row8<T>(vh, l16, x);
+      store_row8<T>(reinterpret_cast<T*>(a.V) + ((size_t)unit * a.cap + slot) * D, l16, x);
+    }
+  }
+  if (single) {
+    while (true) {
+      const int pb = attempt & 1;
+      Tuple128 best; best.hi = xbest[(pb * C) * 2]; best.lo = xbest[(pb * C) * 2 + 1];
+      for (int p = 1; p < C; ++p) {
+        Tuple128 t; t.hi = xbest[(pb * C + p) * 2]; t.lo = xbest[(pb * C + p) * 2 + 1];
+        if (tuple_less(t, best)) best = t;
+      }
+      if (best.lo == ~0ull) break;                            // no candidate left
+      const uint32_t ka_c = (uint32_t)(best.hi & 0xffffffffu);
+      l_c = (uint32_t)(best.lo >> 32);
+      owner = (int)((best.lo >> 24) & 0xffu);
+      e_c = (int)(best.lo & 0xffffffu);
+      if (st.policy != EKV_POLICY_ROCO) { found = true; break; }
+      int cnt = 0;                                            // this slice's share of the candidate's std rank
+      for (int e = tid; e < NEl; e += NCONS)
+        cnt += ((flag[e] & F_CAND) && (keyA[e] < ka_c || (keyA[e] == ka_c && (uint32_t)lj[e] < l_c))) ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) redi[pb * 32 + gw] = cnt;
+      grp.sync();
+      if (tid < C) {
+        int tot = 0;
+        for (int w = 0; w < NWARP; ++w) tot += redi[pb * 32 + w];
+        st_cluster_u32(map_to_rank(&xcnt[pb * C + rank], tid), (uint32_t)tot);
+      }
+      cluster_sync_all();                                                           // (4a)
+      int rk = 0;
+      for (int p = 0; p < C; ++p) rk += xcnt[pb * C + p];
+      if (rk < st.k_feasible) { found = true; break; }
+      // rejected: the owner drops it and every CTA publishes its next best
+      if (rank == owner && tid == 0) flag[e_c] |= F_REJ;
+      grp.sync();
+      ++attempt;
+      const Tuple128 b = local_best();
+      if (tid < C) {
+        const uint32_t dst = map_to_rank(&xbest[((attempt & 1) * C + rank) * 2], tid);
+        st_cluster_u64(dst, b.hi);
+        st_cluster_u64(dst + 8, b.lo);
+      }
+      cluster_sync_all();                                                           // (4b)
+    }
+  } else if (evicting) {                                      // RANGE with one victim: positional
+    l_c = (uint32_t)(P + st.range_start);
+    found = true;
+  }
+
+  // ---- apply: renumber this slice, free the victim's slot, publish the new slot ----------------------------------------
+  const bool is_range = evicting && st.policy == EKV_POLICY_RANGE;
+  for (int e = tid; e < NEl; e += NCONS) {
+    const int l = lj[e];
+    if (l < 0) continue;
+    const int phys = phys_of(e);
+    const bool victim = found && (is_range ? (uint32_t)l == l_c : (rank == owner && e == e_c));
+    if (victim) {
+      if (a.victim_lidx) a.victim_lidx[unit] = l;
+      if (a.victim_slots) a.victim_slots[unit] = phys;
+      if (st.apply) lidx_g[phys] = -1;
+      else if (e >= nloc) lidx_g[phys] = l;
+    } else if (found && st.apply && (uint32_t)l > l_c) {
+      lidx_g[phys] = l - 1;
+    } else if (e >= nloc) {
+      lidx_g[phys] = l;
+    }
+  }
+  if (evicting && !found && rank == 0 && tid == 0) {          // degenerate: no candidate (rejected by validation normally)
+    if (a.victim_lidx) a.victim_lidx[unit] = -1;
+    if (a.victim_slots) a.victim_slots[unit] = -1;
+  }
+  // peers may still be reading what this CTA was sent, never what it owns: no remote access follows, but a
+  // CTA must not exit while others can still write into it
+  cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int G>
+static int launch_cluster_tg(const KernelArgs& a, int C, int slice, int stages, int smem_bytes, cudaStream_t stream) {
+  static thread_local int configured[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
+  cudaError_t err;
+  if (!configured[dev]) {
+    err = cudaFuncSetAttribute(decode_cluster_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(decode_cluster)", err);
+    configured[dev] = 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a.B * a.Hkv * C), 1, 1);
+  cfg.blockDim = dim3(DecodeCfg<T>::NCONS + 32, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  err = cudaLaunchKernelEx(&cfg, decode_cluster_kernel<T, G>, a, stages, slice);
+  if (err != cudaSuccess) return set_cuda_error("decode_cluster_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+// Chooses the cluster size: the smallest power of two for which a slice fits one CTA, doubled while the
+// grid still fits the chip in one wave (more CTAs = more of the chip's HBM bandwidth in flight).
+template <typename T, int G> static int plan_cluster(const KernelArgs& a, int sms, int force_c, int& C, int& slice, int& stages, int& smem) {
+  using Cfg = DecodeCfg<T>;
+  const int U = a.B * a.Hkv, sm_total = 227 * 1024;
+  auto fits = [&](int c, int& sl, int& stg, int& bytes) {
+    sl = align_up((a.n_phys + c - 1) / c, 8);
+    if (sl < 8) sl = 8;
+    const ClusterSmem<T> L(G, sl, c);
+    int ring = sm_total - L.fixed;
+    if (ring < ClusterSmem<T>::min_ring(G) || ring < 3 * Cfg::TILE_BYTES) return false;
+    stg = ring / Cfg::TILE_BYTES;
+    if (stg > Cfg::MAX_STAGES) stg = Cfg::MAX_STAGES;
+    const int tiles = 2 * ((sl + Cfg::TILE_ROWS - 1) / Cfg::TILE_ROWS);
+    if (stg > tiles) stg = tiles < 3 ? 3 : tiles;
+    bytes = L.fixed + stg * Cfg::TILE_BYTES;
+    if (bytes < L.fixed + ClusterSmem<T>::min_ring(G)) bytes = L.fixed + ClusterSmem<T>::min_ring(G);
+    return true;
+  };
+  int best = 0;
+  for (int c = 1; c <= 8; c *= 2) {
+    if (force_c && c != force_c) continue;
+    int sl, stg, bytes;
+    if (!fits(c, sl, stg, bytes)) continue;
+    if (best && !force_c && (U * c > sms || sl < 2 * Cfg::TILE_ROWS)) break;      // keep one wave, keep slices non-trivial
+    best = c; C = c; slice = sl; stages = stg; smem = bytes;
+  }
+  return best ? EKV_OK : EKV_ERR_UNSUPPORTED;
+}
+
+int decode_cluster_size();   // ekv_api.cu (env EKV_DECODE_CLUSTER): 0 = automatic, else forced cluster size
+
+template <typename T, int G> static int launch_cluster_plan(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
+  static thread_local int sm_count[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
+  if (!sm_count[dev]) {
+    cudaError_t err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return set_cuda_error("cudaDeviceGetAttribute", err);
+  }
+  int C = 0, slice = 0, stages = 0, smem = 0;
+  const int rc = plan_cluster<T, G>(a, sm_count[dev], decode_cluster_size(), C, slice, stages, smem);
+  if (rc) return rc;
+  if (only_if_better && C == 1) return EKV_ERR_UNSUPPORTED;   // the single-CTA kernels serve this shape
+  return launch_cluster_tg<T, G>(a, C, slice, stages, smem, stream);
+}
+
+template <typename T> static int launch_cluster_t(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
+  switch (a.H / a.Hkv) {
+    case 1: return launch_cluster_plan<T, 1>(a, only_if_better, stream);
+    case 2: return launch_cluster_plan<T, 2>(a, only_if_better, stream);
+    case 4: return launch_cluster_plan<T, 4>(a, only_if_better, stream);
+    case 8: return launch_cluster_plan<T, 8>(a, only_if_better, stream);
+    default: return EKV_ERR_UNSUPPORTED;
+  }
+}
+
+// `only_if_better`: decline (EKV_ERR_UNSUPPORTED) when the plan degenerates to one CTA per unit.
+int launch_decode_cluster(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
+  if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean || a.st.evict > 1) return EKV_ERR_UNSUPPORTED;
+  switch (a.dtype) {
+    case EKV_F16: return launch_cluster_t<__half>(a, only_if_better, stream);
+    case EKV_BF16: return launch_cluster_t<__nv_bfloat16>(a, only_if_better, stream);
+    case EKV_F32: return launch_cluster_t<float>(a, only_if_better, stream);
+    default: return EKV_ERR_INVALID;
+  }
+}
+
+}  // namespace ekv

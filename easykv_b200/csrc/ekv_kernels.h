@@ -28,6 +28,7 @@ int set_error(int code, const char* fmt, ...);
 void count_launch();
 
 int launch_decode(const KernelArgs& a, cudaStream_t stream);      // ekv_decode.cu
+int launch_decode_cluster(const KernelArgs& a, bool only_if_better, cudaStream_t stream);   // ekv_decode_cluster.cu
 int launch_general(const KernelArgs& a, cudaStream_t stream);     // ekv_chunk.cu
 int launch_select(const KernelArgs& a, cudaStream_t stream);      // ekv_aux.cu
 int launch_tova_head_mean(const KernelArgs& a, cudaStream_t stream);

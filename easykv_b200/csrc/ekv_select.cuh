@@ -133,6 +133,39 @@ __device__ __forceinline__ bool tuple_less(const Tuple128& a, const Tuple128& b)
   return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
 }
 
+// One scored entry's share of a forward: policy-state update (accumulate, counter) and, when evicting,
+// its selection keys and candidate flags.  j = logical index relative to score_offset, n_s = scored
+// slots after the append.  Shared by every kernel so that the arithmetic is the same everywhere.
+__device__ __forceinline__ void entry_update(const ekv_step& st, int j, int n_s, bool is_new, float ds, float dsq,
+                                             float& s, float& sq, float& cc, uint32_t& ka, uint32_t& kb, uint8_t& f,
+                                             bool& dirty) {
+  const int policy = st.policy;
+  const bool evicting = st.evict > 0;
+  ka = 0; kb = 0; f = 0;
+  dirty = is_new;
+  if (st.accumulate) {
+    if (policy == EKV_POLICY_ROCO) { s = __fadd_rn(s, ds); sq = __fadd_rn(sq, dsq); dirty = true; }
+    else if (policy == EKV_POLICY_H2O) { s = __fadd_rn(s, ds); dirty = true; }
+    else if (policy == EKV_POLICY_TOVA) { s = ds; dirty = true; }
+  }
+  if (evicting && st.counter_add != 0.f) { cc = __fadd_rn(cc, st.counter_add); dirty = true; }
+  if (evicting) {
+    if (policy == EKV_POLICY_ROCO) {
+      const float mean = __fdiv_rn(s, cc);
+      float sd = __fsqrt_rn(__fsub_rn(__fdiv_rn(sq, cc), __fmul_rn(mean, mean)));
+      if (j >= n_s - st.protect_last || j < st.sink_protect) sd = 1e9f;
+      ka = order_key(sd);
+      kb = order_key(mean);
+      f = F_CAND;
+    } else if (policy == EKV_POLICY_H2O || policy == EKV_POLICY_TOVA) {
+      kb = order_key(s);
+      if (j >= st.win_lo && j < n_s - st.win_recent) f = F_CAND | F_FEAS;
+    } else if (policy == EKV_POLICY_RANGE) {
+      if (j >= st.range_start && j < st.range_start + st.evict) f = F_CAND | F_FEAS | F_CHOSEN;
+    }
+  }
+}
+
 // Acc: void operator()(int e, float& ds, float& dsq) — this forward's (folded, rounded)
 // contribution of entry e to S and SQ.
 template <class Acc>
@@ -183,32 +216,9 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
 #pragma unroll
     for (int k = 0; k < FCH; ++k) {
       const int e = base + k * g.n + g.tid;
-      const int j = rl[k] - P;
       rka[k] = 0; rkb[k] = 0; rf[k] = 0; dirty[k] = false;
-      if (e < NE && rl[k] >= 0 && j >= 0) {
-        dirty[k] = e >= n_phys;
-        if (st.accumulate) {
-          if (policy == EKV_POLICY_ROCO) { s[k] = __fadd_rn(s[k], ds[k]); sq[k] = __fadd_rn(sq[k], dsq[k]); dirty[k] = true; }
-          else if (policy == EKV_POLICY_H2O) { s[k] = __fadd_rn(s[k], ds[k]); dirty[k] = true; }
-          else if (policy == EKV_POLICY_TOVA) { s[k] = ds[k]; dirty[k] = true; }
-        }
-        if (evicting && st.counter_add != 0.f) { cc[k] = __fadd_rn(cc[k], st.counter_add); dirty[k] = true; }
-        if (evicting) {
-          if (policy == EKV_POLICY_ROCO) {
-            const float mean = __fdiv_rn(s[k], cc[k]);
-            float sd = __fsqrt_rn(__fsub_rn(__fdiv_rn(sq[k], cc[k]), __fmul_rn(mean, mean)));
-            if (j >= n_s - st.protect_last || j < st.sink_protect) sd = 1e9f;
-            rka[k] = order_key(sd);
-            rkb[k] = order_key(mean);
-            rf[k] = F_CAND;
-          } else if (policy == EKV_POLICY_H2O || policy == EKV_POLICY_TOVA) {
-            rkb[k] = order_key(s[k]);
-            if (j >= st.win_lo && j < n_s - st.win_recent) rf[k] = F_CAND | F_FEAS;
-          } else if (policy == EKV_POLICY_RANGE) {
-            if (j >= st.range_start && j < st.range_start + st.evict) rf[k] = F_CAND | F_FEAS | F_CHOSEN;
-          }
-        }
-      }
+      if (e < NE && rl[k] >= 0 && rl[k] >= P)
+        entry_update(st, rl[k] - P, n_s, e >= n_phys, ds[k], dsq[k], s[k], sq[k], cc[k], rka[k], rkb[k], rf[k], dirty[k]);
     }
 #pragma unroll
     for (int k = 0; k < FCH; ++k) {

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EKV_ABI_VERSION 2
+#define EKV_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define EKV_API __attribute__((visibility("default")))
@@ -166,6 +166,12 @@ EKV_API int64_t ekv_launch_count(void);
  * phase boundaries (unit start, header, first tile, K phase, softmax, V phase, out, tail) plus the
  * CTA's start %globaltimer in slot [cta][15][7].  NULL (the default) disables it. */
 EKV_API void ekv_debug_set_timeline(void* device_buffer);
+
+/* Kernel-selection override (development / test hook, not part of the data path).
+ * decode_variant: 0 = automatic, 1 = one consumer group per CTA, 2 = ping-pong groups (ekv_decode.cu).
+ * cluster_size:   0 = automatic, -1 = never use the cluster-split decode kernel, 1/2/4/8 = always use it with
+ *                 this many CTAs per (sequence, kv head) (ekv_decode_cluster.cu). */
+EKV_API void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,20 @@ def test_golden_replay(engines, name, kernel):
     assert rep.max_out_err <= tol, rep.max_out_err
 
 
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("name", [n for n in CASES if "auto" in n or "decoding" in n])
+def test_golden_replay_cluster_kernel(engines, dispatch, name, cluster):
+    """The decode steps of the reference's runs through the cluster-split kernel (chunks still go through
+    the general kernel): same ids, same cache."""
+    dispatch(0, cluster)
+    rep = replay.replay(name, lambda *a: engines.CudaEngine(*a), resync=True, shadow=replay.OracleEngine)
+    assert rep.n_events > 0 and not rep.victim_mismatch, rep.victim_mismatch[:2]
+    for f, l, ref, got, margin in rep.tie_ambiguous:
+        assert min(margin) == 0.0 and "fp32" not in name
+    assert len(rep.tie_ambiguous) <= 1 and rep.final_cache_equal
+    assert rep.max_out_err <= (2e-6 if "fp32" in name else 1e-3)
+
+
 def test_c1_free_running(engines):
     """BASELINE configs[0] without re-synchronisation: the CUDA path's own evictions, start to end."""
     rep = replay.replay("c1_llama_enc_roco_fp32", lambda *a: engines.CudaEngine(*a), resync=False)
@@ -100,11 +114,23 @@ def test_select_matches_oracle(ekv_lib, policy, evict, n, quant):
 # ------------------------------------------------------------------------------------------------
 # 3. fused decode kernel vs the CPU restatement on random inputs (MHA / GQA, fp16 / bf16 / fp32)
 # ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def dispatch(ekv_lib):
+    """Force a decode kernel: dispatch(variant, cluster) (ekv_debug_set_dispatch); automatic again afterwards."""
+    yield ekv_lib.ekv_debug_set_dispatch
+    ekv_lib.ekv_debug_set_dispatch(0, 0)
+
+
+@pytest.mark.parametrize("cluster", [-1, 0, 1, 2, 4, 8], ids=lambda c: f"cluster{c}")
 @pytest.mark.parametrize("dtype,H,Hkv,policy", [
     (torch.float16, 8, 8, "roco"), (torch.float16, 8, 2, "roco"), (torch.bfloat16, 8, 1, "h2o_head"),
     (torch.float32, 4, 4, "roco"), (torch.float32, 8, 4, "tova"), (torch.float16, 16, 2, "roco"),
+    (torch.float16, 4, 4, "recency"),
 ])
-def test_decode_random_vs_oracle(engines, dtype, H, Hkv, policy):
+def test_decode_random_vs_oracle(engines, dispatch, dtype, H, Hkv, policy, cluster):
+    """cluster: -1 = single-CTA kernels only, 0 = automatic, 1/2/4/8 = the cluster-split kernel with that many
+    CTAs per (sequence, kv head)."""
+    dispatch(0, cluster)
     d, n0, steps = 128, 203, 24
     g = torch.Generator().manual_seed(7)
     rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
@@ -116,7 +142,7 @@ def test_decode_random_vs_oracle(engines, dtype, H, Hkv, policy):
         e.load_prefill(0, K, V, n0, C0)
     recent = int(n0 * 0.3)
     st = restate.Step(policy=policy, accumulate=True, evict=1, counter_add=1.0, k_feasible=n0 - recent,
-                      win_recent=recent if policy == "h2o_head" else 0)
+                      win_recent=recent if policy == "h2o_head" else 0, range_start=4)
     bad = 0
     for t in range(steps):
         q, k, v = rnd(H, 1, d) * 0.3, rnd(Hkv, 1, d), rnd(Hkv, 1, d)
@@ -175,6 +201,49 @@ def test_full_size_decode_properties(ekv_lib):
     srt = torch.sort(lidx, dim=-1)[0]
     assert torch.equal(srt[..., -n:], torch.arange(n, device=dev, dtype=torch.int32).expand(B, Hkv, n))
     assert int(srt[..., :-n].max()) == -1
+
+
+@pytest.mark.parametrize("B,H,Hkv,n,cluster", [(2, 64, 8, 8256, 0), (1, 32, 8, 8208, 0), (1, 32, 32, 1088, 0),
+                                               (3, 32, 32, 1088, 8), (2, 64, 8, 4100, 4)])
+def test_long_gqa_decode_properties(ekv_lib, dispatch, B, H, Hkv, n, cluster):
+    """Shapes served by the cluster-split kernel (BASELINE configs[2]/[4] geometries: Mistral n=8208, 70B
+    n=8256; and small batches of the 7B layout): outputs vs fp32 torch attention, victims never among the 10
+    newest, the exported cache equals an order-preserving deletion replay, the slot map stays a permutation,
+    and the trajectory agrees with the single-CTA general kernel."""
+    from easykv_b200.cache import BudgetedKVCache
+    from easykv_b200.plan import StepParams
+    dispatch(0, cluster)
+    d, steps, dev = 128, 6, "cuda"
+    torch.manual_seed(5)
+    caches = [BudgetedKVCache(1, B, H, Hkv, d, n + 1, dtype=torch.float16) for _ in range(2)]
+    K0 = torch.randn(B, Hkv, n, d, device=dev).half(); V0 = torch.randn(B, Hkv, n, d, device=dev).half()
+    for c in caches:
+        c.load_prefill(0, K0, V0, n, [float(n - i) for i in range(n)])
+    sp = StepParams(policy="roco", accumulate=True, evict=1, counter_add=1.0, k_feasible=n - int(n * 0.3))
+    Kl, Vl = K0.clone(), V0.clone()
+    g = H // Hkv
+    agree = 0
+    for t in range(steps):
+        q = torch.randn(B, H, 1, d, device=dev).half() * 0.2
+        k = torch.randn(B, Hkv, 1, d, device=dev).half(); v = torch.randn(B, Hkv, 1, d, device=dev).half()
+        out, vl = caches[0].step(0, sp, q, k, v)
+        out1, vl1 = caches[1].step(0, sp, q, k, v, apply=False, kernel=1)
+        caches[1].evict(0, vl)
+        agree += int(torch.equal(vl, vl1))
+        assert (out.float() - out1.float()).abs().max().item() <= 1e-3
+        Kl, Vl = torch.cat([Kl, k], 2), torch.cat([Vl, v], 2)
+        Kr = Kl.float().repeat_interleave(g, dim=1); Vr = Vl.float().repeat_interleave(g, dim=1)
+        w = torch.softmax((q.float() @ Kr.transpose(2, 3)) / math.sqrt(d), -1)
+        assert (out.float() - w @ Vr).abs().max().item() <= 2e-3
+        keep = torch.ones(B, Hkv, n + 1, dtype=torch.bool, device=dev)
+        keep.scatter_(2, vl.long(), False)
+        Kl = Kl[keep].view(B, Hkv, n, d); Vl = Vl[keep].view(B, Hkv, n, d)
+        assert int(vl.max()) <= n - 10 and int(vl.min()) >= 0
+    assert agree >= steps - 1
+    Ke, Ve = caches[0].export(0)
+    assert torch.equal(Ke, Kl) and torch.equal(Ve, Vl)
+    srt = torch.sort(caches[0].lidx[0], dim=-1)[0]
+    assert torch.equal(srt[..., -n:], torch.arange(n, device=dev, dtype=torch.int32).expand(B, Hkv, n))
 
 
 def test_errors_are_python_exceptions(ekv_lib):

@@ -32,10 +32,11 @@ def steady_state(cache, l, n, dev):
     cache.SQ[l][:, :, :n] = cache.S[l][:, :, :n] ** 2 / cache.Cn[l][:, :, :n] * 1.5
 
 
-def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float16, kernel=0):
+def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float16, kernel=0, cluster=0, variant=0):
     d, dev = 128, "cuda"
     torch.manual_seed(0)
-    cache = BudgetedKVCache(L, B, H, Hkv, d, n + q_len, dtype=dtype)
+    cache = BudgetedKVCache(L, B, H, Hkv, d, n + q_len * (1 if policy != "full" else 3 + steps + 1), dtype=dtype)
+    cache.lib.ekv_debug_set_dispatch(variant, cluster)
     for l in range(L):
         cache.load_prefill(l, torch.randn(B, Hkv, n, d, device=dev, dtype=dtype), torch.randn(B, Hkv, n, d, device=dev, dtype=dtype),
                            n, [float(n - i) for i in range(n)])
@@ -67,8 +68,9 @@ def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float
     us = e0.elapsed_time(e1) * 1e3 / (steps * L)
     ba = bytes_alg(B, H, Hkv, d, n + q_len, q_len, policy, sp.evict, e=torch.empty(0, dtype=dtype).element_size())
     gbs = ba / us / 1e3
-    print(json.dumps(dict(case=name, B=B, H=H, Hkv=Hkv, n=n, q_len=q_len, policy=policy, dtype=str(dtype).split(".")[1], kernel=kernel,
+    print(json.dumps(dict(case=name, B=B, H=H, Hkv=Hkv, n=n, q_len=q_len, policy=policy, dtype=str(dtype).split(".")[1], kernel=kernel, cluster=cluster, variant=variant,
                           us_per_launch=round(us, 1), bytes_alg=ba, GBps=round(gbs, 1), frac_of_measured=round(gbs / PEAK, 3))), flush=True)
+    cache.lib.ekv_debug_set_dispatch(0, 0)
     del cache
     torch.cuda.empty_cache()
 
@@ -86,6 +88,23 @@ def main():
             run_case("13B sweep " + pol, 32, 40, 40, 2112, 1, pol)
         run_case("7B b64 bf16", 64, 32, 32, 1088, 1, "roco", dtype=torch.bfloat16)
         run_case("7B b32 general-kernel", 32, 32, 32, 1088, 1, "roco", kernel=1, steps=3)
+    if what in ("cluster",):
+        for B in (1, 2, 4):
+            for c in (-1, 0, 2, 4, 8):
+                run_case(f"7B b{B}", B, 32, 32, 1088, 1, "roco", cluster=c)
+        for c in (-1, 1, 2, 4):
+            run_case("mistral n8208 b16", 16, 32, 8, 8208, 1, "roco", cluster=c)
+        for c in (0, 2, 4, 8):
+            run_case("mistral n8208 b4", 4, 32, 8, 8208, 1, "roco", cluster=c)
+        for B in (8, 32):
+            for c in (0, 4, 8):
+                run_case(f"70B n8256 b{B}", B, 64, 8, 8256, 1, "roco", cluster=c)
+        for c in (-1, 2, 4):
+            run_case("7B literal n4352 b16", 16, 32, 32, 4352, 1, "roco", cluster=c)
+        for c in (-1, 1, 2):
+            run_case("13B n2112 b32", 32, 40, 40, 2112, 1, "roco", cluster=c)
+        for c in (-1, 1, 2):
+            run_case("7B b64", 64, 32, 32, 1088, 1, "roco", cluster=c)
     if what in ("chunk", "all"):
         for name, B, H, Hkv, n, q in [("C3 mistral stride16", 1, 32, 8, 8208, 16), ("C3 mistral stride16 b8", 8, 32, 8, 8208, 16),
                                       ("C2 7B stride64", 1, 32, 32, 1088, 64), ("C2 7B stride64 b8", 8, 32, 32, 1088, 64),
