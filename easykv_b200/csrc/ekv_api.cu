@@ -95,9 +95,31 @@ void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size) {
 }
 void ekv_debug_set_timeline(void* device_buffer) { g_timeline.store((unsigned long long*)device_buffer, std::memory_order_relaxed); }
 
+static bool chunk_tc_shape(const ekv_shape* sh) {
+  const int G = sh->Hkv > 0 ? sh->H / sh->Hkv : 0;
+  return sh->q_len > 1 && sh->d == 128 && (sh->dtype == EKV_F16 || sh->dtype == EKV_BF16) &&
+         (G == 1 || G == 2 || G == 4 || G == 8);
+}
+static int64_t tc_bytes(const ekv_shape* sh) {
+  return chunk_tc_shape(sh) ? (int64_t)chunk_tc_scratch_bytes(sh->B, sh->Hkv, sh->H / sh->Hkv, sh->q_len, sh->n_phys) : 0;
+}
+
 int64_t ekv_scratch_bytes(const ekv_shape* sh, const ekv_step* st) {
-  if (!sh || !st || !st->tova_head_mean || st->policy != EKV_POLICY_TOVA) return 0;
-  return (int64_t)sh->B * sh->Hkv * (sh->n_before + sh->q_len) * 4;
+  if (!sh) return 0;
+  int64_t bytes = tc_bytes(sh);                       // tensor-core chunk path: row statistics, partial outputs, column sums
+  if (st && st->tova_head_mean && st->policy == EKV_POLICY_TOVA)
+    bytes += (int64_t)sh->B * sh->Hkv * (sh->n_before + sh->q_len) * 4;
+  return bytes;
+}
+
+// q_len > 1 in a 16-bit dtype -> the tensor-core chunk kernels (when the caller supplied scratch); anything
+// else, or kernel == 1 -> the exact-arithmetic general kernel
+static int launch_chunk_auto(const KernelArgs& a, const ekv_shape* sh, int32_t kernel, cudaStream_t s) {
+  if (kernel == 0 && chunk_tc_shape(sh) && a.scratch) {
+    const int rc = launch_chunk_tc(a, s);
+    if (rc != EKV_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_general(a, s);
 }
 
 int ekv_attend_evict(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, int32_t kernel, void* stream) {
@@ -118,9 +140,10 @@ int ekv_attend_evict(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step
     if (!io->scratch) return set_error(EKV_ERR_INVALID, "tova_head_mean needs scratch (ekv_scratch_bytes)");
     const ekv_step full = a.st;
     a.st.evict = 0;
-    rc = launch_general(a, s);
+    rc = launch_chunk_auto(a, sh, kernel, s);
     if (rc) return rc;
     KernelArgs b = a;
+    b.scratch = reinterpret_cast<unsigned char*>(io->scratch) + tc_bytes(sh);     // the head-mean staging follows the chunk scratch
     b.n_before = sh->n_before + sh->q_len;
     b.n_phys = io->new_slots ? sh->n_phys : sh->n_phys + sh->q_len;
     b.q_len = 0;
@@ -134,7 +157,7 @@ int ekv_attend_evict(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step
     rc = launch_decode(a, s);
     if (rc != EKV_ERR_UNSUPPORTED) return rc;
   }
-  return launch_general(a, s);
+  return launch_chunk_auto(a, sh, kernel, s);
 }
 
 int ekv_select(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, void* stream) {

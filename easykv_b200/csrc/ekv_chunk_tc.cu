@@ -1,0 +1,563 @@
+// Strided-prefill chunk (q_len = stride query rows per head) for 16-bit dtypes on the tensor cores.
+//
+// Here Q·K^T is a real dense contraction: R = q_len * g (query, head) rows share one pass over a kv head's
+// keys, arithmetic intensity g*q_len flop/B (64 for Mistral stride 16 or 7B stride 64, 512 for 70B stride
+// 64) — far beyond what the FP32 pipes sustain at HBM speed (the CUDA-core general kernel in ekv_chunk.cu
+// is FP32-issue-bound by three orders of magnitude on these shapes), so the contraction runs as
+// mma.sync.m16n8k16 (HMMA, fp32 accumulate) out of shared memory.
+//
+// A chunk forward of one layer is four launches:
+//   1. chunk_tc_kernel<PASS=1>  grid (unit, row block of 64 rows, key split): streams the split's K tiles
+//      (cp.async, 3 stages), S = Q K^T, logits rounded at the reference's rounding points, per-row online
+//      (max, sum of exp) -> scratch.
+//   2. chunk_tc_kernel<PASS=2>  same grid: combines the splits' row statistics, recomputes S (K now comes
+//      from L2), p = model-dtype(exp(x - max) / sum) exactly as softmax forms it, O_partial = P V with P fed
+//      to the tensor cores straight from the accumulator registers, and the per-key column statistics
+//      (GQA fold in the model dtype, p and p^2 summed over the chunk's queries) -> scratch.
+//   3. chunk_out_kernel         sums the splits' partial outputs in split order -> out.
+//   4. chunk_tail_kernel        one CTA per unit: appends the chunk's K/V rows, folds the column statistics
+//      into the policy state and runs the budgeted select / eviction (ekv_select.cuh).
+// The [H, q, n] probability tensor the reference materialises per layer (easykv/llama_patch.py:244-246)
+// never exists; nothing is synchronised with the host.
+//
+// Replaces: llama_patch.py:193-230 / mistral_patch.py:137-170 and easykv.py:439-499 / :599-661 / :830-892
+// for one layer of one strided forward (and the dense prefill issued as causal chunks).
+#include "ekv_select.cuh"
+#include "ekv_kernels.h"
+
+namespace ekv {
+
+namespace tc {
+constexpr int D = 128;
+constexpr int TK = 64;               // keys per tile
+constexpr int MR = 64;               // (query, head) rows per CTA = 4 warps x 16
+constexpr int NT = 128;
+constexpr int NW = 4;
+constexpr int PITCH = 272;           // bytes per shared-memory row: 256 + 16 keeps ldmatrix conflict-free
+constexpr int TILE_BYTES = TK * PITCH;
+constexpr int STAGES = 3;            // pass 1; pass 2 (K and V tiles) uses 2 so that two CTAs fit an SM
+constexpr int TARGET_CTAS = 296;      // two CTAs per SM: their dependency stalls overlap
+}  // namespace tc
+
+struct ChunkPlan {
+  int R, RB, Rpad, NE, NEpad, ntiles, splits, tps;      // tps = tiles per split
+  long long off_stats, off_opart, off_cpart, bytes;
+};
+
+ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
+  using namespace tc;
+  ChunkPlan p;
+  p.R = q_len * G;
+  p.RB = (p.R + MR - 1) / MR;
+  p.Rpad = p.RB * MR;
+  p.NE = n_phys + q_len;
+  p.ntiles = (p.NE + TK - 1) / TK;
+  p.NEpad = p.ntiles * TK;
+  const int U = B * Hkv;
+  int want = TARGET_CTAS / (U * p.RB);
+  if (want < 1) want = 1;
+  if (want > p.ntiles) want = p.ntiles;
+  p.tps = (p.ntiles + want - 1) / want;
+  if (p.tps < 2 && p.ntiles >= 2) p.tps = 2;             // at least two tiles per CTA: keep the pipeline worth its prologue
+  p.splits = (p.ntiles + p.tps - 1) / p.tps;
+  long long o = 0;
+  p.off_stats = o; o += (long long)U * p.splits * p.Rpad * 2 * 4;
+  o = (o + 255) / 256 * 256;
+  p.off_opart = o; o += (long long)U * p.splits * p.Rpad * D * 4;
+  o = (o + 255) / 256 * 256;
+  p.off_cpart = o; o += (long long)U * p.RB * p.NEpad * 2 * 4;
+  p.bytes = (o + 255) / 256 * 256;
+  return p;
+}
+
+long long chunk_tc_scratch_bytes(int B, int Hkv, int G, int q_len, int n_phys) {
+  return make_chunk_plan(B, Hkv, G, q_len, n_phys).bytes;
+}
+
+// ---- tensor-core primitives ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T> __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);      // both already model-dtype values
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- passes 1 and 2 ---------------------------------------------------------------------------------------------------
+template <typename T, int G, int PASS>
+__global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a, const ChunkPlan pl) {
+  using namespace tc;
+  constexpr int STAGES = PASS == 2 ? 2 : tc::STAGES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* Qs = smem;                                       // [MR][PITCH]
+  unsigned char* Ks = Qs + MR * PITCH;                            // [STAGES][TK][PITCH]
+  unsigned char* Vs = Ks + STAGES * TILE_BYTES;                   // [STAGES][TK][PITCH]   (pass 2)
+  int32_t* ljs = reinterpret_cast<int32_t*>(Vs + (PASS == 2 ? STAGES * TILE_BYTES : 0));   // [STAGES][TK]
+  float* cpart = reinterpret_cast<float*>(ljs + STAGES * TK);     // [NW][TK][2]           (pass 2)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x % pl.splits;
+  const int rb = (blockIdx.x / pl.splits) % pl.RB;
+  const int unit = blockIdx.x / (pl.splits * pl.RB);
+  const int b = unit / a.Hkv, h = unit % a.Hkv;
+  const int QL = a.q_len, n_phys = a.n_phys, NE = pl.NE, R = pl.R;
+  const int t_begin = split * pl.tps, t_end = min(pl.ntiles, t_begin + pl.tps);
+  const T* Kg = reinterpret_cast<const T*>(a.K) + (size_t)unit * a.cap * D;
+  const T* Vg = reinterpret_cast<const T*>(a.V) + (size_t)unit * a.cap * D;
+  const T* kn = reinterpret_cast<const T*>(a.k_new) + (size_t)unit * QL * D;
+  const T* vn = reinterpret_cast<const T*>(a.v_new) + (size_t)unit * QL * D;
+  const T* qg = reinterpret_cast<const T*>(a.q) + (size_t)b * a.H * QL * D;
+  const int32_t* lg = a.lidx + (size_t)unit * a.cap;
+
+  auto issue_tile = [&](int tile, int stage) {
+    unsigned char* kd = Ks + stage * TILE_BYTES;
+    unsigned char* vd = Vs + stage * TILE_BYTES;
+#pragma unroll
+    for (int j = 0; j < TK * 16 / NT; ++j) {
+      const int idx = tid + j * NT, row = idx >> 4, c = idx & 15;
+      const int e = tile * TK + row;
+      if (e < NE) {
+        const T* ks = e < n_phys ? Kg + (size_t)e * D : kn + (size_t)(e - n_phys) * D;
+        cp_async16(kd + row * PITCH + c * 16, reinterpret_cast<const unsigned char*>(ks) + c * 16);
+        if (PASS == 2) {
+          const T* vs = e < n_phys ? Vg + (size_t)e * D : vn + (size_t)(e - n_phys) * D;
+          cp_async16(vd + row * PITCH + c * 16, reinterpret_cast<const unsigned char*>(vs) + c * 16);
+        }
+      } else {
+        *reinterpret_cast<uint4*>(kd + row * PITCH + c * 16) = make_uint4(0, 0, 0, 0);
+        if (PASS == 2) *reinterpret_cast<uint4*>(vd + row * PITCH + c * 16) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (tid < TK) {
+      const int e = tile * TK + tid;
+      if (e < n_phys) cp_async4(&ljs[stage * TK + tid], lg + e);
+      else ljs[stage * TK + tid] = e < NE ? a.n_before + (e - n_phys) : -1;
+    }
+  };
+
+  // ---- Q block -> shared memory -> A fragments ---------------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < MR * 16 / NT; ++j) {
+    const int idx = tid + j * NT, rr = idx >> 4, c = idx & 15;
+    const int r = rb * MR + rr;
+    if (r < R) {
+      const int i = r / G, g = r % G;                             // query-major rows: the g heads of a query are adjacent
+      cp_async16(Qs + rr * PITCH + c * 16,
+                 reinterpret_cast<const unsigned char*>(qg + ((size_t)(h * G + g) * QL + i) * D) + c * 16);
+    } else {
+      *reinterpret_cast<uint4*>(Qs + rr * PITCH + c * 16) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_commit();
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (t_begin + s < t_end) issue_tile(t_begin + s, s);
+    cp_async_commit();
+  }
+  cp_async_wait<STAGES - 1>();                                    // the Q group
+  __syncthreads();
+  uint32_t aq[8][4];
+  {
+    const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int colb = (lane >> 4) * 16;                            // second pair of matrices: dims +8
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) ldsm_x4(smem_u32(Qs + row * PITCH + ks * 32 + colb), aq[ks]);
+  }
+
+  // the two rows of this thread (C-fragment layout): r0 = warp*16 + lane/4, r1 = r0 + 8
+  const int rr0 = warp * 16 + (lane >> 2), rr1 = rr0 + 8;
+  const int row0 = rb * MR + rr0, row1 = rb * MR + rr1;
+  const int qi0 = row0 / G, qi1 = row1 / G;                       // query index inside the chunk
+  const bool rv0 = row0 < R, rv1 = row1 < R;
+
+  // ---- pass 2: the rows' softmax statistics over ALL keys (combine the splits of pass 1) ---------------------------------
+  const float2* stats = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_stats);
+  float M0 = 0.f, M1 = 0.f, L0 = 1.f, L1 = 1.f;
+  if (PASS == 2) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int s = 0; s < pl.splits; ++s) {
+      const float2* st = stats + ((size_t)unit * pl.splits + s) * pl.Rpad;
+      m0 = fmaxf(m0, st[rb * MR + rr0].x); m1 = fmaxf(m1, st[rb * MR + rr1].x);
+    }
+    float l0 = 0.f, l1 = 0.f;
+    for (int s = 0; s < pl.splits; ++s) {                         // split order on every CTA
+      const float2* st = stats + ((size_t)unit * pl.splits + s) * pl.Rpad;
+      const float2 x0 = st[rb * MR + rr0], x1 = st[rb * MR + rr1];
+      if (x0.x != -INFINITY) l0 += x0.y * expf(x0.x - m0);
+      if (x1.x != -INFINITY) l1 += x1.y * expf(x1.x - m1);
+    }
+    M0 = m0; M1 = m1;
+    if (l0 == 0.f) l0 = 1.f;                                      // padding rows (row >= R): p = 0
+    if (l1 == 0.f) l1 = 1.f;
+    L0 = a.st.arith ? l0 : __fdiv_rn(1.0f, l0);
+    L1 = a.st.arith ? l1 : __fdiv_rn(1.0f, l1);
+  }
+
+  float mrun0 = -INFINITY, mrun1 = -INFINITY, lrun0 = 0.f, lrun1 = 0.f;      // pass 1: this thread's columns only
+  float o[16][4];
+  if (PASS == 2) {
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[nb][c] = 0.f;
+  }
+  const bool tova = a.st.policy == EKV_POLICY_TOVA;
+  const bool want_stats = PASS == 2 && a.st.accumulate != 0;
+  const float inv_g = 1.0f / (float)G;
+
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int it = tile - t_begin, stage = it % STAGES;
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();                                              // tile `tile` has landed; slot (it-1)%STAGES is free
+    {
+      const int nxt = tile + STAGES - 1;
+      if (nxt < t_end) issue_tile(nxt, (it + STAGES - 1) % STAGES);
+      cp_async_commit();
+    }
+    const unsigned char* kt = Ks + stage * TILE_BYTES;
+    const int32_t* lt = ljs + stage * TK;
+
+    // ---- S = Q K^T ------------------------------------------------------------------------------------------------
+    float s[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[nb][c] = 0.f;
+    {
+      const int key_l = (lane & 7) + (lane >> 4) * 8;             // matrices 2,3: next 8 keys
+      const int dim_l = ((lane >> 3) & 1) * 16;                   // matrices 1,3: dims +8 (bytes)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int nbp = 0; nbp < 4; ++nbp) {
+          uint32_t bk[4];
+          ldsm_x4(smem_u32(kt + (nbp * 16 + key_l) * PITCH + ks * 32 + dim_l), bk);
+          mma16816<T>(s[2 * nbp], aq[ks], bk[0], bk[1]);
+          mma16816<T>(s[2 * nbp + 1], aq[ks], bk[2], bk[3]);
+        }
+    }
+    // ---- logits at the reference's rounding points, mask -------------------------------------------------------------
+    {
+      // column visibility of this thread's 16 columns: bit nb*2+cc.  Tiles of cached keys only need the slot
+      // map (free slots are masked); the chunk's own keys are causal per row (llama_patch.py:210-215).
+      const bool cached_tile = (tile + 1) * TK <= n_phys;
+      uint32_t cm = 0;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col = nb * 8 + 2 * (lane & 3) + cc;
+          const int e = tile * TK + col;
+          const bool ok = cached_tile ? lt[col] >= 0 : (e < n_phys ? lt[col] >= 0 : e < NE);
+          cm |= (ok ? 1u : 0u) << (nb * 2 + cc);
+        }
+      const uint32_t cm0 = rv0 ? cm : 0u, cm1 = rv1 ? cm : 0u;
+      const int new0 = tile * TK - n_phys;                        // index of the tile's first key among the chunk's keys
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool hi = c >= 2;
+          bool vis = (((hi ? cm1 : cm0) >> (nb * 2 + (c & 1))) & 1u) != 0;
+          if (!cached_tile) {
+            const int jn = new0 + nb * 8 + 2 * (lane & 3) + (c & 1);
+            if (jn >= 0) vis = vis && jn <= (hi ? qi1 : qi0);     // causal inside the chunk
+          }
+          float v = Tr<T>::round_f(s[nb][c]);                                           // llama_patch.py:201
+          v = a.st.arith ? __fmul_rn(v, a.scale_mul) : __fdiv_rn(v, a.scale_div);       // :202
+          s[nb][c] = vis ? Tr<T>::round_f(v) : -INFINITY;
+        }
+    }
+
+    if (PASS == 1) {
+      float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        tm0 = fmaxf(tm0, fmaxf(s[nb][0], s[nb][1]));
+        tm1 = fmaxf(tm1, fmaxf(s[nb][2], s[nb][3]));
+      }
+      const float n0 = fmaxf(mrun0, tm0), n1 = fmaxf(mrun1, tm1);
+      if (n0 != -INFINITY) {
+        float acc = mrun0 == -INFINITY ? 0.f : lrun0 * expf(mrun0 - n0);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) acc += expf(s[nb][0] - n0) + expf(s[nb][1] - n0);
+        lrun0 = acc; mrun0 = n0;
+      }
+      if (n1 != -INFINITY) {
+        float acc = mrun1 == -INFINITY ? 0.f : lrun1 * expf(mrun1 - n1);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) acc += expf(s[nb][2] - n1) + expf(s[nb][3] - n1);
+        lrun1 = acc; mrun1 = n1;
+      }
+    } else {
+      // ---- probabilities (llama_patch.py:218-219) -------------------------------------------------------------------
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool hi = c >= 2;
+          const float x = s[nb][c];
+          float ex = (x == -INFINITY) ? 0.f : expf(x - (hi ? M1 : M0));
+          ex = a.st.arith ? __fdiv_rn(ex, hi ? L1 : L0) : __fmul_rn(ex, hi ? L1 : L0);
+          s[nb][c] = Tr<T>::round_f(ex);
+        }
+      // ---- O += P V: the C fragments of S are the A fragments of P ------------------------------------------------------
+      const unsigned char* vt = Vs + stage * TILE_BYTES;
+      {
+        const int key_l = (lane & 7) + ((lane >> 3) & 1) * 8;     // matrices 1,3: keys +8
+        const int dim_l = (lane >> 4) * 16;                       // matrices 2,3: dims +8 (bytes)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t pa[4];
+          pa[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+          pa[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+          pa[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+          pa[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+          for (int dbp = 0; dbp < 8; ++dbp) {
+            uint32_t bv[4];
+            ldsm_x4_trans(smem_u32(vt + (kk * 16 + key_l) * PITCH + dbp * 32 + dim_l), bv);
+            mma16816<T>(o[2 * dbp], pa, bv[0], bv[1]);
+            mma16816<T>(o[2 * dbp + 1], pa, bv[2], bv[3]);
+          }
+        }
+      }
+      // ---- per-key column statistics of this tile -------------------------------------------------------------------------
+      if (want_stats) {
+        // fold the g heads of a query (adjacent rows = lanes 4 apart), round to the model dtype
+        // (process_for_mqa_gqa, easykv.py:188-196), then sum p and model-dtype(p^2) over the queries (:450-451)
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float lo = s[nb][cc], hi = s[nb][2 + cc];
+            if (G > 1) {
+#pragma unroll
+              for (int off = 4; off < 4 * G; off <<= 1) {
+                lo += __shfl_xor_sync(0xffffffffu, lo, off);
+                hi += __shfl_xor_sync(0xffffffffu, hi, off);
+              }
+              lo = Tr<T>::round_f(__fmul_rn(lo, inv_g));
+              hi = Tr<T>::round_f(__fmul_rn(hi, inv_g));
+            }
+            const bool lead = ((lane >> 2) % G) == 0;             // one lane per (query, column)
+            const bool use0 = lead && rv0 && (!tova || qi0 == QL - 1);
+            const bool use1 = lead && rv1 && (!tova || qi1 == QL - 1);
+            float cs = (use0 ? lo : 0.f) + (use1 ? hi : 0.f);
+            float csq = (use0 ? Tr<T>::round_f(__fmul_rn(lo, lo)) : 0.f) + (use1 ? Tr<T>::round_f(__fmul_rn(hi, hi)) : 0.f);
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+              cs += __shfl_xor_sync(0xffffffffu, cs, off);
+              csq += __shfl_xor_sync(0xffffffffu, csq, off);
+            }
+            if (lane < 4) {
+              const int col = nb * 8 + 2 * lane + cc;
+              cpart[(warp * TK + col) * 2] = cs;
+              cpart[(warp * TK + col) * 2 + 1] = csq;
+            }
+          }
+        __syncthreads();
+        if (tid < TK) {
+          const int e = tile * TK + tid;
+          if (e < NE) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { s1 += cpart[(w * TK + tid) * 2]; s2 += cpart[(w * TK + tid) * 2 + 1]; }
+            float2* cg = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_cpart);
+            cg[((size_t)unit * pl.RB + rb) * pl.NEpad + e] = make_float2(s1, s2);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  if (PASS == 1) {
+    // combine the four lanes that share a row, then one lane per row writes (max, sum)
+#pragma unroll
+    for (int off = 1; off < 4; off <<= 1) {
+      const float om0 = __shfl_xor_sync(0xffffffffu, mrun0, off), ol0 = __shfl_xor_sync(0xffffffffu, lrun0, off);
+      const float om1 = __shfl_xor_sync(0xffffffffu, mrun1, off), ol1 = __shfl_xor_sync(0xffffffffu, lrun1, off);
+      const float n0 = fmaxf(mrun0, om0), n1 = fmaxf(mrun1, om1);
+      lrun0 = (mrun0 == -INFINITY ? 0.f : lrun0 * expf(mrun0 - n0)) + (om0 == -INFINITY ? 0.f : ol0 * expf(om0 - n0));
+      lrun1 = (mrun1 == -INFINITY ? 0.f : lrun1 * expf(mrun1 - n1)) + (om1 == -INFINITY ? 0.f : ol1 * expf(om1 - n1));
+      mrun0 = n0; mrun1 = n1;
+    }
+    if ((lane & 3) == 0) {
+      float2* st = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_stats) +
+                   ((size_t)unit * pl.splits + split) * pl.Rpad;
+      st[rb * MR + rr0] = make_float2(mrun0, lrun0);
+      st[rb * MR + rr1] = make_float2(mrun1, lrun1);
+    }
+  } else {
+    float* op = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_opart) +
+                ((size_t)unit * pl.splits + split) * pl.Rpad * D;
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb) {
+      const int dim = nb * 8 + 2 * (lane & 3);
+      *reinterpret_cast<float2*>(op + (size_t)(rb * MR + rr0) * D + dim) = make_float2(o[nb][0], o[nb][1]);
+      *reinterpret_cast<float2*>(op + (size_t)(rb * MR + rr1) * D + dim) = make_float2(o[nb][2], o[nb][3]);
+    }
+  }
+}
+
+// ---- 3. out = sum over splits of the partial outputs (llama_patch.py:222) ------------------------------------------------------
+template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a, const ChunkPlan pl) {
+  using namespace tc;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // (unit, row, dim4)
+  const int d4 = idx % (D / 4), r = (idx / (D / 4)) % pl.R, unit = idx / ((D / 4) * pl.R);
+  if (unit >= a.B * a.Hkv) return;
+  const float* op = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_opart);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < pl.splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(op + (((size_t)unit * pl.splits + s) * pl.Rpad + r) * D + d4 * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int b = unit / a.Hkv, h = unit % a.Hkv, i = r / G, g = r % G;
+  T* o = reinterpret_cast<T*>(a.out) + (((size_t)b * a.H + h * G + g) * a.q_len + i) * D + d4 * 4;
+  o[0] = Tr<T>::from_f(acc.x); o[1] = Tr<T>::from_f(acc.y); o[2] = Tr<T>::from_f(acc.z); o[3] = Tr<T>::from_f(acc.w);
+}
+
+// ---- 4. tail: append, accumulate, select, evict --------------------------------------------------------------------------------------
+constexpr int TAIL_NT = 512;
+struct TailSmem {
+  int off_ns, off_lj, off_pool, total;
+  __host__ __device__ TailSmem(int NE, int q_len, int evict) {
+    int o = 0;
+    off_ns = o; o += (q_len * 4 + 15) / 16 * 16;
+    off_lj = o; o += (NE * 4 + 15) / 16 * 16;
+    o = (o + 127) / 128 * 128;
+    off_pool = o;
+    total = o + (int)SelScratch::bytes(NE, evict);
+  }
+};
+
+template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kernel(const KernelArgs a, const ChunkPlan pl) {
+  using namespace tc;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n_phys = a.n_phys, QL = a.q_len, NE = pl.NE;
+  const TailSmem L(NE, QL, a.st.evict);
+  int32_t* ns = reinterpret_cast<int32_t*>(smem + L.off_ns);
+  int32_t* lj = reinterpret_cast<int32_t*>(smem + L.off_lj);
+  const int unit = blockIdx.x, tid = threadIdx.x;
+  const Grp grp{tid, TAIL_NT, 0};
+  {
+    const int32_t* lg = a.lidx + (size_t)unit * a.cap;
+    for (int e = tid; e < n_phys; e += TAIL_NT) lj[e] = lg[e];
+    for (int i = tid; i < QL; i += TAIL_NT) {
+      ns[i] = a.new_slots ? a.new_slots[(size_t)unit * QL + i] : n_phys + i;
+      lj[n_phys + i] = a.n_before + i;
+    }
+  }
+  __syncthreads();
+  {                                                               // append the chunk's K/V rows (16-byte pieces)
+    const uint4* kn = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_new) + (size_t)unit * QL * D);
+    const uint4* vn = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.v_new) + (size_t)unit * QL * D);
+    uint4* Kw = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.K) + (size_t)unit * a.cap * D);
+    uint4* Vw = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.V) + (size_t)unit * a.cap * D);
+    constexpr int CPR = D * (int)sizeof(T) / 16;                  // 16-byte pieces per row
+    for (int idx = tid; idx < QL * CPR; idx += TAIL_NT) {
+      const int i = idx / CPR, c = idx % CPR;
+      Kw[(size_t)ns[i] * CPR + c] = kn[(size_t)i * CPR + c];
+      Vw[(size_t)ns[i] * CPR + c] = vn[(size_t)i * CPR + c];
+    }
+  }
+  SelScratch sc;
+  sc.lj = lj;
+  sc.carve(smem + L.off_pool, NE, a.st.evict);
+  UnitState u;
+  u.S = a.S + (size_t)unit * a.cap; u.SQ = a.SQ + (size_t)unit * a.cap; u.C = a.C + (size_t)unit * a.cap;
+  u.lidx = a.lidx + (size_t)unit * a.cap;
+  u.new_slots = ns;
+  u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
+  u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
+  const float2* cg = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_cpart) +
+                     (size_t)unit * pl.RB * pl.NEpad;
+  auto accf = [&](int e, float& ds, float& dsq) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < pl.RB; ++r) { const float2 v = cg[(size_t)r * pl.NEpad + e]; s1 += v.x; s2 += v.y; }
+    ds = Tr<T>::round_f(s1);               // p.sum(dim=1) is a model-dtype result (easykv.py:450)
+    dsq = Tr<T>::round_f(s2);              // (p**2).sum(dim=1) likewise (:451)
+  };
+  state_select_apply(a.st, u, a.n_before, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
+}
+
+// ---- launch ---------------------------------------------------------------------------------------------------------------------------
+template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, cudaStream_t stream) {
+  using namespace tc;
+  const ChunkPlan pl = make_chunk_plan(a.B, a.Hkv, G, a.q_len, a.n_phys);
+  const TailSmem TL(pl.NE, a.q_len, a.st.evict);
+  if (TL.total > 227 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "chunk tail: %d bytes of shared memory needed", TL.total);
+  const int smem1 = MR * PITCH + STAGES * TILE_BYTES + STAGES * TK * 4;
+  const int smem2 = MR * PITCH + 2 * 2 * TILE_BYTES + 2 * TK * 4 + NW * TK * 2 * 4;
+  static thread_local int configured[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
+  cudaError_t err;
+  if (!configured[dev]) {
+    err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(chunk_tc)", err);
+    configured[dev] = 1;
+  }
+  const int U = a.B * a.Hkv;
+  const int grid = U * pl.RB * pl.splits;
+  chunk_tc_kernel<T, G, 1><<<grid, NT, smem1, stream>>>(a, pl);
+  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<1> launch", err);
+  count_launch();
+  chunk_tc_kernel<T, G, 2><<<grid, NT, smem2, stream>>>(a, pl);
+  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<2> launch", err);
+  count_launch();
+  const int nout = U * pl.R * (D / 4);
+  chunk_out_kernel<T, G><<<(nout + 255) / 256, 256, 0, stream>>>(a, pl);
+  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_out_kernel launch", err);
+  count_launch();
+  chunk_tail_kernel<T><<<U, TAIL_NT, TL.total, stream>>>(a, pl);
+  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tail_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+template <typename T> static int launch_chunk_tc_t(const KernelArgs& a, cudaStream_t stream) {
+  switch (a.H / a.Hkv) {
+    case 1: return launch_chunk_tc_tg<T, 1>(a, stream);
+    case 2: return launch_chunk_tc_tg<T, 2>(a, stream);
+    case 4: return launch_chunk_tc_tg<T, 4>(a, stream);
+    case 8: return launch_chunk_tc_tg<T, 8>(a, stream);
+    default: return EKV_ERR_UNSUPPORTED;
+  }
+}
+
+// 16-bit dtypes, head_dim 128, any q_len; needs `scratch` of chunk_tc_scratch_bytes().
+int launch_chunk_tc(const KernelArgs& a, cudaStream_t stream) {
+  if (a.d != tc::D || !a.scratch) return EKV_ERR_UNSUPPORTED;
+  switch (a.dtype) {
+    case EKV_F16: return launch_chunk_tc_t<__half>(a, stream);
+    case EKV_BF16: return launch_chunk_tc_t<__nv_bfloat16>(a, stream);
+    default: return EKV_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace ekv

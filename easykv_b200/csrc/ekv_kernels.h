@@ -30,6 +30,8 @@ void count_launch();
 int launch_decode(const KernelArgs& a, cudaStream_t stream);      // ekv_decode.cu
 int launch_decode_cluster(const KernelArgs& a, bool only_if_better, cudaStream_t stream);   // ekv_decode_cluster.cu
 int launch_general(const KernelArgs& a, cudaStream_t stream);     // ekv_chunk.cu
+int launch_chunk_tc(const KernelArgs& a, cudaStream_t stream);    // ekv_chunk_tc.cu (16-bit dtypes, needs scratch)
+long long chunk_tc_scratch_bytes(int B, int Hkv, int G, int q_len, int n_phys);
 int launch_select(const KernelArgs& a, cudaStream_t stream);      // ekv_aux.cu
 int launch_tova_head_mean(const KernelArgs& a, cudaStream_t stream);
 int launch_evict_explicit(const KernelArgs& a, const int32_t* victims, int evict, cudaStream_t stream);

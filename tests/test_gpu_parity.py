@@ -159,6 +159,82 @@ def test_decode_random_vs_oracle(engines, dispatch, dtype, H, Hkv, policy, clust
 
 
 # ------------------------------------------------------------------------------------------------
+# 3b. strided-prefill chunks: tensor-core path (kernel 0, 16-bit) and general kernel vs the CPU restatement
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", [0, 1], ids=["tensorcore", "general"])
+@pytest.mark.parametrize("dtype,H,Hkv,stride,policy,n0", [
+    (torch.float16, 8, 8, 16, "roco", 300), (torch.float16, 8, 2, 16, "roco", 517), (torch.float16, 8, 1, 8, "h2o_head", 200),
+    (torch.bfloat16, 4, 4, 64, "roco", 1100), (torch.float16, 16, 2, 24, "tova", 260), (torch.float16, 4, 2, 96, "roco", 700),
+    (torch.float16, 4, 4, 7, "recency", 150),
+])
+def test_chunk_random_vs_oracle(engines, dtype, H, Hkv, stride, policy, n0, kernel):
+    d, steps = 128, 5
+    g = torch.Generator().manual_seed(11)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
+    eng = engines.CudaEngine(1, H, Hkv, d, dtype, kernel=kernel, capacity=n0 + stride)
+    orc = replay.OracleEngine(1, H, Hkv, d, dtype)
+    K, V = rnd(Hkv, n0, d), rnd(Hkv, n0, d)
+    for e in (eng, orc):
+        e.load_prefill(0, K, V, n0, torch.zeros(n0))
+    recent, sink = int(n0 * 0.1), 4
+    st = restate.Step(policy=policy, accumulate=True, evict=stride, counter_add=float(stride), c_new_step=1.0,
+                      k_feasible=max(n0 - recent - sink, stride), sink_protect=sink, win_lo=sink, win_recent=recent,
+                      range_start=sink)
+    bad = 0
+    for t in range(steps):
+        q, k, v = rnd(H, stride, d) * 0.3, rnd(Hkv, stride, d), rnd(Hkv, stride, d)
+        o_ref, v_ref = orc.forward(0, st, q, k, v)
+        o, vic = eng.forward(0, st, q, k, v, force=v_ref)
+        tol = 1e-3 if dtype == torch.float16 else 8e-3
+        assert (o.float() - o_ref.float()).abs().max().item() <= tol * max(1.0, o_ref.float().abs().max().item())
+        if not torch.equal(torch.sort(vic, dim=-1)[0], torch.sort(v_ref, dim=-1)[0]):
+            assert min(orc.margin(0)) < 1e-5            # only near-ties of 16-bit probabilities may differ
+            bad += 1
+    assert bad <= 1
+    Kc, Vc = eng.export(0)
+    assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
+
+
+def test_chunk_full_size_tensorcore_vs_general(ekv_lib):
+    """BASELINE configs[2] geometry (Mistral: H=32, Hkv=8, stride 16, 8208 retained, h2o_head) and the 7B
+    stride-64 chunk: the tensor-core path against the exact CUDA-core kernel on the same state — same victims
+    (up to near-ties), outputs within 1e-3, and a dense causal prefill issued as chunks vs fp32 torch."""
+    from easykv_b200.cache import BudgetedKVCache
+    from easykv_b200.plan import StepParams
+    dev = "cuda"
+    for (B, H, Hkv, n, stride, policy) in [(1, 32, 8, 8208, 16, "h2o_head"), (2, 32, 32, 1088, 64, "roco")]:
+        torch.manual_seed(2)
+        d = 128
+        caches = [BudgetedKVCache(1, B, H, Hkv, d, n + stride, dtype=torch.float16) for _ in range(2)]
+        K0 = torch.randn(B, Hkv, n, d, device=dev).half(); V0 = torch.randn(B, Hkv, n, d, device=dev).half()
+        for c in caches:
+            c.load_prefill(0, K0, V0, n, [0.0] * n)
+        recent = int(n * 0.1)
+        sp = StepParams(policy=policy, accumulate=True, evict=stride, counter_add=float(stride), c_new_step=1.0,
+                        k_feasible=max(n - recent - 4, stride), sink_protect=4, win_lo=4, win_recent=recent)
+        for t in range(3):
+            q = torch.randn(B, H, stride, d, device=dev).half() * 0.2
+            k = torch.randn(B, Hkv, stride, d, device=dev).half(); v = torch.randn(B, Hkv, stride, d, device=dev).half()
+            out, vl = caches[0].step(0, sp, q, k, v)
+            out1, vl1 = caches[1].step(0, sp, q, k, v, apply=False, kernel=1)
+            caches[1].evict(0, vl)
+            assert (out.float() - out1.float()).abs().max().item() <= 1e-3
+            same = (torch.sort(vl, -1)[0] == torch.sort(vl1, -1)[0]).float().mean().item()
+            assert same >= 0.98, same
+    # dense causal prefill as chunks (policy none) == plain causal attention
+    B, H, Hkv, n, d = 1, 8, 2, 320, 128
+    torch.manual_seed(4)
+    c = BudgetedKVCache(1, B, H, Hkv, d, n, dtype=torch.float16)
+    q = torch.randn(B, H, n, d, device=dev).half() * 0.3
+    k = torch.randn(B, Hkv, n, d, device=dev).half(); v = torch.randn(B, Hkv, n, d, device=dev).half()
+    outs = [c.step(0, StepParams(), q[:, :, t:t + 64], k[:, :, t:t + 64], v[:, :, t:t + 64])[0] for t in range(0, n, 64)]
+    out = torch.cat(outs, 2).float()
+    kr, vr = k.float().repeat_interleave(H // Hkv, 1), v.float().repeat_interleave(H // Hkv, 1)
+    w = (q.float() @ kr.transpose(2, 3)) / math.sqrt(d) + torch.full((n, n), float("-inf"), device=dev).triu(1)
+    assert (out - torch.softmax(w, -1) @ vr).abs().max().item() <= 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
 # 4. BASELINE configs[1] geometry at full size: size-independent properties
 # ------------------------------------------------------------------------------------------------
 def test_full_size_decode_properties(ekv_lib):

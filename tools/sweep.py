@@ -35,7 +35,7 @@ def steady_state(cache, l, n, dev):
 def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float16, kernel=0, cluster=0, variant=0):
     d, dev = 128, "cuda"
     torch.manual_seed(0)
-    cache = BudgetedKVCache(L, B, H, Hkv, d, n + q_len * (1 if policy != "full" else 3 + steps + 1), dtype=dtype)
+    cache = BudgetedKVCache(L, B, H, Hkv, d, n + q_len * (1 if policy != "full" else 3 + steps + 1), dtype=dtype, arith=1)
     cache.lib.ekv_debug_set_dispatch(variant, cluster)
     for l in range(L):
         cache.load_prefill(l, torch.randn(B, Hkv, n, d, device=dev, dtype=dtype), torch.randn(B, Hkv, n, d, device=dev, dtype=dtype),
