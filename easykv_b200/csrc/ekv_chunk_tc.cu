@@ -32,16 +32,16 @@ constexpr int D = 128;
 constexpr int TK = 64;               // keys per tile
 constexpr int MR = 64;               // (query, head) rows per CTA = 4 warps x 16
 constexpr int NT = 128;
-constexpr int NW = 4;
 constexpr int PITCH = 272;           // bytes per shared-memory row: 256 + 16 keeps ldmatrix conflict-free
 constexpr int TILE_BYTES = TK * PITCH;
 constexpr int STAGES = 3;            // pass 1; pass 2 (K and V tiles) uses 2 so that two CTAs fit an SM
+constexpr float NEG = -1.0e30f;      // masked logit: finite, exp(NEG - max) == 0 exactly
 constexpr int TARGET_CTAS = 296;      // two CTAs per SM: their dependency stalls overlap
 }  // namespace tc
 
 struct ChunkPlan {
   int R, RB, Rpad, NE, NEpad, ntiles, splits, tps;      // tps = tiles per split
-  long long off_stats, off_opart, off_cpart, bytes;
+  long long off_stats, off_opart, off_cpart, off_csum, bytes;
 };
 
 ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
@@ -65,7 +65,9 @@ ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
   o = (o + 255) / 256 * 256;
   p.off_opart = o; o += (long long)U * p.splits * p.Rpad * D * 4;
   o = (o + 255) / 256 * 256;
-  p.off_cpart = o; o += (long long)U * p.RB * p.NEpad * 2 * 4;
+  p.off_cpart = o; o += (long long)U * (2 * p.RB) * p.NEpad * 2 * 4;      // two query halves per row block
+  o = (o + 255) / 256 * 256;
+  p.off_csum = o; o += (long long)U * p.NEpad * 2 * 4;                     // column sums over all row blocks
   p.bytes = (o + 255) / 256 * 256;
   return p;
 }
@@ -104,6 +106,26 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, f
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// round a pair to the model dtype and back with the packed conversions (one F2FP per pair instead of
+// two scalar F2F per element)
+template <typename T> __device__ __forceinline__ void round2(float& x, float& y);
+template <> __device__ __forceinline__ void round2<__half>(float& x, float& y) {
+  const float2 f = __half22float2(__floats2half2_rn(x, y));
+  x = f.x; y = f.y;
+}
+template <> __device__ __forceinline__ void round2<__nv_bfloat16>(float& x, float& y) {
+  const uint32_t u = pack2<__nv_bfloat16>(x, y);
+  x = __uint_as_float(u << 16); y = __uint_as_float(u & 0xffff0000u);
+}
+// a / b correctly rounded for normal operands, given rb = RN(1/b) (Markstein: q = a*rb; r = a - b*q exactly
+// by FMA; q + r*rb).  Here 0 <= a <= 1 <= b, so neither overflow nor a subnormal quotient that would
+// survive the rounding to the model dtype can occur.
+__device__ __forceinline__ float div_rn_by(float a, float b, float rb) {
+  const float q = __fmul_rn(a, rb);
+  const float r = __fmaf_rn(-b, q, a);
+  return __fmaf_rn(r, rb, q);
+}
+
 // ---- passes 1 and 2 ---------------------------------------------------------------------------------------------------
 template <typename T, int G, int PASS>
 __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a, const ChunkPlan pl) {
@@ -114,7 +136,8 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
   unsigned char* Ks = Qs + MR * PITCH;                            // [STAGES][TK][PITCH]
   unsigned char* Vs = Ks + STAGES * TILE_BYTES;                   // [STAGES][TK][PITCH]   (pass 2)
   int32_t* ljs = reinterpret_cast<int32_t*>(Vs + (PASS == 2 ? STAGES * TILE_BYTES : 0));   // [STAGES][TK]
-  float* cpart = reinterpret_cast<float*>(ljs + STAGES * TK);     // [NW][TK][2]           (pass 2)
+  T* pfs = reinterpret_cast<T*>(ljs + STAGES * TK);               // [MR / G][PFP] folded probabilities (pass 2)
+  constexpr int PFP = TK + 2;                                     // row pitch in elements: conflict-free both ways
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x % pl.splits;
@@ -133,6 +156,20 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
   auto issue_tile = [&](int tile, int stage) {
     unsigned char* kd = Ks + stage * TILE_BYTES;
     unsigned char* vd = Vs + stage * TILE_BYTES;
+    if ((tile + 1) * TK <= n_phys) {                              // a tile of cached rows: straight copies
+      const int row = tid >> 4, c = tid & 15;
+      const unsigned char* ks = reinterpret_cast<const unsigned char*>(Kg + (size_t)(tile * TK + row) * D) + c * 16;
+      const unsigned char* vs = reinterpret_cast<const unsigned char*>(Vg + (size_t)(tile * TK + row) * D) + c * 16;
+      unsigned char* kdd = kd + row * PITCH + c * 16;
+      unsigned char* vdd = vd + row * PITCH + c * 16;
+#pragma unroll
+      for (int j = 0; j < TK * 16 / NT; ++j) {                    // 8 rows further per step
+        cp_async16(kdd + j * 8 * PITCH, ks + (size_t)j * 8 * D * sizeof(T));
+        if (PASS == 2) cp_async16(vdd + j * 8 * PITCH, vs + (size_t)j * 8 * D * sizeof(T));
+      }
+      if (tid < TK) cp_async4(&ljs[stage * TK + tid], lg + tile * TK + tid);
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < TK * 16 / NT; ++j) {
       const int idx = tid + j * NT, row = idx >> 4, c = idx & 15;
@@ -188,13 +225,12 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
   const int rr0 = warp * 16 + (lane >> 2), rr1 = rr0 + 8;
   const int row0 = rb * MR + rr0, row1 = rb * MR + rr1;
   const int qi0 = row0 / G, qi1 = row1 / G;                       // query index inside the chunk
-  const bool rv0 = row0 < R, rv1 = row1 < R;
 
   // ---- pass 2: the rows' softmax statistics over ALL keys (combine the splits of pass 1) ---------------------------------
   const float2* stats = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_stats);
-  float M0 = 0.f, M1 = 0.f, L0 = 1.f, L1 = 1.f;
+  float M0 = 0.f, M1 = 0.f, L0 = 1.f, L1 = 1.f, R0 = 1.f, R1 = 1.f;
   if (PASS == 2) {
-    float m0 = -INFINITY, m1 = -INFINITY;
+    float m0 = NEG, m1 = NEG;
     for (int s = 0; s < pl.splits; ++s) {
       const float2* st = stats + ((size_t)unit * pl.splits + s) * pl.Rpad;
       m0 = fmaxf(m0, st[rb * MR + rr0].x); m1 = fmaxf(m1, st[rb * MR + rr1].x);
@@ -203,17 +239,18 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
     for (int s = 0; s < pl.splits; ++s) {                         // split order on every CTA
       const float2* st = stats + ((size_t)unit * pl.splits + s) * pl.Rpad;
       const float2 x0 = st[rb * MR + rr0], x1 = st[rb * MR + rr1];
-      if (x0.x != -INFINITY) l0 += x0.y * expf(x0.x - m0);
-      if (x1.x != -INFINITY) l1 += x1.y * expf(x1.x - m1);
+      l0 += x0.y * expf(x0.x - m0);
+      l1 += x1.y * expf(x1.x - m1);
     }
     M0 = m0; M1 = m1;
     if (l0 == 0.f) l0 = 1.f;                                      // padding rows (row >= R): p = 0
     if (l1 == 0.f) l1 = 1.f;
     L0 = a.st.arith ? l0 : __fdiv_rn(1.0f, l0);
     L1 = a.st.arith ? l1 : __fdiv_rn(1.0f, l1);
+    R0 = __frcp_rn(l0); R1 = __frcp_rn(l1);
   }
 
-  float mrun0 = -INFINITY, mrun1 = -INFINITY, lrun0 = 0.f, lrun1 = 0.f;      // pass 1: this thread's columns only
+  float mrun0 = NEG, mrun1 = NEG, lrun0 = 0.f, lrun1 = 0.f;      // pass 1: this thread's columns only
   float o[16][4];
   if (PASS == 2) {
 #pragma unroll
@@ -256,71 +293,67 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
           mma16816<T>(s[2 * nbp + 1], aq[ks], bk[2], bk[3]);
         }
     }
-    // ---- logits at the reference's rounding points, mask -------------------------------------------------------------
+    // ---- logits at the reference's rounding points (llama_patch.py:201-202) ---------------------------------------------
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      round2<T>(s[nb][0], s[nb][1]);
+      round2<T>(s[nb][2], s[nb][3]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        s[nb][c] = a.st.arith ? __fmul_rn(s[nb][c], a.scale_mul) : __fdiv_rn(s[nb][c], a.scale_div);
+      round2<T>(s[nb][0], s[nb][1]);
+      round2<T>(s[nb][2], s[nb][3]);
+    }
+    // ---- mask (:210-215): free slots, and causality among the chunk's own keys.  Masked logits become a huge
+    // negative FINITE value: exp(x - max) is exactly 0 as with the reference's finfo.min, and no inf - inf can
+    // arise.  Padding rows (row >= R) are left alone: nothing reads them.
     {
-      // column visibility of this thread's 16 columns: bit nb*2+cc.  Tiles of cached keys only need the slot
-      // map (free slots are masked); the chunk's own keys are causal per row (llama_patch.py:210-215).
       const bool cached_tile = (tile + 1) * TK <= n_phys;
-      uint32_t cm = 0;
+      const bool clean = cached_tile && !__any_sync(0xffffffffu, (lt[lane] | lt[lane + 32]) < 0);
+      if (!clean) {
+        const int new0 = tile * TK - n_phys;                      // index of the tile's first key among the chunk's keys
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
+        for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int col = nb * 8 + 2 * (lane & 3) + cc;
-          const int e = tile * TK + col;
-          const bool ok = cached_tile ? lt[col] >= 0 : (e < n_phys ? lt[col] >= 0 : e < NE);
-          cm |= (ok ? 1u : 0u) << (nb * 2 + cc);
-        }
-      const uint32_t cm0 = rv0 ? cm : 0u, cm1 = rv1 ? cm : 0u;
-      const int new0 = tile * TK - n_phys;                        // index of the tile's first key among the chunk's keys
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const bool hi = c >= 2;
-          bool vis = (((hi ? cm1 : cm0) >> (nb * 2 + (c & 1))) & 1u) != 0;
-          if (!cached_tile) {
-            const int jn = new0 + nb * 8 + 2 * (lane & 3) + (c & 1);
-            if (jn >= 0) vis = vis && jn <= (hi ? qi1 : qi0);     // causal inside the chunk
+          for (int cc = 0; cc < 2; ++cc) {
+            const int col = nb * 8 + 2 * (lane & 3) + cc;
+            const int jn = new0 + col;
+            const bool ok = jn < 0 ? lt[col] >= 0 : tile * TK + col < NE;
+            if (!(ok && (jn < 0 || jn <= qi0))) s[nb][cc] = NEG;
+            if (!(ok && (jn < 0 || jn <= qi1))) s[nb][2 + cc] = NEG;
           }
-          float v = Tr<T>::round_f(s[nb][c]);                                           // llama_patch.py:201
-          v = a.st.arith ? __fmul_rn(v, a.scale_mul) : __fdiv_rn(v, a.scale_div);       // :202
-          s[nb][c] = vis ? Tr<T>::round_f(v) : -INFINITY;
-        }
+      }
     }
 
     if (PASS == 1) {
-      float tm0 = -INFINITY, tm1 = -INFINITY;
+      float tm0 = NEG, tm1 = NEG;
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         tm0 = fmaxf(tm0, fmaxf(s[nb][0], s[nb][1]));
         tm1 = fmaxf(tm1, fmaxf(s[nb][2], s[nb][3]));
       }
       const float n0 = fmaxf(mrun0, tm0), n1 = fmaxf(mrun1, tm1);
-      if (n0 != -INFINITY) {
-        float acc = mrun0 == -INFINITY ? 0.f : lrun0 * expf(mrun0 - n0);
+      float acc0 = lrun0 * expf(mrun0 - n0), acc1 = lrun1 * expf(mrun1 - n1);
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) acc += expf(s[nb][0] - n0) + expf(s[nb][1] - n0);
-        lrun0 = acc; mrun0 = n0;
+      for (int nb = 0; nb < 8; ++nb) {
+        acc0 += expf(s[nb][0] - n0) + expf(s[nb][1] - n0);
+        acc1 += expf(s[nb][2] - n1) + expf(s[nb][3] - n1);
       }
-      if (n1 != -INFINITY) {
-        float acc = mrun1 == -INFINITY ? 0.f : lrun1 * expf(mrun1 - n1);
-#pragma unroll
-        for (int nb = 0; nb < 8; ++nb) acc += expf(s[nb][2] - n1) + expf(s[nb][3] - n1);
-        lrun1 = acc; mrun1 = n1;
-      }
+      lrun0 = acc0; mrun0 = n0; lrun1 = acc1; mrun1 = n1;
     } else {
       // ---- probabilities (llama_patch.py:218-219) -------------------------------------------------------------------
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
+      for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const bool hi = c >= 2;
           const float x = s[nb][c];
-          float ex = (x == -INFINITY) ? 0.f : expf(x - (hi ? M1 : M0));
-          ex = a.st.arith ? __fdiv_rn(ex, hi ? L1 : L0) : __fmul_rn(ex, hi ? L1 : L0);
-          s[nb][c] = Tr<T>::round_f(ex);
+          const float ex = expf(x - (hi ? M1 : M0));
+          s[nb][c] = a.st.arith ? div_rn_by(ex, hi ? L1 : L0, hi ? R1 : R0) : __fmul_rn(ex, hi ? L1 : L0);
         }
+        round2<T>(s[nb][0], s[nb][1]);
+        round2<T>(s[nb][2], s[nb][3]);
+      }
       // ---- O += P V: the C fragments of S are the A fragments of P ------------------------------------------------------
       const unsigned char* vt = Vs + stage * TILE_BYTES;
       {
@@ -344,47 +377,52 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
       }
       // ---- per-key column statistics of this tile -------------------------------------------------------------------------
       if (want_stats) {
-        // fold the g heads of a query (adjacent rows = lanes 4 apart), round to the model dtype
-        // (process_for_mqa_gqa, easykv.py:188-196), then sum p and model-dtype(p^2) over the queries (:450-451)
+        // fold the g heads of a query (adjacent rows = lanes 4 apart) and round to the model dtype
+        // (process_for_mqa_gqa, easykv.py:188-196); the lead lane of each query parks the folded row in shared
+        // memory, then every thread sums one key column over half of the CTA's queries: p and
+        // model-dtype(p^2), the chunk's row sums of easykv.py:450-451.
+        constexpr int QW = 16 / G;                                // queries per warp
+        const bool lead = ((lane >> 2) % G) == 0;
+        const int qlo = warp * QW + (lane >> 2) / G, qhi = qlo + 8 / G;
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb)
+        for (int nb = 0; nb < 8; ++nb) {
+          float l0 = s[nb][0], l1 = s[nb][1], h0 = s[nb][2], h1 = s[nb][3];
+          if (G > 1) {
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            float lo = s[nb][cc], hi = s[nb][2 + cc];
-            if (G > 1) {
-#pragma unroll
-              for (int off = 4; off < 4 * G; off <<= 1) {
-                lo += __shfl_xor_sync(0xffffffffu, lo, off);
-                hi += __shfl_xor_sync(0xffffffffu, hi, off);
+            for (int off = 4; off < 4 * G; off <<= 1) {
+              l0 += __shfl_xor_sync(0xffffffffu, l0, off); l1 += __shfl_xor_sync(0xffffffffu, l1, off);
+              h0 += __shfl_xor_sync(0xffffffffu, h0, off); h1 += __shfl_xor_sync(0xffffffffu, h1, off);
+            }
+            l0 = __fmul_rn(l0, inv_g); l1 = __fmul_rn(l1, inv_g); h0 = __fmul_rn(h0, inv_g); h1 = __fmul_rn(h1, inv_g);
+          }
+          if (lead) {                                             // pack2 rounds to the model dtype
+            const int col = nb * 8 + 2 * (lane & 3);
+            *reinterpret_cast<uint32_t*>(&pfs[qlo * PFP + col]) = pack2<T>(l0, l1);
+            if (G < 16) *reinterpret_cast<uint32_t*>(&pfs[qhi * PFP + col]) = pack2<T>(h0, h1);
+          }
+        }
+        __syncthreads();
+        {
+          constexpr int QR = MR / G;                              // queries of this CTA
+          constexpr int QH = QR >= 2 ? QR / 2 : 1;                // per thread: half of them
+          const int col = tid & (TK - 1), part = tid >> 6;
+          const int e = tile * TK + col;
+          float cs = 0.f, csq = 0.f;
+          if (part * QH < QR) {
+#pragma unroll 8
+            for (int qq = 0; qq < QH; ++qq) {
+              const int ql = part * QH + qq;                      // query row inside the CTA
+              const int qi = rb * QR + ql;                        // query index inside the chunk
+              if (qi < QL && (!tova || qi == QL - 1)) {
+                const float v = Tr<T>::to_f(pfs[ql * PFP + col]);
+                cs += v;
+                csq += Tr<T>::round_f(__fmul_rn(v, v));
               }
-              lo = Tr<T>::round_f(__fmul_rn(lo, inv_g));
-              hi = Tr<T>::round_f(__fmul_rn(hi, inv_g));
-            }
-            const bool lead = ((lane >> 2) % G) == 0;             // one lane per (query, column)
-            const bool use0 = lead && rv0 && (!tova || qi0 == QL - 1);
-            const bool use1 = lead && rv1 && (!tova || qi1 == QL - 1);
-            float cs = (use0 ? lo : 0.f) + (use1 ? hi : 0.f);
-            float csq = (use0 ? Tr<T>::round_f(__fmul_rn(lo, lo)) : 0.f) + (use1 ? Tr<T>::round_f(__fmul_rn(hi, hi)) : 0.f);
-#pragma unroll
-            for (int off = 4; off < 32; off <<= 1) {
-              cs += __shfl_xor_sync(0xffffffffu, cs, off);
-              csq += __shfl_xor_sync(0xffffffffu, csq, off);
-            }
-            if (lane < 4) {
-              const int col = nb * 8 + 2 * lane + cc;
-              cpart[(warp * TK + col) * 2] = cs;
-              cpart[(warp * TK + col) * 2 + 1] = csq;
             }
           }
-        __syncthreads();
-        if (tid < TK) {
-          const int e = tile * TK + tid;
           if (e < NE) {
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) { s1 += cpart[(w * TK + tid) * 2]; s2 += cpart[(w * TK + tid) * 2 + 1]; }
             float2* cg = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_cpart);
-            cg[((size_t)unit * pl.RB + rb) * pl.NEpad + e] = make_float2(s1, s2);
+            cg[((size_t)unit * (2 * pl.RB) + 2 * rb + part) * pl.NEpad + e] = make_float2(cs, csq);
           }
         }
       }
@@ -399,8 +437,8 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
       const float om0 = __shfl_xor_sync(0xffffffffu, mrun0, off), ol0 = __shfl_xor_sync(0xffffffffu, lrun0, off);
       const float om1 = __shfl_xor_sync(0xffffffffu, mrun1, off), ol1 = __shfl_xor_sync(0xffffffffu, lrun1, off);
       const float n0 = fmaxf(mrun0, om0), n1 = fmaxf(mrun1, om1);
-      lrun0 = (mrun0 == -INFINITY ? 0.f : lrun0 * expf(mrun0 - n0)) + (om0 == -INFINITY ? 0.f : ol0 * expf(om0 - n0));
-      lrun1 = (mrun1 == -INFINITY ? 0.f : lrun1 * expf(mrun1 - n1)) + (om1 == -INFINITY ? 0.f : ol1 * expf(om1 - n1));
+      lrun0 = lrun0 * expf(mrun0 - n0) + ol0 * expf(om0 - n0);
+      lrun1 = lrun1 * expf(mrun1 - n1) + ol1 * expf(om1 - n1);
       mrun0 = n0; mrun1 = n1;
     }
     if ((lane & 3) == 0) {
@@ -422,8 +460,20 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
 }
 
 // ---- 3. out = sum over splits of the partial outputs (llama_patch.py:222) ------------------------------------------------------
-template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a, const ChunkPlan pl) {
+template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a, const ChunkPlan pl, const int out_blocks) {
   using namespace tc;
+  if ((int)blockIdx.x >= out_blocks) {
+    // the second part of the grid: per-key column statistics summed over the row blocks (in row-block order)
+    const int idx = (blockIdx.x - out_blocks) * blockDim.x + threadIdx.x;     // (unit, key)
+    const int e = idx % pl.NEpad, unit = idx / pl.NEpad;
+    if (unit >= a.B * a.Hkv || e >= pl.NE) return;
+    const float2* cg = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_cpart) +
+                       (size_t)unit * (2 * pl.RB) * pl.NEpad;
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < 2 * pl.RB; ++r) { const float2 v = cg[(size_t)r * pl.NEpad + e]; s1 += v.x; s2 += v.y; }
+    reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_csum)[(size_t)unit * pl.NEpad + e] = make_float2(s1, s2);
+    return;
+  }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // (unit, row, dim4)
   const int d4 = idx % (D / 4), r = (idx / (D / 4)) % pl.R, unit = idx / ((D / 4) * pl.R);
   if (unit >= a.B * a.Hkv) return;
@@ -491,13 +541,12 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
   u.new_slots = ns;
   u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
   u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
-  const float2* cg = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_cpart) +
-                     (size_t)unit * pl.RB * pl.NEpad;
+  const float2* csum = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_csum) +
+                       (size_t)unit * pl.NEpad;
   auto accf = [&](int e, float& ds, float& dsq) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = 0; r < pl.RB; ++r) { const float2 v = cg[(size_t)r * pl.NEpad + e]; s1 += v.x; s2 += v.y; }
-    ds = Tr<T>::round_f(s1);               // p.sum(dim=1) is a model-dtype result (easykv.py:450)
-    dsq = Tr<T>::round_f(s2);              // (p**2).sum(dim=1) likewise (:451)
+    const float2 v = csum[e];
+    ds = Tr<T>::round_f(v.x);              // p.sum(dim=1) is a model-dtype result (easykv.py:450)
+    dsq = Tr<T>::round_f(v.y);             // (p**2).sum(dim=1) likewise (:451)
   };
   state_select_apply(a.st, u, a.n_before, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
 }
@@ -509,7 +558,7 @@ template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, 
   const TailSmem TL(pl.NE, a.q_len, a.st.evict);
   if (TL.total > 227 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "chunk tail: %d bytes of shared memory needed", TL.total);
   const int smem1 = MR * PITCH + STAGES * TILE_BYTES + STAGES * TK * 4;
-  const int smem2 = MR * PITCH + 2 * 2 * TILE_BYTES + 2 * TK * 4 + NW * TK * 2 * 4;
+  const int smem2 = MR * PITCH + 2 * 2 * TILE_BYTES + 2 * TK * 4 + MR * (TK + 2) * 2;
   static thread_local int configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -530,8 +579,9 @@ template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, 
   chunk_tc_kernel<T, G, 2><<<grid, NT, smem2, stream>>>(a, pl);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<2> launch", err);
   count_launch();
-  const int nout = U * pl.R * (D / 4);
-  chunk_out_kernel<T, G><<<(nout + 255) / 256, 256, 0, stream>>>(a, pl);
+  const int out_blocks = (U * pl.R * (D / 4) + 255) / 256;
+  const int col_blocks = a.st.accumulate ? (U * pl.NEpad + 255) / 256 : 0;
+  chunk_out_kernel<T, G><<<out_blocks + col_blocks, 256, 0, stream>>>(a, pl, out_blocks);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_out_kernel launch", err);
   count_launch();
   chunk_tail_kernel<T><<<U, TAIL_NT, TL.total, stream>>>(a, pl);
