@@ -500,9 +500,12 @@ static int launch_decode_single(const KernelArgs& a, cudaStream_t stream) {
 int launch_decode(const KernelArgs& a, cudaStream_t stream) {
   if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean) return EKV_ERR_UNSUPPORTED;
   if (a.st.evict <= 1) {
+    const int G = a.H / a.Hkv;
     if (decode_cluster_size() > 0) return launch_decode_cluster(a, false, stream);
-    if (decode_cluster_size() == 0 && a.B * a.Hkv * 2 <= 148) {
-      const int rc = launch_decode_cluster(a, true, stream);
+    // g = 8: the persistent kernel's 544-thread CTAs leave 96 registers per thread and spill; the cluster
+    // kernel's 288-thread CTAs do not
+    if (decode_cluster_size() == 0 && (a.B * a.Hkv * 2 <= 148 || G >= 8)) {
+      const int rc = launch_decode_cluster(a, G < 8, stream);
       if (rc != EKV_ERR_UNSUPPORTED) return rc;
     }
   }

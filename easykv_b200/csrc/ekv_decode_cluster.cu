@@ -23,6 +23,7 @@
 //
 // Replaces the same reference lines as ekv_decode.cu.
 #include "ekv_decode_common.cuh"
+#include "ekv_mma.cuh"
 
 namespace ekv {
 
@@ -43,10 +44,13 @@ __device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long
   asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
+constexpr int TC_PITCH = 272;                     // tensor-core variant: bytes per shared-memory row (256 + 16 keeps
+constexpr int TC_TILE_BYTES = 64 * TC_PITCH;      // ldmatrix conflict-free), 64 rows per tile
+
 template <typename T> struct ClusterSmem {
-  int off_bar, off_red, off_q, off_k, off_v, off_ns, off_lj, off_plog, off_ka, off_kb, off_flag;
-  int off_xmax, off_xsum, off_xout, off_xbest, off_xcnt, off_ring, fixed, slp;
-  __host__ __device__ ClusterSmem(int G, int slice, int C) {
+  int off_bar, off_red, off_xnew, off_q, off_qp, off_k, off_v, off_ns, off_lj, off_plog, off_ka, off_kb, off_flag;
+  int off_xmax, off_xsum, off_xout, off_xbest, off_xcnt, off_hist, off_xhist, off_ring, fixed, slp;
+  __host__ __device__ ClusterSmem(int G, int slice, int C, bool tc = false) {
     using Cfg = DecodeCfg<T>;
     const int NEl = slice + 1;                    // rank 0 also owns the appended token's entry
     slp = align_up(NEl, 8);
@@ -54,6 +58,8 @@ template <typename T> struct ClusterSmem {
     off_bar = o; o += 2 * Cfg::MAX_STAGES * 8;
     o = align_up(o, 128);
     off_red = o; o += 2 * 8 * Cfg::NWARP * 4 + 64 * 8 + 64 * 4;     // float maxima/sums | u64 tuples | int counts
+    off_xnew = o; o += 16 * 4;                                      // the appended token's logits (tensor-core variant)
+    off_qp = o; o += tc ? 16 * TC_PITCH : 0;                        // q as a 16-row A operand, rows >= G zero
     off_q = o; o += G * Cfg::ROW_BYTES;
     off_k = o; o += Cfg::ROW_BYTES;
     off_v = o; o += Cfg::ROW_BYTES;
@@ -68,6 +74,8 @@ template <typename T> struct ClusterSmem {
     off_xout = o; o += G * Cfg::D * 4;            // [C][G][D/C]
     off_xbest = align_up(o, 16); o = off_xbest + 2 * C * 16;
     off_xcnt = o; o += 2 * C * 4;
+    off_hist = align_up(o, 16); o = off_hist + 256 * 4 + 16;          // radix select: local histogram + 4 ints
+    off_xhist = o; o += 2 * C * 256 * 4;                              // every CTA's histogram, double-buffered
     o = align_up(o, 128);
     off_ring = o;                                 // the ring doubles as the cross-warp P·V scratch [NWARP][G][D] fp32
     fixed = o;
@@ -75,14 +83,21 @@ template <typename T> struct ClusterSmem {
   static __host__ __device__ int min_ring(int G) { return DecodeCfg<T>::NWARP * G * DecodeCfg<T>::D * 4; }
 };
 
-template <typename T, int G>
-__global__ void __launch_bounds__(DecodeCfg<T>::NCONS + 32, 1)
+// TC: the contractions run on the tensor cores (mma.sync m16n8k16, the g query heads padded to a 16-row A
+// operand).  With g >= 4 the FP32 pipes cannot keep up with HBM (g FMAs per 2 loaded bytes for Q·K^T and again
+// for P·V: measured FMA-bound at 0.17-0.45 of the roofline on the Mistral / 70B layouts), the tensor cores can.
+// The producer then lands every row with its own bulk copy at a 272-byte pitch so that ldmatrix is
+// conflict-free.  Only for 16-bit dtypes.
+template <typename T, int G, bool TC>
+__global__ void __launch_bounds__(DecodeCfg<T>::NCONS + 32, (TC || G <= 4) ? 2 : 1)
 decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   using Cfg = DecodeCfg<T>;
   constexpr int D = Cfg::D, NWARP = Cfg::NWARP, NCONS = Cfg::NCONS, RPT = Cfg::RPT, TILE_ROWS = Cfg::TILE_ROWS;
+  constexpr int TILEB = TC ? TC_TILE_BYTES : Cfg::TILE_BYTES;
+  static_assert(!TC || (sizeof(T) == 2 && TILE_ROWS == 64), "tensor-core variant: 16-bit dtypes");
   extern __shared__ __align__(128) unsigned char smem[];
   const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
-  const ClusterSmem<T> L(G, slice, C);
+  const ClusterSmem<T> L(G, slice, C, TC);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* empty = full + Cfg::MAX_STAGES;
   unsigned char* ring = smem + L.off_ring;
@@ -104,7 +119,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
 
   if (warp == NWARP) {
     // ===== TMA producer ==============================================================================
-    if (lane == 0) {
+    if (TC || lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
       const T* Kg = reinterpret_cast<const T*>(a.K) + ((size_t)unit * a.cap + lo) * D;
       const T* Vg = reinterpret_cast<const T*>(a.V) + ((size_t)unit * a.cap + lo) * D;
@@ -114,21 +129,29 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
         if (use > 0) {
           // A slot last filled with a V tile is only released after the consumers have passed the two
           // softmax cluster barriers.  A cluster barrier completes when every NON-EXITED thread of the
-          // cluster has arrived, so this thread has to take part in those two phases before it may
+          // cluster has arrived, so the producer has to take part in those two phases before it may
           // block on such a slot (it exits before the later ones; exited threads are not waited for).
           if (!synced && i - stages >= nt) {
             cluster_sync_unaligned();
             cluster_sync_unaligned();
             synced = true;
           }
-          mbar_wait(&empty[s], (use - 1) & 1);
+          if (!TC || lane == 0) mbar_wait(&empty[s], (use - 1) & 1);
         }
         const int tt = i < nt ? i : i - nt;
         const int rows = min(TILE_ROWS, nloc - tt * TILE_ROWS);
-        const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
         const T* src = (i < nt ? Kg : Vg) + (size_t)tt * TILE_ROWS * D;
-        mbar_arrive_expect_tx(&full[s], bytes);
-        tma_bulk_g2s(ring + (size_t)s * Cfg::TILE_BYTES, src, bytes, &full[s], pol);
+        if (TC) {
+          // one 256-byte bulk copy per row, spread over the warp's lanes, all signalling the slot's barrier
+          if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)rows * Cfg::ROW_BYTES);
+          __syncwarp();
+          for (int r = lane; r < rows; r += 32)
+            tma_bulk_g2s(ring + (size_t)s * TILEB + (size_t)r * TC_PITCH, src + (size_t)r * D, Cfg::ROW_BYTES, &full[s], pol);
+        } else {
+          const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
+          mbar_arrive_expect_tx(&full[s], bytes);
+          tma_bulk_g2s(ring + (size_t)s * TILEB, src, bytes, &full[s], pol);
+        }
         if (++s == stages) { s = 0; ++use; }
       }
     }
@@ -156,6 +179,9 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   float* xout = reinterpret_cast<float*>(smem + L.off_xout);
   unsigned long long* xbest = reinterpret_cast<unsigned long long*>(smem + L.off_xbest);
   int* xcnt = reinterpret_cast<int*>(smem + L.off_xcnt);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L.off_hist);
+  int* hmisc = reinterpret_cast<int*>(hist + 256);
+  uint32_t* xhist = reinterpret_cast<uint32_t*>(smem + L.off_xhist);
 
   auto finish_logit = [&](float dot, bool valid) -> T {
     float x = Tr<T>::round_f(dot);                                           // llama_patch.py:201
@@ -163,6 +189,9 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     return valid ? Tr<T>::from_f(x) : neg_inf<T>();
   };
 
+  unsigned long long* tl = a.timeline ? a.timeline + (size_t)blockIdx.x * 8 : nullptr;   // profiling hook
+  auto stamp = [&](int i) { if (tl && tid == 0) tl[i] = clock64(); };
+  stamp(0);
   // ---- header ----------------------------------------------------------------------------------------
   {
     const uint4* qg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D);
@@ -188,21 +217,105 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       }
     }
   }
+  unsigned char* qp = smem + L.off_qp;
+  float* xnew_s = reinterpret_cast<float*>(smem + L.off_xnew);
+  if (TC) {
+    // q again, as the 16-row A operand (rows >= G are zero)
+    const uint4* qg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D);
+    for (int i = tid; i < 16 * 16; i += NCONS) {
+      const int r = i >> 4, c = i & 15;
+      *reinterpret_cast<uint4*>(qp + r * TC_PITCH + c * 16) = r < G ? qg[r * 16 + c] : make_uint4(0, 0, 0, 0);
+    }
+    // rows of a partially filled LAST tile that no earlier tile has ever written hold whatever the shared
+    // memory held; P·V multiplies them by p == 0, so they must at least be finite
+    const int rows_last = nloc - (nt - 1) * TILE_ROWS;
+    if (nt > 0 && rows_last < TILE_ROWS) {
+      for (int which = 0; which < 2; ++which) {
+        const int idx = which * nt + nt - 1;                  // sequence index of the last K / V tile
+        if (idx < stages) {
+          unsigned char* base = ring + (size_t)idx * TILEB;
+          for (int i = tid; i < (TILE_ROWS - rows_last) * 16; i += NCONS)
+            *reinterpret_cast<uint4*>(base + (rows_last + (i >> 4)) * TC_PITCH + (i & 15) * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  }
   grp.sync();
-  Row8<T> qr[G], knew;
+  Row8<T> qr[TC ? 1 : G], knew;
+  if (!TC) {
 #pragma unroll
-  for (int g = 0; g < G; ++g) qr[g].load(qh + g * D, l16);
+    for (int g = 0; g < (TC ? 1 : G); ++g) qr[g].load(qh + g * D, l16);
+  }
   knew.load(kh, l16);
 
-  // ---- K phase (same structure as ekv_decode.cu) -----------------------------------------------------------
+  stamp(1);
+  // ---- K phase -------------------------------------------------------------------------------------------------
+  float mloc = -INFINITY;
+  int s = 0;
+  uint32_t par = 0;
+  float xnew[G];
+  const int gw = warp;
+  if constexpr (TC) {
+    // tensor cores: warp w owns keys [8w, 8w+8) of every 64-key tile; A = q (16 x 128, rows >= G zero)
+    uint32_t aq[8][4];
+    {
+      const int row = (lane & 7) + ((lane >> 3) & 1) * 8, colb = (lane >> 4) * 16;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) ldsm_x4(smem_u32(qp + row * TC_PITCH + ks * 32 + colb), aq[ks]);
+    }
+    const int g_t = lane >> 2;                                  // the head (A row) this thread's accumulators belong to
+    for (int i = 0; i < nt; ++i) {
+      mbar_wait(&full[s], (par >> s) & 1u);
+      par ^= 1u << s;
+      const unsigned char* tile = ring + (size_t)s * TILEB;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t kaddr = smem_u32(tile + (warp * 8 + (lane & 7)) * TC_PITCH + (lane >> 3) * 16);
+#pragma unroll
+      for (int ksp = 0; ksp < 4; ++ksp) {                       // two k-steps (32 dims) per ldmatrix.x4
+        uint32_t bk[4];
+        ldsm_x4(kaddr + ksp * 64, bk);
+        mma16816<T>(c, aq[2 * ksp], bk[0], bk[1]);
+        mma16816<T>(c, aq[2 * ksp + 1], bk[2], bk[3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      s = s + 1 == stages ? 0 : s + 1;
+      if (g_t < G) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int e = i * TILE_ROWS + warp * 8 + 2 * (lane & 3) + cc;
+          if (e < nloc) {
+            const T x = finish_logit(c[cc], lj[e] >= 0);
+            plog[g_t * slp + e] = x;
+            mloc = fmaxf(mloc, Tr<T>::to_f(x));
+          }
+        }
+      }
+    }
+    // the appended token's own key (rank 0 owns it): one half-warp per head, FMA path
+    if (tid < 16 * G) {
+      const int g = tid >> 4;
+      Row8<T> qg8;
+      qg8.load(qh + g * D, l16);
+      float v = dot8(knew, qg8, 0.f);
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      const T x = finish_logit(v, true);
+      if (l16 == 0) {
+        if (rank == 0) plog[g * slp + nloc] = x;
+        xnew_s[g] = rank == 0 ? Tr<T>::to_f(x) : -INFINITY;
+      }
+    }
+    // this thread's running max covers head g_t only: combine the four lanes of the row
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
+    if ((lane & 3) == 0 && g_t < G) red[g_t * NWARP + gw] = mloc;
+  } else {
   constexpr int NVT = RPT * G;
   constexpr int TB = NVT >= 16 ? 1 : 16 / NVT;
   constexpr int NB = NVT >= 16 ? NVT / 16 : 1;
   static_assert(NVT * TB == 16 * NB, "batch must be a whole number of 16-value reductions");
   const int vi0 = bitrev_idx<16>(l16);
-  float mloc = -INFINITY;
-  int s = 0;
-  uint32_t par = 0;
   for (int i0 = 0; i0 < nt; i0 += TB) {
     float part[NVT * TB];
 #pragma unroll
@@ -243,7 +356,6 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     }
   }
   // the appended token's own key: rank 0 owns it (every half-warp computes it, the shuffles need all lanes)
-  float xnew[G];
   {
     float v[G];
 #pragma unroll
@@ -258,15 +370,19 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     }
   }
 
+  }
+
+  stamp(2);
   // ---- softmax across the cluster ------------------------------------------------------------------------
-  const int gw = warp;
   float mx[G], inv[G];
   {
-    const int my_g = vi0 % G;
+    if constexpr (!TC) {
+      const int my_g = bitrev_idx<16>(l16) % G;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const float m = fmaxf(warp_max(my_g == g ? mloc : -INFINITY), xnew[g]);
-      if (lane == 0) red[g * NWARP + gw] = m;
+      for (int g = 0; g < G; ++g) {
+        const float m = fmaxf(warp_max(my_g == g ? mloc : -INFINITY), xnew[g]);
+        if (lane == 0) red[g * NWARP + gw] = m;
+      }
     }
     grp.sync();
     if (tid < G * C) {                                        // thread (g, p): this slice's max of head g -> peer p
@@ -274,6 +390,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       float v = red[g * NWARP];
 #pragma unroll
       for (int w = 1; w < NWARP; ++w) v = fmaxf(v, red[g * NWARP + w]);
+      if (TC) v = fmaxf(v, xnew_s[g]);
       st_cluster_f32(map_to_rank(&xmax[rank * G + g], p), v);
     }
     cluster_sync_all();                                                             // (1)
@@ -319,7 +436,62 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   }
   grp.sync();
 
+  stamp(3);
   // ---- V phase ---------------------------------------------------------------------------------------------
+  if constexpr (TC) {
+    // warp w: keys [16*(w%4), +16) of every tile x dims [64*(w/4), +64); A = P (rows = heads) from shared memory
+    const int kq = warp & 3, dh = warp >> 2, g_t = lane >> 2;
+    float o[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[nb][c] = 0.f;
+    const int key_l = (lane & 7) + ((lane >> 3) & 1) * 8, dim_l = (lane >> 4) * 16;
+    for (int i = 0; i < nt; ++i) {
+      mbar_wait(&full[s], (par >> s) & 1u);
+      par ^= 1u << s;
+      const unsigned char* tile = ring + (size_t)s * TILEB;
+      const int e0 = i * TILE_ROWS + kq * 16 + 2 * (lane & 3);
+      uint32_t pa[4] = {0u, 0u, 0u, 0u};
+      if (g_t < G) {                                            // keys >= nloc (incl. the appended token) contribute nothing here
+        const T* pr = plog + g_t * slp;
+        const uint32_t lo0 = e0 < nloc ? (uint32_t)(*reinterpret_cast<const uint16_t*>(&pr[e0])) : 0u;
+        const uint32_t hi0 = e0 + 1 < nloc ? (uint32_t)(*reinterpret_cast<const uint16_t*>(&pr[e0 + 1])) : 0u;
+        const uint32_t lo1 = e0 + 8 < nloc ? (uint32_t)(*reinterpret_cast<const uint16_t*>(&pr[e0 + 8])) : 0u;
+        const uint32_t hi1 = e0 + 9 < nloc ? (uint32_t)(*reinterpret_cast<const uint16_t*>(&pr[e0 + 9])) : 0u;
+        pa[0] = lo0 | (hi0 << 16);
+        pa[2] = lo1 | (hi1 << 16);
+      }
+      const uint32_t vaddr = smem_u32(tile + (kq * 16 + key_l) * TC_PITCH + dh * 128 + dim_l);
+#pragma unroll
+      for (int dbp = 0; dbp < 4; ++dbp) {
+        uint32_t bv[4];
+        ldsm_x4_trans(vaddr + dbp * 32, bv);
+        mma16816<T>(o[2 * dbp], pa, bv[0], bv[1]);
+        mma16816<T>(o[2 * dbp + 1], pa, bv[2], bv[3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      s = s + 1 == stages ? 0 : s + 1;
+    }
+    grp.sync();                     // every tile of this CTA has been consumed: the ring is free scratch now
+    float* part = reinterpret_cast<float*>(ring);               // [4 key quarters][G][D]
+    if (g_t < G) {
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+        *reinterpret_cast<float2*>(&part[(kq * G + g_t) * D + dh * 64 + nb * 8 + 2 * (lane & 3)]) = make_float2(o[nb][0], o[nb][1]);
+    }
+    grp.sync();
+    const int DPC = D / C;                                      // output dims finished by each CTA
+    for (int i = tid; i < G * D; i += NCONS) {
+      const int g = i / D, dim = i % D;
+      float v = part[i];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) v += part[w * G * D + i];
+      if (rank == 0) v = fmaf(Tr<T>::to_f(plog[g * slp + nloc]), Tr<T>::to_f(vh[dim]), v);     // the appended token's own value row
+      st_cluster_f32(map_to_rank(&xout[(rank * G + g) * DPC + dim % DPC], dim / DPC), v);
+    }
+  } else {
   float oacc[G][8];
 #pragma unroll
   for (int g = 0; g < G; ++g)
@@ -375,6 +547,9 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     }
   }
 
+  }
+
+  stamp(4);
   // ---- tail, pass 1: this slice's policy state and selection keys ------------------------------------------------
   const ekv_step& st = a.st;
   const int P = st.score_offset;
@@ -439,10 +614,10 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   bool found = false;
   uint32_t l_c = 0;
   int owner = -1, e_c = -1;
-  auto local_best = [&]() {
+  auto local_best = [&](uint8_t need) {
     Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
     for (int e = tid; e < NEl; e += NCONS) {
-      if ((flag[e] & (need_flag | F_REJ)) == need_flag) {
+      if ((flag[e] & (need | F_REJ)) == need) {
         Tuple128 t;
         t.hi = ((unsigned long long)keyB[e] << 32) | keyA[e];
         t.lo = ((unsigned long long)(uint32_t)lj[e] << 32) | ((uint32_t)rank << 24) | (uint32_t)e;
@@ -470,14 +645,16 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     return none;
   };
   int attempt = 0;
+  constexpr int MAX_TRY = 2;                                    // candidate walks before the radix select
   if (single) {
-    const Tuple128 b = local_best();
+    const Tuple128 b = local_best(need_flag);
     if (tid < C) {
       const uint32_t dst = map_to_rank(&xbest[(0 * C + rank) * 2], tid);
       st_cluster_u64(dst, b.hi);
       st_cluster_u64(dst + 8, b.lo);
     }
   }
+  stamp(5);
   cluster_sync_all();                                                               // (3) partial outputs + candidates
   {
     // finish this CTA's share of the output: dims [rank*DPC, (rank+1)*DPC) of every head (llama_patch.py:222)
@@ -532,7 +709,112 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       if (rank == owner && tid == 0) flag[e_c] |= F_REJ;
       grp.sync();
       ++attempt;
-      const Tuple128 b = local_best();
+      if (attempt >= MAX_TRY) {
+        // The low-mean slots keep falling outside the k_feasible lowest std: stop walking and select properly.
+        // Cluster-wide MSB-first radix select (8 bits per pass) of the k-th smallest 64-bit key (std key,
+        // logical index) — unique keys, so no tie handling — then one cluster argmin over the feasible set.
+        int xpass = 0;                                             // exchange-buffer parity across both selects
+        // m-th smallest (1-based) 32-bit key over {e : pred(e)}: threshold T, how many entries equal to T belong
+        // to the m smallest (need) and how many equal T (tcount) — ekv_select.cuh's radix_select, with the
+        // histogram of every pass summed over the cluster
+        auto cluster_radix32 = [&](int m, auto key, auto pred, uint32_t& Tk, int& need, int& tcount) {
+          uint32_t prefix = 0u, maskp = 0u;
+          int rem = m;
+          tcount = 0;
+#pragma unroll 1
+          for (int shift = 24; shift >= 0; shift -= 8, ++xpass) {
+            const int hb = xpass & 1;
+            hist[tid] = 0u;                                        // NCONS == 256 bins
+            grp.sync();
+            for (int e = tid; e < NEl; e += NCONS) {
+              if (pred(e)) {
+                const uint32_t k = key(e);
+                if ((k & maskp) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+              }
+            }
+            grp.sync();
+            {
+              const uint32_t v = hist[tid];
+              for (int p2 = 0; p2 < C; ++p2) st_cluster_u32(map_to_rank(&xhist[(hb * C + rank) * 256 + tid], p2), v);
+            }
+            cluster_sync_all();                                                     // (5) one per radix pass
+            if (tid < 32) {
+              uint32_t loc[8], sum = 0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t t = 0;
+                for (int p2 = 0; p2 < C; ++p2) t += xhist[(hb * C + p2) * 256 + tid * 8 + j];
+                loc[j] = t; sum += t;
+              }
+              uint32_t inc = sum;
+#pragma unroll
+              for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o2);
+                if (lane >= o2) inc += t;
+              }
+              const uint32_t exc = inc - sum, total = __shfl_sync(0xffffffffu, inc, 31);
+              uint32_t want = (uint32_t)rem;
+              if (want > total) want = total;                      // fewer candidates than requested: all of them
+              if (want == 0) want = 1;
+              if (exc < want && want <= inc) {
+                uint32_t cum = exc;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (want <= cum + loc[j]) { hmisc[0] = tid * 8 + j; hmisc[1] = (int)cum; hmisc[2] = (int)loc[j]; break; }
+                  cum += loc[j];
+                }
+              }
+              if (lane == 0 && total == 0) { hmisc[0] = 255; hmisc[1] = 0; hmisc[2] = 0; }
+            }
+            grp.sync();
+            prefix |= (uint32_t)hmisc[0] << shift;
+            maskp |= 255u << shift;
+            rem -= hmisc[1];
+            tcount = hmisc[2];
+            grp.sync();                                            // hmisc / hist are rewritten by the next pass
+          }
+          Tk = prefix;
+          need = rem < tcount ? rem : tcount;
+          if (need < 0) need = 0;
+        };
+        uint32_t T1, jT = 0xffffffffu;
+        int need1, tc1;
+        cluster_radix32(st.k_feasible, [&](int e) { return keyA[e]; }, [&](int e) { return (flag[e] & F_CAND) != 0; }, T1, need1, tc1);
+        if (need1 < tc1) {                                         // the cut falls inside a run of equal std: lowest logical index first
+          int nd, tc;
+          cluster_radix32(need1, [&](int e) { return (uint32_t)lj[e]; },
+                          [&](int e) { return (flag[e] & F_CAND) && keyA[e] == T1; }, jT, nd, tc);
+        }
+        for (int e = tid; e < NEl; e += NCONS) {
+          if (flag[e] & F_CAND) {
+            const uint32_t ka = keyA[e];
+            const bool feas = ka < T1 || (ka == T1 && (uint32_t)lj[e] <= jT);
+            flag[e] = (uint8_t)((flag[e] & ~F_REJ) | (feas ? F_FEAS : 0));
+          }
+        }
+        grp.sync();
+        const Tuple128 b = local_best((uint8_t)F_FEAS);
+        if (tid < C) {
+          const uint32_t dst = map_to_rank(&xbest[((attempt & 1) * C + rank) * 2], tid);
+          st_cluster_u64(dst, b.hi);
+          st_cluster_u64(dst + 8, b.lo);
+        }
+        cluster_sync_all();                                                         // (6)
+        const int pb2 = attempt & 1;
+        Tuple128 best2; best2.hi = xbest[(pb2 * C) * 2]; best2.lo = xbest[(pb2 * C) * 2 + 1];
+        for (int p2 = 1; p2 < C; ++p2) {
+          Tuple128 t; t.hi = xbest[(pb2 * C + p2) * 2]; t.lo = xbest[(pb2 * C + p2) * 2 + 1];
+          if (tuple_less(t, best2)) best2 = t;
+        }
+        if (best2.lo != ~0ull) {
+          l_c = (uint32_t)(best2.lo >> 32);
+          owner = (int)((best2.lo >> 24) & 0xffu);
+          e_c = (int)(best2.lo & 0xffffffu);
+          found = true;
+        }
+        break;
+      }
+      const Tuple128 b = local_best(need_flag);
       if (tid < C) {
         const uint32_t dst = map_to_rank(&xbest[((attempt & 1) * C + rank) * 2], tid);
         st_cluster_u64(dst, b.hi);
@@ -545,6 +827,8 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     found = true;
   }
 
+  stamp(6);
+  if (tl && tid == 0) tl[7] = (unsigned long long)attempt;
   // ---- apply: renumber this slice, free the victim's slot, publish the new slot ----------------------------------------
   const bool is_range = evicting && st.policy == EKV_POLICY_RANGE;
   for (int e = tid; e < NEl; e += NCONS) {
@@ -573,7 +857,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int G>
+template <typename T, int G, bool TC>
 static int launch_cluster_tg(const KernelArgs& a, int C, int slice, int stages, int smem_bytes, cudaStream_t stream) {
   static thread_local int configured[16] = {0};
   int dev = 0;
@@ -581,7 +865,7 @@ static int launch_cluster_tg(const KernelArgs& a, int C, int slice, int stages, 
   if (dev >= 16) dev = 15;
   cudaError_t err;
   if (!configured[dev]) {
-    err = cudaFuncSetAttribute(decode_cluster_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    err = cudaFuncSetAttribute(decode_cluster_kernel<T, G, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(decode_cluster)", err);
     configured[dev] = 1;
   }
@@ -597,28 +881,36 @@ static int launch_cluster_tg(const KernelArgs& a, int C, int slice, int stages, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  err = cudaLaunchKernelEx(&cfg, decode_cluster_kernel<T, G>, a, stages, slice);
+  err = cudaLaunchKernelEx(&cfg, decode_cluster_kernel<T, G, TC>, a, stages, slice);
   if (err != cudaSuccess) return set_cuda_error("decode_cluster_kernel launch", err);
   count_launch();
   return EKV_OK;
 }
 
-// Chooses the cluster size: the smallest power of two for which a slice fits one CTA, doubled while the
-// grid still fits the chip in one wave (more CTAs = more of the chip's HBM bandwidth in flight).
-template <typename T, int G> static int plan_cluster(const KernelArgs& a, int sms, int force_c, int& C, int& slice, int& stages, int& smem) {
+// Chooses the cluster size.  FMA variant: the smallest power of two for which a slice fits one CTA, doubled
+// while the grid still fits the chip in one wave (more CTAs = more of the chip's HBM bandwidth in flight).
+// Tensor-core variant: slices of at most ~1.5K slots so that a CTA needs less than half an SM's shared memory
+// and two CTAs (of different clusters) overlap each other's barrier and tail latencies.
+template <typename T, int G, bool TC>
+static int plan_cluster(const KernelArgs& a, int sms, int force_c, int& C, int& slice, int& stages, int& smem) {
   using Cfg = DecodeCfg<T>;
-  const int U = a.B * a.Hkv, sm_total = 227 * 1024;
+  constexpr int TILEB = TC ? TC_TILE_BYTES : Cfg::TILE_BYTES;
+  const int U = a.B * a.Hkv, sm_total = 227 * 1024, half_sm = 112 * 1024;
   auto fits = [&](int c, int& sl, int& stg, int& bytes) {
     sl = align_up((a.n_phys + c - 1) / c, 8);
     if (sl < 8) sl = 8;
-    const ClusterSmem<T> L(G, sl, c);
+    const ClusterSmem<T> L(G, sl, c, TC);
+    const int min_ring = ClusterSmem<T>::min_ring(G) > 3 * TILEB ? ClusterSmem<T>::min_ring(G) : 3 * TILEB;
     int ring = sm_total - L.fixed;
-    if (ring < ClusterSmem<T>::min_ring(G) || ring < 3 * Cfg::TILE_BYTES) return false;
-    stg = ring / Cfg::TILE_BYTES;
+    if (ring < min_ring) return false;
+    // more CTAs than SMs: leave room for a second CTA per SM so that one CTA's barrier / tail latencies overlap
+    // the other's streaming (the FMA variant with g = 8 needs too many registers for that)
+    if ((TC || (G <= 4 && U * c > sms)) && half_sm - L.fixed >= min_ring) ring = half_sm - L.fixed;
+    stg = ring / TILEB;
     if (stg > Cfg::MAX_STAGES) stg = Cfg::MAX_STAGES;
     const int tiles = 2 * ((sl + Cfg::TILE_ROWS - 1) / Cfg::TILE_ROWS);
     if (stg > tiles) stg = tiles < 3 ? 3 : tiles;
-    bytes = L.fixed + stg * Cfg::TILE_BYTES;
+    bytes = L.fixed + stg * TILEB;
     if (bytes < L.fixed + ClusterSmem<T>::min_ring(G)) bytes = L.fixed + ClusterSmem<T>::min_ring(G);
     return true;
   };
@@ -627,15 +919,23 @@ template <typename T, int G> static int plan_cluster(const KernelArgs& a, int sm
     if (force_c && c != force_c) continue;
     int sl, stg, bytes;
     if (!fits(c, sl, stg, bytes)) continue;
-    if (best && !force_c && (U * c > sms || sl < 2 * Cfg::TILE_ROWS)) break;      // keep one wave, keep slices non-trivial
+    if (best && !force_c) {
+      if (TC) {
+        if (slice <= 1536 && (U * c > 2 * sms || sl < 4 * Cfg::TILE_ROWS)) break;   // small enough already; keep slices non-trivial
+      } else if (U * c > sms || sl < 2 * Cfg::TILE_ROWS) {
+        break;                                                                      // keep one wave, keep slices non-trivial
+      }
+    }
     best = c; C = c; slice = sl; stages = stg; smem = bytes;
   }
   return best ? EKV_OK : EKV_ERR_UNSUPPORTED;
 }
 
 int decode_cluster_size();   // ekv_api.cu (env EKV_DECODE_CLUSTER): 0 = automatic, else forced cluster size
+int decode_variant();        // ekv_api.cu: 4 = use the (experimental) tensor-core variant
 
-template <typename T, int G> static int launch_cluster_plan(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
+template <typename T, int G, bool TC>
+static int launch_cluster_plan_v(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
   static thread_local int sm_count[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -645,10 +945,17 @@ template <typename T, int G> static int launch_cluster_plan(const KernelArgs& a,
     if (err != cudaSuccess) return set_cuda_error("cudaDeviceGetAttribute", err);
   }
   int C = 0, slice = 0, stages = 0, smem = 0;
-  const int rc = plan_cluster<T, G>(a, sm_count[dev], decode_cluster_size(), C, slice, stages, smem);
+  const int rc = plan_cluster<T, G, TC>(a, sm_count[dev], decode_cluster_size(), C, slice, stages, smem);
   if (rc) return rc;
-  if (only_if_better && C == 1) return EKV_ERR_UNSUPPORTED;   // the single-CTA kernels serve this shape
-  return launch_cluster_tg<T, G>(a, C, slice, stages, smem, stream);
+  if (only_if_better && C == 1 && !TC) return EKV_ERR_UNSUPPORTED;   // the single-CTA kernels serve this shape
+  return launch_cluster_tg<T, G, TC>(a, C, slice, stages, smem, stream);
+}
+
+template <typename T, int G> static int launch_cluster_plan(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
+  if constexpr (sizeof(T) == 2 && G >= 4) {
+    if (decode_variant() == 4) return launch_cluster_plan_v<T, G, true>(a, only_if_better, stream);
+  }
+  return launch_cluster_plan_v<T, G, false>(a, only_if_better, stream);
 }
 
 template <typename T> static int launch_cluster_t(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {

@@ -279,6 +279,37 @@ def test_full_size_decode_properties(ekv_lib):
     assert int(srt[..., :-n].max()) == -1
 
 
+@pytest.mark.parametrize("cluster", [-1, 0, 2, 8], ids=lambda c: f"cluster{c}")
+@pytest.mark.parametrize("n0", [333, 1500])
+def test_decode_select_when_low_mean_slots_are_infeasible(engines, dispatch, n0, cluster):
+    """roco with the std ranking anti-correlated to the mean ranking: the slots with the lowest mean all lie
+    outside the k_feasible lowest std, so walking candidates by mean fails and the kernels must fall back to
+    the real two-stage select (single CTA: shared-memory radix select; cluster: cluster-wide radix select)."""
+    dispatch(0, cluster)
+    dtype, H, Hkv, d = torch.float16, 4, 2, 128
+    g = torch.Generator().manual_seed(n0)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
+    eng = engines.CudaEngine(1, H, Hkv, d, dtype, capacity=n0 + 8)
+    orc = replay.OracleEngine(1, H, Hkv, d, dtype)
+    K, V = rnd(Hkv, n0, d), rnd(Hkv, n0, d)
+    C0 = torch.full((n0,), 50.0)
+    for e in (eng, orc):
+        e.load_prefill(0, K, V, n0, C0)
+    mean = torch.rand(Hkv, n0, generator=g) * 1e-2 + 1e-3
+    std = 1e-2 / (mean * 1e2)                       # low mean <-> high std
+    S = mean * 50.0
+    SQ = (std ** 2 + mean ** 2) * 50.0
+    orc.layers[0].S, orc.layers[0].SQ = S.clone(), SQ.clone()
+    eng.cache.S[0][0, :, :n0] = S.cuda(); eng.cache.SQ[0][0, :, :n0] = SQ.cuda()
+    st = restate.Step(policy="roco", accumulate=True, evict=1, counter_add=1.0, k_feasible=n0 // 3)
+    for t in range(6):
+        q, k, v = rnd(H, 1, d) * 0.3, rnd(Hkv, 1, d), rnd(Hkv, 1, d)
+        o_ref, v_ref = orc.forward(0, st, q, k, v)
+        o, vic = eng.forward(0, st, q, k, v, force=v_ref)
+        assert torch.equal(vic, v_ref), (t, vic, v_ref, orc.margin(0))
+        assert (o.float() - o_ref.float()).abs().max().item() <= 1e-3
+
+
 @pytest.mark.parametrize("B,H,Hkv,n,cluster", [(2, 64, 8, 8256, 0), (1, 32, 8, 8208, 0), (1, 32, 32, 1088, 0),
                                                (3, 32, 32, 1088, 8), (2, 64, 8, 4100, 4)])
 def test_long_gqa_decode_properties(ekv_lib, dispatch, B, H, Hkv, n, cluster):
