@@ -181,7 +181,7 @@ def main():
     B, L = args.seqs_per_gpu, args.layers
     n = RETAINED
     torch.manual_seed(1234 + rank)
-    cache = BudgetedKVCache(L, B, H, HKV, D, n + 1, dtype=torch.float16, device=dev)
+    cache = BudgetedKVCache(L, B, H, HKV, D, n + 1, dtype=torch.float16, device=dev, arith=1)   # ATen's CUDA flavour
     cinit = [float(n - i) for i in range(n)]
     for l in range(L):
         cache.load_prefill(l, torch.randn(B, HKV, n, D, device=dev, dtype=torch.float16),

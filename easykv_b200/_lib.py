@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeasykv_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 F16, BF16, F32 = 0, 1, 2
 POLICY_NONE, POLICY_ROCO, POLICY_H2O, POLICY_TOVA, POLICY_RANGE = 0, 1, 2, 3, 4
@@ -25,7 +25,8 @@ class Step(C.Structure):
                 ("score_offset", C.c_int32), ("counter_add", C.c_float), ("c_new0", C.c_float),
                 ("c_new_step", C.c_float), ("k_feasible", C.c_int32), ("protect_last", C.c_int32),
                 ("sink_protect", C.c_int32), ("win_lo", C.c_int32), ("win_recent", C.c_int32),
-                ("range_start", C.c_int32), ("arith", C.c_int32), ("tova_head_mean", C.c_int32)]
+                ("range_start", C.c_int32), ("arith", C.c_int32), ("tova_head_mean", C.c_int32),
+                ("raw_colsum", C.c_int32)]
 
 
 class LayerIO(C.Structure):

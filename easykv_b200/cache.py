@@ -101,6 +101,13 @@ class BudgetedKVCache:
         c = torch.as_tensor(values, dtype=torch.float32, device=self.device)
         self.Cn[l][:, :, :c.numel()] = c
 
+    def round_state(self, l):
+        """Round S / SQ to the model dtype once (what `torch.sum(attention_map, dim=1)` does for the whole dense
+        map in h2o_head_score, easykv.py:183-184) after a dense prefill issued with `raw_colsum` chunks."""
+        if self.dtype != torch.float32:
+            self.S[l].copy_(self.S[l].to(self.dtype).float())
+            self.SQ[l].copy_(self.SQ[l].to(self.dtype).float())
+
     def step(self, l, sp: StepParams, q, k_new, v_new, apply=True, kernel=0):
         """One forward of layer `l`: q `[B, H, q_len, d]`, k_new / v_new `[B, Hkv, q_len, d]`
         (post-RoPE).  Returns (out `[B, H, q_len, d]`, victim_lidx `[B, Hkv, evict]` int32 or None).

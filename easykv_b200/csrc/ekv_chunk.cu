@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
   u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
   u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
   auto accf = [&](int e, float& ds, float& dsq) {
-    ds = Tr<T>::round_f(colS[e]);          // p.sum(dim=1) is a model-dtype result (easykv.py:450)
-    dsq = Tr<T>::round_f(colSQ[e]);        // (p**2).sum(dim=1) likewise (:451)
+    ds = a.st.raw_colsum ? colS[e] : Tr<T>::round_f(colS[e]);       // p.sum(dim=1) is a model-dtype result (easykv.py:450)
+    dsq = a.st.raw_colsum ? colSQ[e] : Tr<T>::round_f(colSQ[e]);    // (p**2).sum(dim=1) likewise (:451)
   };
   state_select_apply(a.st, u, a.n_before, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
 }

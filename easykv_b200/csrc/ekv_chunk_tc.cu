@@ -496,8 +496,8 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
                        (size_t)unit * pl.NEpad;
   auto accf = [&](int e, float& ds, float& dsq) {
     const float2 v = csum[e];
-    ds = Tr<T>::round_f(v.x);              // p.sum(dim=1) is a model-dtype result (easykv.py:450)
-    dsq = Tr<T>::round_f(v.y);             // (p**2).sum(dim=1) likewise (:451)
+    ds = a.st.raw_colsum ? v.x : Tr<T>::round_f(v.x);       // p.sum(dim=1) is a model-dtype result (easykv.py:450)
+    dsq = a.st.raw_colsum ? v.y : Tr<T>::round_f(v.y);      // (p**2).sum(dim=1) likewise (:451)
   };
   state_select_apply(a.st, u, a.n_before, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
 }

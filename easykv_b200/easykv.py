@@ -105,8 +105,10 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
     bsz, length = input_ids.shape
     ppl_mode = kv_mode == "ppl"
     plan = P.resolve_plan(kv_mode, length, budget, stride, recent_ratio, temp_length)
-    if keep_attention and plan.mode in ("encoding", "encoding_decoding", "ppl"):
-        raise NotImplementedError("keep_attention=True needs the dense-prefill column statistics (SURVEY §8f row 1)")
+    # keep_attention=True: the reference seeds S / SQ with the column sums of the dense prefill's [r_idx, r_idx]
+    # attention map (h2o_head_score, easykv.py:173-186; 137 GB of maps for Mistral at 16K).  Here the dense
+    # prefill's chunks accumulate those sums in-kernel (raw_colsum) and nothing is materialised.
+    seed = bool(keep_attention) and plan.mode in ("encoding", "encoding_decoding", "ppl") and policy in ("roco", "h2o_head")
 
     mods = find_attention_modules(self)
     H, Hkv, d = geometry(mods[0], getattr(self, "config", None))
@@ -132,8 +134,12 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
         """Causal attention over tokens [0, upto) with no policy: the reference's unpatched / patched dense
         forward (easykv.py:232, :396, :557).  Chunked so that every forward is one fused launch per layer."""
         logits = None
+        sp = P.StepParams(policy=policy, accumulate=True, raw_colsum=True) if seed else P.StepParams()
         for t0 in range(0, upto, DENSE_CHUNK):
-            logits = forward(input_ids[:, t0:min(t0 + DENSE_CHUNK, upto)], t0, P.StepParams())
+            logits = forward(input_ids[:, t0:min(t0 + DENSE_CHUNK, upto)], t0, sp)
+        if seed:
+            for l in range(cache.L):
+                cache.round_state(l)
         return logits
 
     def sample(prob):

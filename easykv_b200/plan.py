@@ -47,6 +47,7 @@ class StepParams:
     win_recent: int = 0
     tova_head_mean: bool = False
     range_start: int = 0
+    raw_colsum: bool = False
 
     def to_c(self, apply=True, arith=0) -> "_lib.Step":
         pol = _POLICY_ENUM[self.policy]
@@ -57,7 +58,8 @@ class StepParams:
                          protect_last=int(self.protect_last), sink_protect=int(self.sink_protect),
                          win_lo=int(self.win_lo), win_recent=int(self.win_recent),
                          range_start=int(self.range_start), arith=int(arith),
-                         tova_head_mean=int(self.tova_head_mean and self.policy == "tova"))
+                         tova_head_mean=int(self.tova_head_mean and self.policy == "tova"),
+                         raw_colsum=int(self.raw_colsum))
 
     @classmethod
     def from_fields(cls, obj) -> "StepParams":

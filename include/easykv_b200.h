@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EKV_ABI_VERSION 3
+#define EKV_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define EKV_API __attribute__((visibility("default")))
@@ -87,6 +87,10 @@ typedef struct ekv_step {
                                     1 = CUDA (logits * (1/sqrt(d)); exp / sum)                    */
   int32_t tova_head_mean;/* tova in 'encoding'/'ppl': state = mean over KV heads of the last
                             query row, broadcast to all heads (:454-457,:845-848)                 */
+  int32_t raw_colsum;    /* keep_attention seeding (h2o_head_score, :173-186): the dense prefill is issued
+                            as causal chunks whose column sums must be added to S / SQ WITHOUT the
+                            per-forward model-dtype rounding of :450-451; the caller rounds S / SQ once
+                            when the prefill is complete (torch.sum over the whole map rounds once) */
 } ekv_step;
 
 /* One layer's tensors for one forward.  Replaces the body of llama_forward / mistral_forward

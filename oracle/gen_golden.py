@@ -55,6 +55,16 @@ CASES = {
     "llama_ppl_roco_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=144, dtype="float32",
                                 mode="ppl", stride=8, max_new_tokens=0,
                                 gen=dict(budget=0.4, kv_policy="roco")),
+    # keep_attention=True: state seeded from the dense prefill's attention map (h2o_head_score, easykv.py:173-186)
+    "llama_enc_roco_keep_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=200, dtype="float32",
+                                     mode="encoding", stride=8, max_new_tokens=2,
+                                     gen=dict(budget=0.5, kv_policy="roco", keep_attention=True)),
+    "gqa_mistral_enc_h2o_keep_fp32": dict(arch="mistral", L=2, H=8, Hkv=2, d=128, seq=164, dtype="float32",
+                                          mode="encoding", stride=4, max_new_tokens=2,
+                                          gen=dict(budget=0.5, kv_policy="h2o_head", keep_attention=True)),
+    "gqa_mistral_enc_h2o_keep_fp16": dict(arch="mistral", L=1, H=8, Hkv=2, d=128, seq=164, dtype="float16",
+                                          mode="encoding", stride=4, max_new_tokens=2,
+                                          gen=dict(budget=0.5, kv_policy="h2o_head", keep_attention=True)),
     # 16-bit rounding points
     "gqa_mistral_auto_roco_fp16": dict(arch="mistral", L=2, H=8, Hkv=2, d=128, seq=160, dtype="float16",
                                        mode="auto", stride=8, max_new_tokens=24,
@@ -89,6 +99,8 @@ def run_case(name, c):
     for e, ev in enumerate(tr.events):
         arrs[f"ev{e}_ids"] = ev["ids"].numpy().astype(np.int64)
         emeta.append(dict(kind=ev["kind"], fwd=ev["fwd"], n_before=ev["n_before"]))
+    if tr.seed is not None:
+        arrs["seed_S"], arrs["seed_SQ"] = tr.seed[0].numpy().astype(np.float32), tr.seed[1].numpy().astype(np.float32)
     for l, kv in enumerate(tr.final_cache):
         arrs[f"final_K_{l}"], arrs[f"final_V_{l}"] = kv[0][0].numpy().astype(npdt), kv[1][0].numpy().astype(npdt)
     meta = dict(name=name, case=c, forwards=fmeta, events=emeta, printed=tr.printed, tokens=tr.tokens,

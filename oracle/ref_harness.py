@@ -46,6 +46,7 @@ class Trace:
         self.forwards, self.events, self.final_cache, self.printed, self.result = [], [], None, "", None
         self.tokens = []
         self.prefill_cache = None
+        self.seed = None          # keep_attention: (S, SQ) returned by h2o_head_score, [L, Hkv, idx + stride]
 
 
 @contextlib.contextmanager
@@ -80,6 +81,15 @@ def _patched(model, trace: Trace, record_tensors=True):
         trace.final_cache = out
         return out
     ref_main.truncate_kv_cache = spy_range
+    save(ref_main, "h2o_head_score")
+    orig_seed = saved[(ref_main, "h2o_head_score")]
+
+    def seed_spy(attention_map, device, stride, budget, num_layers, num_heads, empty=False):
+        out = orig_seed(attention_map, device, stride, budget, num_layers, num_heads, empty=empty)
+        if not empty:
+            trace.seed = (out[0].detach().cpu().clone(), out[1].detach().cpu().clone())
+        return out
+    ref_main.h2o_head_score = seed_spy
 
     # (2) device shims ---------------------------------------------------------------
     for fname in ("llama_forward", "llama_forward_stream", "mistral_forward", "mistral_forward_stream"):

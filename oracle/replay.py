@@ -45,8 +45,10 @@ class OracleEngine:
         self.layers = [restate.LayerOracle(Hkv, d, dtype) for _ in range(L)]
         self.scale_mul = scale_mul
 
-    def load_prefill(self, l, K, V, n_scored, C_init):
+    def load_prefill(self, l, K, V, n_scored, C_init, S_init=None, SQ_init=None):
         self.layers[l].load_prefill(K, V, n_scored, C_init)
+        if S_init is not None:                       # keep_attention seeding (h2o_head_score)
+            self.layers[l].S, self.layers[l].SQ = S_init.clone().float(), SQ_init.clone().float()
 
     def forward(self, l, st, q, k, v, force=None):
         return self.layers[l].forward(st, q, k, v, self.scale_mul, force=force)
@@ -84,6 +86,10 @@ def case_plan(meta):
     return plan, gen["kv_policy"], c["max_new_tokens"]
 
 
+def case_keep_attention(meta):
+    return bool(meta["case"]["gen"].get("keep_attention", False))
+
+
 def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0) -> Report:
     """`resync`: after comparing, apply the REFERENCE's victims so every later step is again
     tested on identical state.  `shadow`: an OracleEngine factory run in lock-step (always
@@ -98,17 +104,22 @@ def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0) -> Repor
     sh = shadow(L, H, Hkv, d, dtype) if shadow is not None else None
     rep = Report(name)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
-    C0 = restate.initial_counter(plan)
+    keep = case_keep_attention(meta)
+    C0 = restate.initial_counter(plan, keep)
     for l in range(L):
         K, V = T(z[f"prefill_K_{l}"]), T(z[f"prefill_V_{l}"])
         n_scored = 0 if plan.mode == "decoding" else K.shape[1]
-        eng.load_prefill(l, K, V, n_scored, C0)
+        seeds = ()
+        if keep:                                     # the reference's own seeds for the prefilled slots
+            n0 = K.shape[1]
+            seeds = (torch.from_numpy(z["seed_S"][l][:, :n0].copy()), torch.from_numpy(z["seed_SQ"][l][:, :n0].copy()))
+        eng.load_prefill(l, K, V, n_scored, C0, *seeds)
         if sh is not None:
-            sh.load_prefill(l, K, V, n_scored, C0)
+            sh.load_prefill(l, K, V, n_scored, C0, *seeds)
     events = {}
     for e, ev in enumerate(meta["events"]):
         events[ev["fwd"]] = (ev, z[f"ev{e}_ids"])
-    sched = list(restate.schedule(plan, policy, max_new))
+    sched = list(restate.schedule(plan, policy, max_new, keep))
     fwds = meta["forwards"][1:]
     assert len(sched) == len(fwds), (len(sched), len(fwds))
     for f, ((kind, ql, st), fm) in enumerate(zip(sched, fwds), start=1):

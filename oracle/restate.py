@@ -133,6 +133,7 @@ class Step:
     win_recent: int = 0
     tova_head_mean: bool = False
     range_start: int = 0        # recency / random: evict logical [range_start, range_start + evict)
+    raw_colsum: bool = False    # keep_attention seeding: add fp32 column sums, no per-forward rounding (:173-186)
 
 
 # ----------------------------------------------------------------------------------------
@@ -141,7 +142,10 @@ class Step:
 def accumulate(st: Step, S, SQ, pf):
     """pf: folded probabilities [Hkv, ql, n] (model dtype).  S,SQ: fp32 [Hkv, n_s], n_s = n - P."""
     P = st.score_offset
-    if st.policy == "h2o_head":
+    if st.raw_colsum and st.policy in ("h2o_head", "roco"):  # h2o_head_score, :183-184, one chunk of the dense map
+        S += pf[:, :, P:].float().sum(dim=1)
+        SQ += (pf[:, :, P:] ** 2).float().sum(dim=1)
+    elif st.policy == "h2o_head":
         S += pf[:, :, P:].sum(dim=1) if pf.shape[1] > 1 else pf[:, 0, P:]
     elif st.policy == "roco":
         if pf.shape[1] > 1:                                  # strided: row sums in the model dtype

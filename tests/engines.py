@@ -12,11 +12,15 @@ class CudaEngine:
         self.cache = BudgetedKVCache(L, 1, H, Hkv, d, capacity, dtype=dtype, device="cuda", arith=arith)
         self.kernel = kernel
 
-    def load_prefill(self, l, K, V, n_scored, C_init):
+    def load_prefill(self, l, K, V, n_scored, C_init, S_init=None, SQ_init=None):
         c = None
         if C_init is not None and n_scored:
             c = C_init[-n_scored:] if n_scored < len(C_init) else C_init
         self.cache.load_prefill(l, K.cuda(), V.cuda(), n_scored, c)
+        if S_init is not None:                       # keep_attention seeding
+            n = S_init.shape[-1]
+            self.cache.S[l][0, :, :n] = S_init.cuda().float()
+            self.cache.SQ[l][0, :, :n] = SQ_init.cuda().float()
 
     def forward(self, l, st, q, k, v, force=None):
         sp = StepParams.from_fields(st)

@@ -33,8 +33,13 @@ class OracleCache:
 
     def set_counter(self, l, values):
         lo, n = self.layers[l], len(values)
-        lo.S, lo.SQ = torch.zeros(self.Hkv, n), torch.zeros(self.Hkv, n)
+        if lo.S.shape[-1] != n:                       # no state yet (the dense prefill ran without a policy)
+            lo.S, lo.SQ = torch.zeros(self.Hkv, n), torch.zeros(self.Hkv, n)
         lo.C = torch.tensor(values, dtype=torch.float32).repeat(self.Hkv, 1)
+
+    def round_state(self, l):
+        lo = self.layers[l]
+        lo.S, lo.SQ = lo.S.to(lo.dtype).float(), lo.SQ.to(lo.dtype).float()
 
     def step(self, l, sp, q, k, v, apply=True, kernel=0):
         lo = self.layers[l]
