@@ -1,0 +1,84 @@
+"""End-to-end run of the user surface on a full-size random-weight model (development aid; bench.py is the
+contract): BASELINE configs[1] — Llama-2-7B shape, fp16, 4K prompt, mode='auto', budget 1024, stride 64, roco —
+through `enable_fixed_kv` / `model.easykv_generate` bound to the INSTALLED transformers model classes.
+
+    python tools/e2e_generate.py [--layers 32] [--prompt 4096] [--new 64] [--arch llama|mistral]
+
+Prints one JSON line: prefill seconds, decode tokens/s (whole model: projections, MLP, sampling and the Python
+driver included — at batch 1 that is launch- and weight-bound, the hot path is a few percent of it), retained
+cache, number of eviction events.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import easykv_b200  # noqa: E402
+
+
+class Tok:
+    eos_token_id = -1
+
+    def decode(self, ids, skip_special_tokens=True):
+        return " ".join(str(int(i)) for i in ids)
+
+    def convert_ids_to_tokens(self, ids):
+        return [str(int(i)) for i in ids]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--arch", default="llama")
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--prompt", type=int, default=4096)
+    ap.add_argument("--new", type=int, default=64)
+    ap.add_argument("--budget", type=int, default=1024)
+    ap.add_argument("--stride", type=int, default=64)
+    ap.add_argument("--policy", default="roco")
+    args = ap.parse_args()
+    import transformers
+    if args.arch == "llama":
+        cfg = transformers.LlamaConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=args.layers,
+                                       num_attention_heads=32, num_key_value_heads=32, vocab_size=32000,
+                                       max_position_embeddings=8192, attn_implementation="eager")
+        cls = transformers.LlamaForCausalLM
+    else:
+        cfg = transformers.MistralConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=args.layers,
+                                         num_attention_heads=32, num_key_value_heads=8, vocab_size=32000,
+                                         max_position_embeddings=32768, sliding_window=None, attn_implementation="eager")
+        cls = transformers.MistralForCausalLM
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = cls(cfg).half().eval()
+    ids = torch.randint(3, 32000, (1, args.prompt), generator=torch.Generator().manual_seed(1)).cuda()
+    with contextlib.redirect_stdout(io.StringIO()):
+        easykv_b200.enable_fixed_kv(model, Tok(), mode="auto", stride=args.stride)
+    gen = dict(temperature=1e-9, top_p=1.0, budget=args.budget, kv_policy=args.policy)
+    out = {}
+    for name, new in (("prefill_only", 0), ("prefill_and_decode", args.new)):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            model.easykv_generate(input_ids=ids, generation_config=dict(gen, max_new_tokens=new))
+        torch.cuda.synchronize()
+        out[name] = time.time() - t0
+        out["printed"] = buf.getvalue().strip()
+    sess = model.easykv_last
+    dec = out["prefill_and_decode"] - out["prefill_only"]
+    print(json.dumps(dict(arch=args.arch, layers=args.layers, prompt=args.prompt, new_tokens=args.new, budget=args.budget,
+                          stride=args.stride, policy=args.policy, prefill_s=round(out["prefill_only"], 3),
+                          decode_tokens_per_s=round(args.new / dec, 2), decode_ms_per_token=round(dec / args.new * 1e3, 2),
+                          retained=sess.cache.n[0], eviction_events=len(sess.events), printed=out["printed"],
+                          launches=int(sess.cache.lib.ekv_launch_count()))))
+
+
+if __name__ == "__main__":
+    main()
