@@ -84,9 +84,9 @@ template <typename T> struct ClusterSmem {
 };
 
 // TC: the contractions run on the tensor cores (mma.sync m16n8k16, the g query heads padded to a 16-row A
-// operand).  With g >= 4 the FP32 pipes cannot keep up with HBM (g FMAs per 2 loaded bytes for Q·K^T and again
-// for P·V: measured FMA-bound at 0.17-0.45 of the roofline on the Mistral / 70B layouts), the tensor cores can.
-// The producer then lands every row with its own bulk copy at a 272-byte pitch so that ldmatrix is
+// operand).  With g = 8 the FP32 pipes cannot keep up with HBM (g mixed-precision FMAs per 2 loaded bytes for
+// Q·K^T and again for P·V), the tensor cores can.
+// The producer warp then lands the rows with 16-byte cp.async copies at a 272-byte pitch so that ldmatrix is
 // conflict-free.  Only for 16-bit dtypes.
 template <typename T, int G, bool TC>
 __global__ void __launch_bounds__(DecodeCfg<T>::NCONS + 32, (TC || G <= 4) ? 2 : 1)
@@ -112,7 +112,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], TC ? 32 : 1); mbar_init(&empty[s], NWARP); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -142,11 +142,18 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
         const int rows = min(TILE_ROWS, nloc - tt * TILE_ROWS);
         const T* src = (i < nt ? Kg : Vg) + (size_t)tt * TILE_ROWS * D;
         if (TC) {
-          // one 256-byte bulk copy per row, spread over the warp's lanes, all signalling the slot's barrier
-          if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)rows * Cfg::ROW_BYTES);
-          __syncwarp();
-          for (int r = lane; r < rows; r += 32)
-            tma_bulk_g2s(ring + (size_t)s * TILEB + (size_t)r * TC_PITCH, src + (size_t)r * D, Cfg::ROW_BYTES, &full[s], pol);
+          // rows land at a 272-byte pitch: 16-byte LDGSTS copies, two rows per warp instruction, and every lane's
+          // copies arrive on the slot's barrier when they complete (cp.async.mbarrier.arrive.noinc; the barrier
+          // expects the 32 lanes).  (One 256-byte bulk copy per row was measured at ~58 cycles per row.)
+          __syncwarp();                                           // lane 0 has seen the slot released
+          unsigned char* dst = ring + (size_t)s * TILEB;
+          const unsigned char* sb = reinterpret_cast<const unsigned char*>(src);
+#pragma unroll 8
+          for (int j = 0; j < TILE_ROWS * 16 / 32; ++j) {
+            const int idx = lane + 32 * j, r = idx >> 4, c = idx & 15;
+            if (r < rows) cp_async16(dst + r * TC_PITCH + c * 16, sb + (size_t)r * Cfg::ROW_BYTES + c * 16);
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
         } else {
           const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
           mbar_arrive_expect_tx(&full[s], bytes);
@@ -645,7 +652,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     return none;
   };
   int attempt = 0;
-  constexpr int MAX_TRY = 2;                                    // candidate walks before the radix select
+  constexpr int MAX_TRY = 1;                                    // candidate walks before the radix select (2 cluster barriers each)
   if (single) {
     const Tuple128 b = local_best(need_flag);
     if (tid < C) {
@@ -932,7 +939,7 @@ static int plan_cluster(const KernelArgs& a, int sms, int force_c, int& C, int& 
 }
 
 int decode_cluster_size();   // ekv_api.cu (env EKV_DECODE_CLUSTER): 0 = automatic, else forced cluster size
-int decode_variant();        // ekv_api.cu: 4 = use the (experimental) tensor-core variant
+int decode_variant();        // ekv_api.cu: 3 = never / 4 = always use the tensor-core variant (g >= 4, 16-bit)
 
 template <typename T, int G, bool TC>
 static int launch_cluster_plan_v(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
@@ -952,8 +959,11 @@ static int launch_cluster_plan_v(const KernelArgs& a, bool only_if_better, cudaS
 }
 
 template <typename T, int G> static int launch_cluster_plan(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
+  // tensor-core variant: by default for g = 8 (measured 1.15-1.85x over the FMA variant, which is FP32-bound there);
+  // for g = 4 the FMA variant keeps up with HBM and is kept (decode_variant 4 forces the tensor cores, 3 forbids them)
   if constexpr (sizeof(T) == 2 && G >= 4) {
-    if (decode_variant() == 4) return launch_cluster_plan_v<T, G, true>(a, only_if_better, stream);
+    const int v = decode_variant();
+    if (v == 4 || (v != 3 && G >= 8)) return launch_cluster_plan_v<T, G, true>(a, only_if_better, stream);
   }
   return launch_cluster_plan_v<T, G, false>(a, only_if_better, stream);
 }

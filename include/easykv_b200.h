@@ -173,7 +173,8 @@ EKV_API void ekv_debug_set_timeline(void* device_buffer);
 
 /* Kernel-selection override (development / test hook, not part of the data path).
  * decode_variant: 0 = automatic, 1 = one consumer group per CTA, 2 = ping-pong groups (ekv_decode.cu),
- *                 4 = the experimental tensor-core variant of the cluster kernel (g >= 4, 16-bit).
+ *                 3 = never / 4 = always use the tensor-core variant of the cluster kernel (g >= 4, 16-bit;
+ *                 automatic: g = 8 only).
  * cluster_size:   0 = automatic, -1 = never use the cluster-split decode kernel, 1/2/4/8 = always use it with
  *                 this many CTAs per (sequence, kv head) (ekv_decode_cluster.cu). */
 EKV_API void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size);
