@@ -12,7 +12,8 @@ Differences from the reference, by design:
     reference derives from it (easykv.py:271-300) are accumulated inside `ekv_attend_evict`;
   * the cache is the session's `BudgetedKVCache`; `past_key_value` is ignored and returned untouched.
 
-Projections, RoPE and o_proj stay in PyTorch.
+Projections and o_proj stay in PyTorch; RoPE of q / new k and the head-major re-layout
+are one `ekv_rope_qk` launch.
 """
 from __future__ import annotations
 
@@ -58,18 +59,21 @@ def budgeted_attention_forward(self, hidden_states, attention_mask=None, positio
     l = self._ekv_layer
     H, Hkv, d = self._ekv_geometry
     b, ql, _ = hidden_states.shape
-    q = self.q_proj(hidden_states).view(b, ql, H, d).transpose(1, 2)
-    k = self.k_proj(hidden_states).view(b, ql, Hkv, d).transpose(1, 2)
-    v = self.v_proj(hidden_states).view(b, ql, Hkv, d).transpose(1, 2)
-    if position_embeddings is not None:                       # transformers >= 4.48: the model computed them
+    q_in, k_in, v_in = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+    if position_embeddings is not None:                       # transformers >= 4.48: the model computed them, per token
         cos, sin = position_embeddings
+        pos = None
+        if cos.shape[0] != b:
+            cos, sin = cos.expand(b, -1, -1), sin.expand(b, -1, -1)
     else:
         # the table is sized by the largest *position id*, not by the cache length, so positions stay
         # valid after evictions (llama_patch.py:187-189); the session knows it without a device sync
-        cos, sin = self.rotary_emb(v, seq_len=sess.max_position + 1)
+        cos, sin = self.rotary_emb(v_in, seq_len=sess.max_position + 1)
         pos = position_ids if position_ids is not None else sess.position_ids(hidden_states.device)
-        cos, sin = cos[pos], sin[pos]
-    q, k = apply_rope(q, k, cos.to(q.dtype), sin.to(q.dtype))
+        if pos.shape[0] != b:
+            pos = pos.expand(b, -1)
+    # RoPE at the explicit positions + head-major layout in one launch (ekv_rope_qk)
+    q, k, v = sess.cache.rope_qkv(q_in, k_in, v_in, cos, sin, pos)
     out, victims = sess.cache.step(l, sess.step, q, k, v)
     sess.record(l, victims)
     attn_output = self.o_proj(out.transpose(1, 2).reshape(b, ql, H * d))

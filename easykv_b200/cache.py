@@ -101,6 +101,25 @@ class BudgetedKVCache:
         c = torch.as_tensor(values, dtype=torch.float32, device=self.device)
         self.Cn[l][:, :, :c.numel()] = c
 
+    def rope_qkv(self, q_in, k_in, v_in, cos, sin, positions=None):
+        """RoPE of q and k at explicit positions fused with the re-layout of the projections' outputs
+        (`ekv_rope_qk`): q_in `[B, q_len, H*d]`, k_in / v_in `[B, q_len, Hkv*d]` -> q `[B, H, q_len, d]`, k / v
+        `[B, Hkv, q_len, d]`.  cos / sin: `[rows, d]` tables indexed by `positions` (int `[B, q_len]`), or already
+        gathered per token `[B, q_len, d]` when positions is None.  Replaces apply_rotary_pos_emb
+        (easykv/llama_patch.py:47-72) and the transposes around it."""
+        B, ql = q_in.shape[0], q_in.shape[1]
+        q_in, k_in, v_in = q_in.contiguous(), k_in.contiguous(), v_in.contiguous()
+        cos, sin = cos.to(self.dtype).contiguous(), sin.to(self.dtype).contiguous()
+        q = torch.empty(B, self.H, ql, self.d, dtype=self.dtype, device=self.device)
+        k = torch.empty(B, self.Hkv, ql, self.d, dtype=self.dtype, device=self.device)
+        v = torch.empty_like(k)
+        pos = None if positions is None else positions.to(device=self.device, dtype=torch.int32).contiguous()
+        shape = _lib.Shape(dtype=_DTYPES[self.dtype], B=B, H=self.H, Hkv=self.Hkv, d=self.d, q_len=ql, cap=self.cap,
+                           n_before=0, n_phys=0)
+        _lib.check(self.lib.ekv_rope_qk(C.byref(shape), _ptr(q_in), _ptr(k_in), _ptr(v_in), _ptr(cos), _ptr(sin), _ptr(pos),
+                                        _ptr(q), _ptr(k), _ptr(v), self._stream()))
+        return q, k, v
+
     def round_state(self, l):
         """Round S / SQ to the model dtype once (what `torch.sum(attention_map, dim=1)` does for the whole dense
         map in h2o_head_score, easykv.py:183-184) after a dense prefill issued with `raw_colsum` chunks."""

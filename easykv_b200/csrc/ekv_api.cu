@@ -182,6 +182,18 @@ int ekv_evict_explicit(const ekv_shape* sh, const ekv_layer_io* io, const int32_
   return launch_evict_explicit(a, victims, evict, (cudaStream_t)stream);
 }
 
+int ekv_rope_qk(const ekv_shape* sh, const void* q_in, const void* k_in, const void* v_in, const void* cos_t,
+                const void* sin_t, const int32_t* positions, void* q_out, void* k_out, void* v_out, void* stream) {
+  if (!sh) return set_error(EKV_ERR_INVALID, "null shape");
+  if (sh->B <= 0 || sh->H <= 0 || sh->Hkv <= 0 || sh->q_len <= 0 || sh->d <= 0 || (sh->d & 1))
+    return set_error(EKV_ERR_INVALID, "bad dimension (B=%d H=%d Hkv=%d q_len=%d d=%d)", sh->B, sh->H, sh->Hkv, sh->q_len, sh->d);
+  if (((q_in && q_out) || (k_in && k_out)) && (!cos_t || !sin_t)) return set_error(EKV_ERR_INVALID, "null cos / sin table");
+  if ((q_in != nullptr) != (q_out != nullptr) || (k_in != nullptr) != (k_out != nullptr) || (v_in != nullptr) != (v_out != nullptr))
+    return set_error(EKV_ERR_INVALID, "each of q, k, v needs both its input and its output (or neither)");
+  return launch_rope_qk(sh->dtype, q_in, k_in, v_in, cos_t, sin_t, positions, q_out, k_out, v_out, sh->B, sh->H, sh->Hkv,
+                        sh->q_len, sh->d, (cudaStream_t)stream);
+}
+
 int ekv_export_logical(const ekv_shape* sh, const ekv_layer_io* io, void* K_out, void* V_out, float* S_out,
                        float* SQ_out, float* C_out, void* stream) {
   KernelArgs a;

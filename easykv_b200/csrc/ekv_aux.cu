@@ -177,3 +177,75 @@ int launch_export(const KernelArgs& a, void* K_out, void* V_out, float* S_out, f
 }
 
 }  // namespace ekv
+
+// ---- RoPE of q and the new k at explicit positions + head-major re-layout ----------------------------
+// Replaces apply_rotary_pos_emb (easykv/llama_patch.py:47-72, mistral_patch.py:62-87) and the transpose /
+// contiguous copies around it (llama_patch.py:169-171): the projections' [B, q_len, heads, d] outputs are rotated
+// and written as the [B, heads, q_len, d] tensors ekv_attend_evict takes; v is only re-laid out.  Arithmetic as the
+// reference evaluates it in the model dtype: x*cos and rotate_half(x)*sin are each rounded, then their sum.
+namespace ekv {
+
+template <typename T>
+__global__ void rope_qk_kernel(const T* __restrict__ q_in, const T* __restrict__ k_in, const T* __restrict__ v_in,
+                               const T* __restrict__ cos_t, const T* __restrict__ sin_t, const int32_t* __restrict__ positions,
+                               T* __restrict__ q_out, T* __restrict__ k_out, T* __restrict__ v_out,
+                               int B, int H, int Hkv, int QL, int d) {
+  const int heads = H + 2 * Hkv;                       // q heads, then k heads, then v heads
+  const int half = d >> 1;
+  const long long total = (long long)B * QL * heads * half;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % half);
+    const int hh = (int)((idx / half) % heads);
+    const int i = (int)((idx / ((long long)half * heads)) % QL);
+    const int b = (int)(idx / ((long long)half * heads * QL));
+    const int row = positions ? positions[b * QL + i] : b * QL + i;
+    const T* src; T* dst; int nh, h; bool rot = true;
+    if (hh < H) { src = q_in; dst = q_out; nh = H; h = hh; }
+    else if (hh < H + Hkv) { src = k_in; dst = k_out; nh = Hkv; h = hh - H; }
+    else { src = v_in; dst = v_out; nh = Hkv; h = hh - H - Hkv; rot = false; }
+    if (!src || !dst) continue;
+    const T* x = src + (((size_t)b * QL + i) * nh + h) * d;
+    T* y = dst + (((size_t)b * nh + h) * QL + i) * d;
+    const float x1 = Tr<T>::to_f(x[j]), x2 = Tr<T>::to_f(x[j + half]);
+    if (!rot) { y[j] = x[j]; y[j + half] = x[j + half]; continue; }
+    const float c1 = Tr<T>::to_f(cos_t[(size_t)row * d + j]), c2 = Tr<T>::to_f(cos_t[(size_t)row * d + j + half]);
+    const float s1 = Tr<T>::to_f(sin_t[(size_t)row * d + j]), s2 = Tr<T>::to_f(sin_t[(size_t)row * d + j + half]);
+    // rotate_half(x) = cat(-x2, x1)   (llama_patch.py:13-17)
+    const float a1 = Tr<T>::round_f(__fmul_rn(x1, c1)), b1 = Tr<T>::round_f(__fmul_rn(-x2, s1));
+    const float a2 = Tr<T>::round_f(__fmul_rn(x2, c2)), b2 = Tr<T>::round_f(__fmul_rn(x1, s2));
+    y[j] = Tr<T>::from_f(__fadd_rn(a1, b1));
+    y[j + half] = Tr<T>::from_f(__fadd_rn(a2, b2));
+  }
+}
+
+int launch_rope_qk(int dtype, const void* q_in, const void* k_in, const void* v_in, const void* cos_t, const void* sin_t,
+                   const int32_t* positions, void* q_out, void* k_out, void* v_out, int B, int H, int Hkv, int QL, int d,
+                   cudaStream_t stream) {
+  const long long total = (long long)B * QL * (H + 2 * Hkv) * (d / 2);
+  if (total <= 0) return EKV_OK;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  switch (dtype) {
+    case EKV_F16:
+      rope_qk_kernel<__half><<<(int)blocks, threads, 0, stream>>>((const __half*)q_in, (const __half*)k_in, (const __half*)v_in,
+          (const __half*)cos_t, (const __half*)sin_t, positions, (__half*)q_out, (__half*)k_out, (__half*)v_out, B, H, Hkv, QL, d);
+      break;
+    case EKV_BF16:
+      rope_qk_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, stream>>>((const __nv_bfloat16*)q_in, (const __nv_bfloat16*)k_in,
+          (const __nv_bfloat16*)v_in, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, positions, (__nv_bfloat16*)q_out,
+          (__nv_bfloat16*)k_out, (__nv_bfloat16*)v_out, B, H, Hkv, QL, d);
+      break;
+    case EKV_F32:
+      rope_qk_kernel<float><<<(int)blocks, threads, 0, stream>>>((const float*)q_in, (const float*)k_in, (const float*)v_in,
+          (const float*)cos_t, (const float*)sin_t, positions, (float*)q_out, (float*)k_out, (float*)v_out, B, H, Hkv, QL, d);
+      break;
+    default: return set_error(EKV_ERR_INVALID, "dtype %d", dtype);
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("rope_qk_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+}  // namespace ekv

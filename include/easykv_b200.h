@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EKV_ABI_VERSION 4
+#define EKV_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define EKV_API __attribute__((visibility("default")))
@@ -160,6 +160,17 @@ EKV_API int ekv_evict_explicit(const ekv_shape* shape, const ekv_layer_io* io, c
  * (easykv.py:251,302), for re-densifying the physical layout, and for parity checks. */
 EKV_API int ekv_export_logical(const ekv_shape* shape, const ekv_layer_io* io, void* K_out, void* V_out,
                        float* S_out, float* SQ_out, float* C_out, void* stream);
+
+/* RoPE of q and of the new k at explicit positions, fused with the re-layout of the projections' outputs
+ * q_in [B, q_len, H, d], k_in / v_in [B, q_len, Hkv, d] into the head-major q_out [B, H, q_len, d], k_out / v_out
+ * [B, Hkv, q_len, d] that ekv_attend_evict takes (v is only re-laid out; any of the three may be NULL).
+ * cos / sin are [rows, d] tables in the model dtype; row of (b, i) = positions[b * q_len + i], or b * q_len + i
+ * when positions is NULL (tables already gathered per token).  Arithmetic as the reference evaluates it in
+ * the model dtype: rn(x*cos) + rn(rotate_half(x)*sin), rounded.  shape->n_before / n_phys / cap are ignored.
+ * Replaces apply_rotary_pos_emb (easykv/llama_patch.py:47-72, mistral_patch.py:62-87) and the transposes at
+ * llama_patch.py:169-171. */
+EKV_API int ekv_rope_qk(const ekv_shape* shape, const void* q_in, const void* k_in, const void* v_in, const void* cos,
+                const void* sin, const int32_t* positions, void* q_out, void* k_out, void* v_out, void* stream);
 
 /* Number of kernels launched by this library in the calling process since load (bench.py's
  * gpu_launches claim). */

@@ -37,6 +37,19 @@ class OracleCache:
             lo.S, lo.SQ = torch.zeros(self.Hkv, n), torch.zeros(self.Hkv, n)
         lo.C = torch.tensor(values, dtype=torch.float32).repeat(self.Hkv, 1)
 
+    def rope_qkv(self, q_in, k_in, v_in, cos, sin, positions=None):
+        """The torch ops of easykv/llama_patch.py:47-72, 169-171 (what ekv_rope_qk fuses)."""
+        from easykv_b200.attention import apply_rope
+        b, ql = q_in.shape[:2]
+        d = self.layers[0].d
+        q = q_in.view(b, ql, -1, d).transpose(1, 2)
+        k = k_in.view(b, ql, -1, d).transpose(1, 2)
+        v = v_in.view(b, ql, -1, d).transpose(1, 2)
+        if positions is not None:
+            cos, sin = cos[positions], sin[positions]
+        q, k = apply_rope(q, k, cos.to(q.dtype), sin.to(q.dtype))
+        return q, k, v
+
     def round_state(self, l):
         lo = self.layers[l]
         lo.S, lo.SQ = lo.S.to(lo.dtype).float(), lo.SQ.to(lo.dtype).float()

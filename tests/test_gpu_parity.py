@@ -353,6 +353,36 @@ def test_long_gqa_decode_properties(ekv_lib, dispatch, B, H, Hkv, n, cluster):
     assert torch.equal(srt[..., -n:], torch.arange(n, device=dev, dtype=torch.int32).expand(B, Hkv, n))
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("gathered", [False, True], ids=["table+positions", "per-token"])
+def test_rope_kernel_bit_exact(ekv_lib, dtype, gathered):
+    """ekv_rope_qk == the reference's apply_rotary_pos_emb evaluated by torch in the model dtype
+    (easykv/llama_patch.py:47-72), bit for bit, plus the head-major re-layout."""
+    from easykv_b200.attention import apply_rope
+    from easykv_b200.cache import BudgetedKVCache
+    B, H, Hkv, d, ql = 2, 8, 2, 128, 19
+    dev = "cuda"
+    torch.manual_seed(9)
+    cache = BudgetedKVCache(1, B, H, Hkv, d, 32, dtype=dtype)
+    q_in = torch.randn(B, ql, H * d, device=dev).to(dtype)
+    k_in = torch.randn(B, ql, Hkv * d, device=dev).to(dtype)
+    v_in = torch.randn(B, ql, Hkv * d, device=dev).to(dtype)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, d, 2, device=dev).float() / d))
+    t = torch.arange(5000, device=dev).float()
+    emb = torch.cat([torch.outer(t, inv)] * 2, dim=-1)
+    cos_t, sin_t = emb.cos().to(dtype), emb.sin().to(dtype)
+    pos = torch.stack([torch.arange(4000, 4000 + ql), torch.arange(77, 77 + ql)]).to(dev)
+    if gathered:
+        q, k, v = cache.rope_qkv(q_in, k_in, v_in, cos_t[pos], sin_t[pos], None)
+    else:
+        q, k, v = cache.rope_qkv(q_in, k_in, v_in, cos_t, sin_t, pos)
+    qr = q_in.view(B, ql, H, d).transpose(1, 2)
+    kr = k_in.view(B, ql, Hkv, d).transpose(1, 2)
+    q_ref, k_ref = apply_rope(qr, kr, cos_t[pos], sin_t[pos])
+    assert torch.equal(q, q_ref.contiguous()) and torch.equal(k, k_ref.contiguous())
+    assert torch.equal(v, v_in.view(B, ql, Hkv, d).transpose(1, 2).contiguous())
+
+
 def test_errors_are_python_exceptions(ekv_lib):
     from easykv_b200.cache import BudgetedKVCache
     from easykv_b200.plan import StepParams
