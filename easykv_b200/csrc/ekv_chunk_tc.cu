@@ -486,6 +486,10 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
   SelScratch sc;
   sc.lj = lj;
   sc.carve(smem + L.off_pool, NE, a.st.evict);
+  if (a.timeline) {                                               // profiling hook: [unit][8] clock64 stamps
+    sc.dbg = a.timeline + (size_t)unit * 8;
+    if (tid == 0) sc.dbg[6] = clock64();                          // kernel start .. (stamps 0-5 are state_select_apply's)
+  }
   UnitState u;
   u.S = a.S + (size_t)unit * a.cap; u.SQ = a.SQ + (size_t)unit * a.cap; u.C = a.C + (size_t)unit * a.cap;
   u.lidx = a.lidx + (size_t)unit * a.cap;
