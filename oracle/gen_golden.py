@@ -69,6 +69,18 @@ CASES = {
     "gqa_mistral_auto_roco_fp16": dict(arch="mistral", L=2, H=8, Hkv=2, d=128, seq=160, dtype="float16",
                                        mode="auto", stride=8, max_new_tokens=24,
                                        gen=dict(budget=64, kv_policy="roco")),
+    "llama_decoding_roco_fp16": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=32, dtype="float16",
+                                     mode="decoding", stride=1, max_new_tokens=64,
+                                     gen=dict(budget=36, kv_policy="roco")),
+    "gqa_llama_auto_tova_fp16": dict(arch="llama", L=1, H=8, Hkv=2, d=128, seq=96, dtype="float16",
+                                     mode="auto", stride=8, max_new_tokens=16,
+                                     gen=dict(budget=40, kv_policy="tova")),
+    "gqa8_mistral_enc_h2o_fp16": dict(arch="mistral", L=1, H=8, Hkv=1, d=128, seq=144, dtype="float16",
+                                      mode="encoding", stride=16, max_new_tokens=2,
+                                      gen=dict(budget=0.5, kv_policy="h2o_head")),
+    "llama_ppl_roco_bf16": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=136, dtype="bfloat16",
+                                mode="ppl", stride=8, max_new_tokens=0,
+                                gen=dict(budget=0.4, kv_policy="roco")),
     "llama_enc_roco_fp16": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=128, dtype="float16",
                                 mode="encoding", stride=8, max_new_tokens=2,
                                 gen=dict(budget=0.5, kv_policy="roco")),
@@ -83,9 +95,9 @@ def run_case(name, c):
     ppl = c["mode"] == "ppl"
     tr = ref_harness.run_reference(model, ids, gen, mode="encoding" if ppl else c["mode"], stride=c["stride"], ppl=ppl)
     arrs = {}
-    npdt = np.float32 if dtype == torch.float32 else np.float16
+    npdt = np.float32 if dtype in (torch.float32, torch.bfloat16) else np.float16      # bf16 values are exact in fp32
     for l, (k, v) in enumerate(tr.prefill_cache):
-        arrs[f"prefill_K_{l}"], arrs[f"prefill_V_{l}"] = k.numpy().astype(npdt), v.numpy().astype(npdt)
+        arrs[f"prefill_K_{l}"], arrs[f"prefill_V_{l}"] = k.float().numpy().astype(npdt), v.float().numpy().astype(npdt)
     fmeta = []
     for f, fw in enumerate(tr.forwards):
         fmeta.append(dict(q_len=fw["q_len"], recorded=len(fw["layers"]) > 0 and f > 0,
@@ -94,7 +106,7 @@ def run_case(name, c):
             continue
         for l, rec in enumerate(fw["layers"]):
             for key in "qkvo":
-                arrs[f"f{f}_l{l}_{key}"] = rec[key].numpy().astype(npdt)
+                arrs[f"f{f}_l{l}_{key}"] = rec[key].float().numpy().astype(npdt)
     emeta = []
     for e, ev in enumerate(tr.events):
         arrs[f"ev{e}_ids"] = ev["ids"].numpy().astype(np.int64)
@@ -102,7 +114,7 @@ def run_case(name, c):
     if tr.seed is not None:
         arrs["seed_S"], arrs["seed_SQ"] = tr.seed[0].numpy().astype(np.float32), tr.seed[1].numpy().astype(np.float32)
     for l, kv in enumerate(tr.final_cache):
-        arrs[f"final_K_{l}"], arrs[f"final_V_{l}"] = kv[0][0].numpy().astype(npdt), kv[1][0].numpy().astype(npdt)
+        arrs[f"final_K_{l}"], arrs[f"final_V_{l}"] = kv[0][0].float().numpy().astype(npdt), kv[1][0].float().numpy().astype(npdt)
     meta = dict(name=name, case=c, forwards=fmeta, events=emeta, printed=tr.printed, tokens=tr.tokens,
                 result=tr.result if isinstance(tr.result, float) else str(tr.result),
                 torch=torch.__version__, reference_commit="a1d71cae3b562d9a709dda3741bd63e46a09ad31")

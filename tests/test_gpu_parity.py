@@ -32,7 +32,9 @@ def test_golden_replay(engines, name, kernel):
     assert not rep.victim_mismatch, rep.victim_mismatch[:2]
     for f, l, ref, got, margin in rep.tie_ambiguous:      # exact ties: torch.topk's pick is unspecified
         assert min(margin) == 0.0 and "fp32" not in name
-    assert len(rep.tie_ambiguous) <= 1
+    # bf16 probabilities of diffuse attention take so few distinct values that exact ties are the norm
+    # (SURVEY §7.3 item 2): there the victims are only pinned where the reference's own decision margin is > 0
+    assert len(rep.tie_ambiguous) <= 1 or "bf16" in name
     assert rep.final_cache_equal
     tol = 2e-6 if "fp32" in name else 1e-3
     assert rep.max_out_err <= tol, rep.max_out_err
@@ -48,7 +50,7 @@ def test_golden_replay_cluster_kernel(engines, dispatch, name, cluster):
     assert rep.n_events > 0 and not rep.victim_mismatch, rep.victim_mismatch[:2]
     for f, l, ref, got, margin in rep.tie_ambiguous:
         assert min(margin) == 0.0 and "fp32" not in name
-    assert len(rep.tie_ambiguous) <= 1 and rep.final_cache_equal
+    assert (len(rep.tie_ambiguous) <= 1 or "bf16" in name) and rep.final_cache_equal
     assert rep.max_out_err <= (2e-6 if "fp32" in name else 1e-3)
 
 

@@ -9,7 +9,7 @@ CASES = replay.list_golden()
 
 
 def test_golden_present():
-    assert "c1_llama_enc_roco_fp32" in CASES and len(CASES) >= 10
+    assert "c1_llama_enc_roco_fp32" in CASES and len(CASES) >= 18
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -22,8 +22,10 @@ def test_restatement_reproduces_reference(name):
     assert not rep.victim_mismatch, rep.victim_mismatch[:2]
     for f, l, ref, got, margin in rep.tie_ambiguous:
         assert min(margin) == 0.0 and "fp32" not in name
-        assert (ref != got).sum() <= 2 * ref.shape[0]        # one swapped pair per head at most
-    assert len(rep.tie_ambiguous) <= 1
+        assert (ref != got).sum() <= 2 * ref.shape[0] or "bf16" in name     # one swapped pair per head at most
+    # bf16 probabilities of diffuse attention take so few distinct values that exact ties are the norm
+    # (SURVEY §7.3 item 2): there the victims are only pinned where the reference's own decision margin is > 0
+    assert len(rep.tie_ambiguous) <= 1 or "bf16" in name
     assert rep.final_cache_equal
     assert rep.max_out_err == 0.0        # same torch CPU ops as the reference => bit-identical outputs
 
