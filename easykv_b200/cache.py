@@ -253,6 +253,14 @@ class SteadyDecode:
             if rc:
                 _lib.check(rc)
 
+    def run_layer(self, l, stream=None):
+        """One layer's launch (for callers that pipeline per-layer host<->device copies around the step)."""
+        shape, io = self.calls[l]
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        rc = self.cache.lib.ekv_attend_evict(C.byref(shape), C.byref(io), C.byref(self.cstep), 0, s)
+        if rc:
+            _lib.check(rc)
+
     def capture(self):
         """Capture one whole step (L launches) into a CUDA graph; `replay()` then costs one launch."""
         self.run()                                   # warm: function attributes are set outside capture
