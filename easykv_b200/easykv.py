@@ -19,6 +19,7 @@ Sampling (`logits_adapter`, torch.multinomial; :115-134, :258) stays in PyTorch.
 """
 from __future__ import annotations
 
+import dataclasses
 import functools
 import math
 import statistics
@@ -97,9 +98,6 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
     if cfg.get("streaming", False):
         raise NotImplementedError("streaming=True (llama_forward_stream) is not part of this path yet (SURVEY §8f row 3)")
     policy = P.canonical_policy(policy)
-    if policy == "random":
-        raise NotImplementedError("kv_policy='random' draws from torch's generator inside the reference's loop and is "
-                                  "not reproduced here")
     if input_ids.dim() == 1:
         input_ids = input_ids[None]
     bsz, length = input_ids.shape
@@ -124,6 +122,11 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
     self.easykv_last = sess                                   # eviction trace / cache of the last call
 
     def forward(ids, pos0, step):
+        if step.policy == "random" and step.evict:
+            # the victim range is the host's draw, exactly where the reference draws it (plan.random_range_start)
+            n_after = cache.n[0] + ids.shape[1]
+            n_state = n_after - step.score_offset if plan.mode == "decoding" else plan.idx + plan.stride
+            step = dataclasses.replace(step, range_start=P.random_range_start(plan, n_state))
         sess.begin(step, pos0, ids.shape[1])
         pos = torch.arange(pos0, pos0 + ids.shape[1], device=device)[None].expand(bsz, -1)
         out = self(input_ids=ids, position_ids=pos, use_cache=False)
@@ -180,6 +183,9 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
         prob, _ = logits_adapter(logits[:, -1, :].float(), temperature, top_p)
         output_ids, times = [], []
         cur_pos = length
+        if plan.mode == "encoding_decoding" and policy == "random" and decodes:
+            # the reference itself fails here (UnboundLocalError: positions_tensor, easykv.py:744)
+            raise NotImplementedError("kv_policy='random' has no decode phase in encoding_decoding / auto mode")
         for _, _, st in decodes:                               # easykv.py:257-363 / :508-526 / :670-748
             nxt = sample(prob)
             output_ids.append(nxt[:, 0].tolist())

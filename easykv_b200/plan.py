@@ -191,3 +191,15 @@ def schedule(plan: Plan, policy: str, max_new_tokens: int, keep_attention=False)
         yield "decode", 1, StepParams(policy=policy, accumulate=scored, evict=int(evicts), counter_add=1.0,
                                       k_feasible=B - recent, win_recent=recent if policy == "h2o_head" else 0,
                                       range_start=sink)
+
+
+def random_range_start(plan: Plan, n_state: int) -> int:
+    """kv_policy='random': the reference draws `torch.rand(...)` from torch's *CPU* default generator inside its loop
+    and evicts at the argmax (easykv.py:353-357 decoding: over the generated slots in the cache; :494-499 / :886-891
+    strided: over the state length with the last `stride` entries excluded).  Drawing the same shape at the same point
+    reproduces its choice exactly under the same `torch.manual_seed`.  Returns range_start (relative to score_offset)."""
+    import torch
+    scores = torch.rand(n_state)
+    if plan.mode != "decoding":
+        scores[-plan.stride:] = -1e9
+    return int(torch.topk(scores, k=1, dim=-1)[1][0])

@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_harness, scaffold  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
+RNG_SEED = 20240229
 
 CASES = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable case
@@ -55,6 +56,13 @@ CASES = {
     "llama_ppl_roco_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=144, dtype="float32",
                                 mode="ppl", stride=8, max_new_tokens=0,
                                 gen=dict(budget=0.4, kv_policy="roco")),
+    # kv_policy='random': victims drawn from torch's CPU generator (seeded below), easykv.py:353-357, :494-499
+    "llama_decoding_random_fp32": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=24, dtype="float32",
+                                       mode="decoding", stride=1, max_new_tokens=40,
+                                       gen=dict(budget=16, kv_policy="random")),
+    "llama_enc_random_fp32": dict(arch="llama", L=1, H=4, Hkv=2, d=128, seq=120, dtype="float32",
+                                  mode="encoding", stride=8, max_new_tokens=2,
+                                  gen=dict(budget=0.5, kv_policy="random")),
     # keep_attention=True: state seeded from the dense prefill's attention map (h2o_head_score, easykv.py:173-186)
     "llama_enc_roco_keep_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=200, dtype="float32",
                                      mode="encoding", stride=8, max_new_tokens=2,
@@ -93,6 +101,7 @@ def run_case(name, c):
     ids = torch.randint(3, 512, (1, c["seq"]), generator=torch.Generator().manual_seed(1))
     gen = dict(temperature=1e-9, top_p=1.0, max_new_tokens=c["max_new_tokens"], **c["gen"])
     ppl = c["mode"] == "ppl"
+    torch.manual_seed(RNG_SEED)                      # the global CPU generator the reference's 'random' policy draws from
     tr = ref_harness.run_reference(model, ids, gen, mode="encoding" if ppl else c["mode"], stride=c["stride"], ppl=ppl)
     arrs = {}
     npdt = np.float32 if dtype in (torch.float32, torch.bfloat16) else np.float16      # bf16 values are exact in fp32
@@ -115,7 +124,7 @@ def run_case(name, c):
         arrs["seed_S"], arrs["seed_SQ"] = tr.seed[0].numpy().astype(np.float32), tr.seed[1].numpy().astype(np.float32)
     for l, kv in enumerate(tr.final_cache):
         arrs[f"final_K_{l}"], arrs[f"final_V_{l}"] = kv[0][0].float().numpy().astype(npdt), kv[1][0].float().numpy().astype(npdt)
-    meta = dict(name=name, case=c, forwards=fmeta, events=emeta, printed=tr.printed, tokens=tr.tokens,
+    meta = dict(name=name, case=c, rng_seed=RNG_SEED, forwards=fmeta, events=emeta, printed=tr.printed, tokens=tr.tokens,
                 result=tr.result if isinstance(tr.result, float) else str(tr.result),
                 torch=torch.__version__, reference_commit="a1d71cae3b562d9a709dda3741bd63e46a09ad31")
     arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

@@ -138,6 +138,8 @@ def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0) -> Repor
                     ref_ids = torch.arange(int(ids[0]), int(ids[1])).repeat(Hkv, 1)
                 else:
                     ref_ids = ids[l].reshape(Hkv, -1)
+            if policy == "random" and ev is not None:      # the range is the host's draw: replay the reference's
+                st.range_start = int(ev[1][0]) - st.score_offset
             force = ref_ids if resync else None
             out, vic = eng.forward(l, st, q, k, v, force=force)
             o_ref = o.view(ql, H, d).transpose(0, 1).float()

@@ -81,6 +81,7 @@ def _run(meta, model, ids, aten_arith):
     c = meta["case"]
     gen = dict(temperature=1e-9, top_p=1.0, max_new_tokens=c["max_new_tokens"], aten_arith=aten_arith, **c["gen"])
     buf = io.StringIO()
+    torch.manual_seed(meta.get("rng_seed", 0))        # kv_policy='random' draws from torch's CPU generator
     with contextlib.redirect_stdout(buf):
         ppl = c["mode"] == "ppl"
         easykv_b200.enable_fixed_kv(model, scaffold.StubTokenizer(), mode="encoding" if ppl else c["mode"], stride=c["stride"])
@@ -127,6 +128,8 @@ def test_driver_reproduces_reference_runs_cpu(name, monkeypatch):
     meta, z = replay.load_golden(name)
     monkeypatch.setattr(drv, "BudgetedKVCache", OracleCache)
     monkeypatch.setattr(drv, "DENSE_CHUNK", 1 << 30)       # one dense forward, as the reference issues it
+    # the golden runs chose tokens greedily without touching the CPU generator (oracle/ref_harness.py)
+    monkeypatch.setattr(torch, "multinomial", lambda p, num_samples=1, **kw: p.argmax(dim=-1, keepdim=True))
     model, ids = _model_and_ids(meta)
     result, printed, sess = _run(meta, model, ids, "cpu")
     _compare(meta, z, result, printed, sess)
