@@ -440,7 +440,7 @@ template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a
 }
 
 // ---- 4. tail: append, accumulate, select, evict --------------------------------------------------------------------------------------
-constexpr int TAIL_NT = 512;
+constexpr int TAIL_NT = 1024;
 struct TailSmem {
   int off_ns, off_lj, off_pool, total;
   __host__ __device__ TailSmem(int NE, int q_len, int evict) {

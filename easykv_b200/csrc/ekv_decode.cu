@@ -497,14 +497,23 @@ static int launch_decode_single(const KernelArgs& a, cudaStream_t stream) {
 // Dispatch between the two decode kernels: fewer units than half the SMs -> split each unit over a
 // cluster (ekv_decode_cluster.cu) so the whole chip streams; otherwise the persistent kernel above; and
 // the cluster kernel again for units too large for one CTA's shared memory.
+static int device_sm_count() {
+  static thread_local int sm_count[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
+  if (!sm_count[dev] && cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count[dev] = 148;
+  return sm_count[dev];
+}
+
 int launch_decode(const KernelArgs& a, cudaStream_t stream) {
   if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean) return EKV_ERR_UNSUPPORTED;
   if (a.st.evict <= 1) {
     const int G = a.H / a.Hkv;
     if (decode_cluster_size() > 0) return launch_decode_cluster(a, false, stream);
-    // g = 8: the persistent kernel's 544-thread CTAs leave 96 registers per thread and spill; the cluster
-    // kernel's 288-thread CTAs do not
-    if (decode_cluster_size() == 0 && (a.B * a.Hkv * 2 <= 148 || G >= 8)) {
+    // fewer units than half the SMs: split each unit over a cluster.  g = 8: the persistent kernel's 544-thread
+    // CTAs leave 96 registers per thread and spill; the cluster kernel's 288-thread CTAs do not
+    if (decode_cluster_size() == 0 && (a.B * a.Hkv * 2 <= device_sm_count() || G >= 8)) {
       const int rc = launch_decode_cluster(a, G < 8, stream);
       if (rc != EKV_ERR_UNSUPPORTED) return rc;
     }
