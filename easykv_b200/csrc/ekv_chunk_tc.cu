@@ -78,7 +78,10 @@ long long chunk_tc_scratch_bytes(int B, int Hkv, int G, int q_len, int n_phys) {
 }
 
 // ---- passes 1 and 2 ---------------------------------------------------------------------------------------------------
-template <typename T, int G, int PASS>
+// ARITH: which ATen flavour's two non-associative spots to reproduce (ekv_step.arith) — a template parameter so
+// that the per-element code is straight-line (as a run-time switch it cost a branch per element and the
+// IEEE-division slow-path calls of the other flavour in the instruction stream).
+template <typename T, int G, int PASS, bool ARITH>
 __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a, const ChunkPlan pl) {
   using namespace tc;
   constexpr int STAGES = PASS == 2 ? 2 : tc::STAGES;
@@ -196,8 +199,8 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
     M0 = m0; M1 = m1;
     if (l0 == 0.f) l0 = 1.f;                                      // padding rows (row >= R): p = 0
     if (l1 == 0.f) l1 = 1.f;
-    L0 = a.st.arith ? l0 : __fdiv_rn(1.0f, l0);
-    L1 = a.st.arith ? l1 : __fdiv_rn(1.0f, l1);
+    L0 = ARITH ? l0 : __fdiv_rn(1.0f, l0);
+    L1 = ARITH ? l1 : __fdiv_rn(1.0f, l1);
     R0 = __frcp_rn(l0); R1 = __frcp_rn(l1);
   }
 
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
       round2<T>(s[nb][2], s[nb][3]);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        s[nb][c] = a.st.arith ? __fmul_rn(s[nb][c], a.scale_mul) : __fdiv_rn(s[nb][c], a.scale_div);
+        s[nb][c] = ARITH ? __fmul_rn(s[nb][c], a.scale_mul) : __fdiv_rn(s[nb][c], a.scale_div);
       round2<T>(s[nb][0], s[nb][1]);
       round2<T>(s[nb][2], s[nb][3]);
     }
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
           const bool hi = c >= 2;
           const float x = s[nb][c];
           const float ex = expf(x - (hi ? M1 : M0));
-          s[nb][c] = a.st.arith ? div_rn_by(ex, hi ? L1 : L0, hi ? R1 : R0) : __fmul_rn(ex, hi ? L1 : L0);
+          s[nb][c] = ARITH ? div_rn_by(ex, hi ? L1 : L0, hi ? R1 : R0) : __fmul_rn(ex, hi ? L1 : L0);
         }
         round2<T>(s[nb][0], s[nb][1]);
         round2<T>(s[nb][2], s[nb][3]);
@@ -520,18 +523,22 @@ template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, 
   if (dev >= 16) dev = 15;
   cudaError_t err;
   if (!configured[dev]) {
-    err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(chunk_tc)", err);
     configured[dev] = 1;
   }
   const int U = a.B * a.Hkv;
   const int grid = U * pl.RB * pl.splits;
-  chunk_tc_kernel<T, G, 1><<<grid, NT, smem1, stream>>>(a, pl);
+  if (a.st.arith) chunk_tc_kernel<T, G, 1, true><<<grid, NT, smem1, stream>>>(a, pl);
+  else chunk_tc_kernel<T, G, 1, false><<<grid, NT, smem1, stream>>>(a, pl);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<1> launch", err);
   count_launch();
-  chunk_tc_kernel<T, G, 2><<<grid, NT, smem2, stream>>>(a, pl);
+  if (a.st.arith) chunk_tc_kernel<T, G, 2, true><<<grid, NT, smem2, stream>>>(a, pl);
+  else chunk_tc_kernel<T, G, 2, false><<<grid, NT, smem2, stream>>>(a, pl);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<2> launch", err);
   count_launch();
   const int out_blocks = (U * pl.R * (D / 4) + 255) / 256;
