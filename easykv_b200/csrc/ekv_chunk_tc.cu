@@ -14,9 +14,10 @@
 //      from L2), p = model-dtype(exp(x - max) / sum) exactly as softmax forms it, O_partial = P V with P fed
 //      to the tensor cores straight from the accumulator registers, and the per-key column statistics
 //      (GQA fold in the model dtype, p and p^2 summed over the chunk's queries) -> scratch.
-//   3. chunk_out_kernel         sums the splits' partial outputs in split order -> out.
-//   4. chunk_tail_kernel        one CTA per unit: appends the chunk's K/V rows, folds the column statistics
-//      into the policy state and runs the budgeted select / eviction (ekv_select.cuh).
+//   3. chunk_out_kernel         sums the splits' partial outputs in split order -> out; and, one thread per
+//      (unit, slot): folds the column statistics into the policy state and prepares the selection keys.
+//   4. chunk_tail_kernel        one CTA per unit: appends the chunk's K/V rows and runs the budgeted select /
+//      eviction (ekv_select.cuh) on those keys.
 // The [H, q, n] probability tensor the reference materialises per layer (easykv/llama_patch.py:244-246)
 // never exists; nothing is synchronised with the host.
 //
@@ -42,7 +43,7 @@ constexpr int TARGET_CTAS = 296;      // two CTAs per SM: their dependency stall
 
 struct ChunkPlan {
   int R, RB, Rpad, NE, NEpad, ntiles, splits, tps;      // tps = tiles per split
-  long long off_stats, off_opart, off_cpart, off_csum, bytes;
+  long long off_stats, off_opart, off_cpart, off_klj, off_ka, off_kb, off_kf, bytes;
 };
 
 ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
@@ -68,7 +69,10 @@ ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
   o = (o + 255) / 256 * 256;
   p.off_cpart = o; o += (long long)U * (2 * p.RB) * p.NEpad * 2 * 4;      // two query halves per row block
   o = (o + 255) / 256 * 256;
-  p.off_csum = o; o += (long long)U * p.NEpad * 2 * 4;                     // column sums over all row blocks
+  p.off_klj = o; o += (long long)U * p.NEpad * 4;                          // per entry: logical index, the two selection
+  p.off_ka = o; o += (long long)U * p.NEpad * 4;                           // keys and the candidate flags (written by the
+  p.off_kb = o; o += (long long)U * p.NEpad * 4;                           // chip-wide state update, read by the tail)
+  p.off_kf = o; o += (long long)U * p.NEpad;
   p.bytes = (o + 255) / 256 * 256;
   return p;
 }
@@ -417,15 +421,45 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
 template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a, const ChunkPlan pl, const int out_blocks) {
   using namespace tc;
   if ((int)blockIdx.x >= out_blocks) {
-    // the second part of the grid: per-key column statistics summed over the row blocks (in row-block order)
-    const int idx = (blockIdx.x - out_blocks) * blockDim.x + threadIdx.x;     // (unit, key)
+    // the second part of the grid, one thread per (unit, entry): column statistics summed over the row blocks
+    // (in row-block order), folded into the policy state (accumulate, counter), selection keys for the tail
+    const int idx = (blockIdx.x - out_blocks) * blockDim.x + threadIdx.x;
     const int e = idx % pl.NEpad, unit = idx / pl.NEpad;
     if (unit >= a.B * a.Hkv || e >= pl.NE) return;
-    const float2* cg = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_cpart) +
-                       (size_t)unit * (2 * pl.RB) * pl.NEpad;
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = 0; r < 2 * pl.RB; ++r) { const float2 v = cg[(size_t)r * pl.NEpad + e]; s1 += v.x; s2 += v.y; }
-    reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_csum)[(size_t)unit * pl.NEpad + e] = make_float2(s1, s2);
+    const ekv_step& st = a.st;
+    const int n_phys = a.n_phys, P = st.score_offset, n_s = a.n_before + a.q_len - P;
+    const bool is_new = e >= n_phys;
+    int rl, phys = e;
+    float sv = 0.f, sq = 0.f, cc = 1.f;
+    if (is_new) {
+      rl = a.n_before + (e - n_phys);
+      cc = __fsub_rn(st.c_new0, __fmul_rn((float)(e - n_phys), st.c_new_step));
+      phys = a.new_slots ? a.new_slots[(size_t)unit * a.q_len + (e - n_phys)] : e;
+    } else {
+      rl = a.lidx[(size_t)unit * a.cap + e];
+      if (rl >= P) { sv = a.S[(size_t)unit * a.cap + e]; sq = a.SQ[(size_t)unit * a.cap + e]; cc = a.C[(size_t)unit * a.cap + e]; }
+    }
+    float ds = 0.f, dsq = 0.f;
+    if (st.accumulate) {
+      const float2* cg = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_cpart) +
+                         (size_t)unit * (2 * pl.RB) * pl.NEpad;
+      float s1 = 0.f, s2 = 0.f;
+      for (int r = 0; r < 2 * pl.RB; ++r) { const float2 v = cg[(size_t)r * pl.NEpad + e]; s1 += v.x; s2 += v.y; }
+      ds = st.raw_colsum ? s1 : Tr<T>::round_f(s1);         // p.sum(dim=1) is a model-dtype result (easykv.py:450)
+      dsq = st.raw_colsum ? s2 : Tr<T>::round_f(s2);        // (p**2).sum(dim=1) likewise (:451)
+    }
+    uint32_t ka = 0, kb = 0;
+    uint8_t f = 0;
+    bool dirty = false;
+    if (rl >= 0 && rl >= P) entry_update(st, rl - P, n_s, is_new, ds, dsq, sv, sq, cc, ka, kb, f, dirty);
+    if (dirty) {
+      a.S[(size_t)unit * a.cap + phys] = sv; a.SQ[(size_t)unit * a.cap + phys] = sq; a.C[(size_t)unit * a.cap + phys] = cc;
+    }
+    unsigned char* sb = reinterpret_cast<unsigned char*>(a.scratch);
+    reinterpret_cast<int32_t*>(sb + pl.off_klj)[(size_t)unit * pl.NEpad + e] = rl;
+    reinterpret_cast<uint32_t*>(sb + pl.off_ka)[(size_t)unit * pl.NEpad + e] = ka;
+    reinterpret_cast<uint32_t*>(sb + pl.off_kb)[(size_t)unit * pl.NEpad + e] = kb;
+    (sb + pl.off_kf)[(size_t)unit * pl.NEpad + e] = f;
     return;
   }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // (unit, row, dim4)
@@ -465,14 +499,7 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
   int32_t* lj = reinterpret_cast<int32_t*>(smem + L.off_lj);
   const int unit = blockIdx.x, tid = threadIdx.x;
   const Grp grp{tid, TAIL_NT, 0};
-  {
-    const int32_t* lg = a.lidx + (size_t)unit * a.cap;
-    for (int e = tid; e < n_phys; e += TAIL_NT) lj[e] = lg[e];
-    for (int i = tid; i < QL; i += TAIL_NT) {
-      ns[i] = a.new_slots ? a.new_slots[(size_t)unit * QL + i] : n_phys + i;
-      lj[n_phys + i] = a.n_before + i;
-    }
-  }
+  for (int i = tid; i < QL; i += TAIL_NT) ns[i] = a.new_slots ? a.new_slots[(size_t)unit * QL + i] : n_phys + i;
   __syncthreads();
   {                                                               // append the chunk's K/V rows (16-byte pieces)
     const uint4* kn = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_new) + (size_t)unit * QL * D);
@@ -499,14 +526,18 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
   u.new_slots = ns;
   u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
   u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
-  const float2* csum = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_csum) +
-                       (size_t)unit * pl.NEpad;
-  auto accf = [&](int e, float& ds, float& dsq) {
-    const float2 v = csum[e];
-    ds = a.st.raw_colsum ? v.x : Tr<T>::round_f(v.x);       // p.sum(dim=1) is a model-dtype result (easykv.py:450)
-    dsq = a.st.raw_colsum ? v.y : Tr<T>::round_f(v.y);      // (p**2).sum(dim=1) likewise (:451)
-  };
-  state_select_apply(a.st, u, a.n_before, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
+  const bool evicting = a.st.evict > 0 && a.st.policy != EKV_POLICY_NONE;
+  if (evicting) {                                                 // the keys the chip-wide state update left in scratch
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(a.scratch);
+    const int32_t* klj = reinterpret_cast<const int32_t*>(sb + pl.off_klj) + (size_t)unit * pl.NEpad;
+    const uint32_t* ka = reinterpret_cast<const uint32_t*>(sb + pl.off_ka) + (size_t)unit * pl.NEpad;
+    const uint32_t* kb = reinterpret_cast<const uint32_t*>(sb + pl.off_kb) + (size_t)unit * pl.NEpad;
+    const unsigned char* kf = sb + pl.off_kf + (size_t)unit * pl.NEpad;
+    for (int e = tid; e < NE; e += TAIL_NT) { sc.lj[e] = klj[e]; sc.keyA[e] = ka[e]; sc.keyB[e] = kb[e]; sc.flag[e] = kf[e]; }
+  }
+  __syncthreads();
+  auto none = [](int, float& ds, float& dsq) { ds = 0.f; dsq = 0.f; };
+  state_select_apply(a.st, u, a.n_before, n_phys, QL, /*lj_preloaded=*/true, none, sc, grp, /*keys_ready=*/true);
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------------------------------------
@@ -542,7 +573,7 @@ template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, 
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<2> launch", err);
   count_launch();
   const int out_blocks = (U * pl.R * (D / 4) + 255) / 256;
-  const int col_blocks = a.st.accumulate ? (U * pl.NEpad + 255) / 256 : 0;
+  const int col_blocks = (U * pl.NEpad + 255) / 256;               // state update: always (new slots need their state)
   chunk_out_kernel<T, G><<<out_blocks + col_blocks, 256, 0, stream>>>(a, pl, out_blocks);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_out_kernel launch", err);
   count_launch();

@@ -170,7 +170,7 @@ __device__ __forceinline__ void entry_update(const ekv_step& st, int j, int n_s,
 // contribution of entry e to S and SQ.
 template <class Acc>
 __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n_before, int n_phys, int q_len,
-                                   bool lj_preloaded, Acc acc, SelScratch& c, const Grp& g) {
+                                   bool lj_preloaded, Acc acc, SelScratch& c, const Grp& g, bool keys_ready = false) {
   const int NE = n_phys + q_len;
   const int n_after = n_before + q_len;
   const int P = st.score_offset;
@@ -186,11 +186,13 @@ __device__ void state_select_apply(const ekv_step& st, const UnitState& u, int n
   // overlap.  When a single trip covers the unit (NE <= FCH * threads) the keys stay in registers for
   // the single-victim fast path below.
   constexpr int FCH = 5;
-  const bool one_trip = NE <= FCH * g.n;
+  // keys_ready: pass 1 already ran elsewhere (the chunk path does it in a chip-wide kernel): c.lj / keyA / keyB /
+  // flag are filled and the state is written back; only the select and the renumbering are left
+  const bool one_trip = !keys_ready && NE <= FCH * g.n;
   int rl[FCH];
   uint32_t rka[FCH], rkb[FCH];
   uint8_t rf[FCH];
-  for (int base = 0; base < NE; base += FCH * g.n) {
+  for (int base = 0; base < (keys_ready ? 0 : NE); base += FCH * g.n) {
     float s[FCH], sq[FCH], cc[FCH], ds[FCH], dsq[FCH];
     int ph[FCH];
 #pragma unroll
