@@ -52,6 +52,8 @@ class BudgetedKVCache:
         self.n_phys = [0] * num_layers     # streamed physical extent
         self.free = [None] * num_layers    # int32 [B, Hkv, f]: free physical slots inside [0, n_phys)
         self.scratch = None
+        self._shape_cache = [self._shape(l, 1) for l in range(num_layers)]
+        self._io_cache = [self._io(l) for l in range(num_layers)]
 
     # ------------------------------------------------------------------------------------------
     def _shape(self, l, q_len):
@@ -142,15 +144,28 @@ class BudgetedKVCache:
         evict = int(sp.evict)
         vs = vl = None
         if evict:
-            vs = torch.empty(self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
-            vl = torch.empty(self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
-        shape = self._shape(l, q_len)
-        cstep = sp.to_c(apply=apply, arith=self.arith)
-        need = self.lib.ekv_scratch_bytes(C.byref(shape), C.byref(cstep))
-        if need and (self.scratch is None or self.scratch.numel() < need):
-            self.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        io = self._io(l, q=q, k_new=k_new, v_new=v_new, out=out, new_slots=new_slots, victim_slots=vs,
-                      victim_lidx=vl, scratch=self.scratch if need else None)
+            vv = torch.empty(2, self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
+            vs, vl = vv[0], vv[1]
+        # the C structs are cached (per layer / per StepParams object) and only the fields that change are
+        # rewritten: at batch 1 this call's host time is comparable to the kernels it launches
+        shape = self._shape_cache[l]
+        shape.q_len, shape.n_before, shape.n_phys = q_len, self.n[l], self.n_phys[l]
+        key = (apply, self.arith)
+        cached = sp.__dict__.get("_c")
+        if cached is None or cached[0] != key:
+            cached = sp.__dict__["_c"] = (key, sp.to_c(apply=apply, arith=self.arith))
+        cstep = cached[1]
+        need = 0
+        if q_len > 1 or cstep.tova_head_mean:           # only the chunk kernels and tova's head mean use scratch
+            need = self.lib.ekv_scratch_bytes(C.byref(shape), C.byref(cstep))
+            if need and (self.scratch is None or self.scratch.numel() < need):
+                self.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        io = self._io_cache[l]
+        io.q, io.k_new, io.v_new, io.out = q.data_ptr(), k_new.data_ptr(), v_new.data_ptr(), out.data_ptr()
+        io.new_slots = None if new_slots is None else new_slots.data_ptr()
+        io.victim_slots = None if vs is None else vs.data_ptr()
+        io.victim_lidx = None if vl is None else vl.data_ptr()
+        io.scratch = self.scratch.data_ptr() if need else None
         _lib.check(self.lib.ekv_attend_evict(C.byref(shape), C.byref(io), C.byref(cstep), kernel, self._stream()))
         self.n[l] += q_len
         if new_slots is None:

@@ -30,9 +30,10 @@ def canonical_policy(name: str) -> str:
     return name
 
 
-@dataclass
+@dataclass(frozen=True)
 class StepParams:
-    """Field-for-field the C struct `ekv_step` (include/easykv_b200.h), policy by name."""
+    """Field-for-field the C struct `ekv_step` (include/easykv_b200.h), policy by name.  Immutable (derive variants
+    with `dataclasses.replace`): the cache memoises the C struct on the object."""
     policy: str = "full"
     accumulate: bool = False
     evict: int = 0
