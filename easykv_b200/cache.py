@@ -54,6 +54,7 @@ class BudgetedKVCache:
         self.scratch = None
         self._shape_cache = [self._shape(l, 1) for l in range(num_layers)]
         self._io_cache = [self._io(l) for l in range(num_layers)]
+        self._rope_shape = self._shape(0, 1)
 
     # ------------------------------------------------------------------------------------------
     def _shape(self, l, q_len):
@@ -111,15 +112,23 @@ class BudgetedKVCache:
         (easykv/llama_patch.py:47-72) and the transposes around it."""
         B, ql = q_in.shape[0], q_in.shape[1]
         q_in, k_in, v_in = q_in.contiguous(), k_in.contiguous(), v_in.contiguous()
-        cos, sin = cos.to(self.dtype).contiguous(), sin.to(self.dtype).contiguous()
-        q = torch.empty(B, self.H, ql, self.d, dtype=self.dtype, device=self.device)
-        k = torch.empty(B, self.Hkv, ql, self.d, dtype=self.dtype, device=self.device)
-        v = torch.empty_like(k)
-        pos = None if positions is None else positions.to(device=self.device, dtype=torch.int32).contiguous()
-        shape = _lib.Shape(dtype=_DTYPES[self.dtype], B=B, H=self.H, Hkv=self.Hkv, d=self.d, q_len=ql, cap=self.cap,
-                           n_before=0, n_phys=0)
-        _lib.check(self.lib.ekv_rope_qk(C.byref(shape), _ptr(q_in), _ptr(k_in), _ptr(v_in), _ptr(cos), _ptr(sin), _ptr(pos),
-                                        _ptr(q), _ptr(k), _ptr(v), self._stream()))
+        if cos.dtype != self.dtype:
+            cos, sin = cos.to(self.dtype), sin.to(self.dtype)
+        cos, sin = cos.contiguous(), sin.contiguous()
+        nq, nk = B * self.H * ql * self.d, B * self.Hkv * ql * self.d
+        buf = torch.empty(nq + 2 * nk, dtype=self.dtype, device=self.device)           # one allocation for q, k, v
+        q = buf[:nq].view(B, self.H, ql, self.d)
+        k = buf[nq:nq + nk].view(B, self.Hkv, ql, self.d)
+        v = buf[nq + nk:].view(B, self.Hkv, ql, self.d)
+        pos = None
+        if positions is not None:
+            pos = positions if positions.dtype == torch.int32 else positions.to(torch.int32)
+            pos = pos.contiguous()
+        shape = self._rope_shape
+        shape.B, shape.q_len = B, ql
+        _lib.check(self.lib.ekv_rope_qk(C.byref(shape), q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), cos.data_ptr(),
+                                        sin.data_ptr(), None if pos is None else pos.data_ptr(), q.data_ptr(), k.data_ptr(),
+                                        v.data_ptr(), torch.cuda.current_stream().cuda_stream))
         return q, k, v
 
     def round_state(self, l):

@@ -180,6 +180,9 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
             lp = torch.nn.functional.cross_entropy(lg[:-1], ids[1:], reduction="none")
             return math.exp(statistics.mean(lp.cpu().numpy().tolist()))
         # ---- generation ------------------------------------------------------------------------------------
+        if cfg.get("record_timing", False):                    # for benchmarks: when the prompt phase was complete
+            torch.cuda.synchronize(device)
+            sess.t_prompt_done = time.perf_counter()
         prob, _ = logits_adapter(logits[:, -1, :].float(), temperature, top_p)
         output_ids, times = [], []
         cur_pos = length

@@ -39,7 +39,9 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--prompt", type=int, default=4096)
     ap.add_argument("--new", type=int, default=64)
-    ap.add_argument("--budget", type=int, default=1024)
+    ap.add_argument("--budget", type=float, default=1024, help="integer = absolute, fraction < 1 = ratio of the prompt (encoding / ppl)")
+    ap.add_argument("--mode", default="auto")
+    ap.add_argument("--keep-attention", action="store_true")
     ap.add_argument("--stride", type=int, default=64)
     ap.add_argument("--policy", default="roco")
     args = ap.parse_args()
@@ -59,24 +61,24 @@ def main():
         model = cls(cfg).half().eval()
     ids = torch.randint(3, 32000, (1, args.prompt), generator=torch.Generator().manual_seed(1)).cuda()
     with contextlib.redirect_stdout(io.StringIO()):
-        easykv_b200.enable_fixed_kv(model, Tok(), mode="auto", stride=args.stride)
-    gen = dict(temperature=1e-9, top_p=1.0, budget=args.budget, kv_policy=args.policy)
+        easykv_b200.enable_fixed_kv(model, Tok(), mode=args.mode, stride=args.stride)
+    budget = args.budget if args.budget < 1 else int(args.budget)
+    gen = dict(temperature=1e-9, top_p=1.0, budget=budget, kv_policy=args.policy, keep_attention=args.keep_attention)
     out = {}
     with contextlib.redirect_stdout(io.StringIO()):           # untimed warm-up (cuBLAS handles, kernel attributes)
-        model.easykv_generate(input_ids=ids[:, :max(2 * args.stride, 256)], generation_config=dict(gen, budget=min(args.budget, 64), max_new_tokens=2))
-    for name, new in (("prefill_only", 0), ("prefill_and_decode", args.new)):
-        torch.cuda.synchronize()
-        t0 = time.time()
-        buf = io.StringIO()
-        with contextlib.redirect_stdout(buf):
-            model.easykv_generate(input_ids=ids, generation_config=dict(gen, max_new_tokens=new))
-        torch.cuda.synchronize()
-        out[name] = time.time() - t0
-        out["printed"] = buf.getvalue().strip()
+        model.easykv_generate(input_ids=ids[:, :max(2 * args.stride, 256)], generation_config=dict(gen, budget=budget if budget < 1 else min(budget, 64), max_new_tokens=2))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        model.easykv_generate(input_ids=ids, generation_config=dict(gen, max_new_tokens=args.new, record_timing=True))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     sess = model.easykv_last
-    dec = out["prefill_and_decode"] - out["prefill_only"]
-    print(json.dumps(dict(arch=args.arch, layers=args.layers, prompt=args.prompt, new_tokens=args.new, budget=args.budget,
-                          stride=args.stride, policy=args.policy, prefill_s=round(out["prefill_only"], 3),
+    out = {"prefill_only": sess.t_prompt_done - t0, "printed": buf.getvalue().strip()}
+    dec = t1 - sess.t_prompt_done
+    print(json.dumps(dict(arch=args.arch, layers=args.layers, prompt=args.prompt, new_tokens=args.new, budget=budget, mode=args.mode,
+                          keep_attention=args.keep_attention, stride=args.stride, policy=args.policy, prefill_s=round(out["prefill_only"], 3),
                           decode_tokens_per_s=round(args.new / dec, 2), decode_ms_per_token=round(dec / args.new * 1e3, 2),
                           retained=sess.cache.n[0], eviction_events=len(sess.events), printed=out["printed"],
                           launches=int(sess.cache.lib.ekv_launch_count()))))

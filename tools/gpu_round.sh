@@ -27,5 +27,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:chunk_tc_kernel -s 8 -c 2 -f -o $OUT/${TAG}_chunk_tc python tools/chunk_profile.py 8 32 8 8208 16 h2o_head > /dev/null 2>&1
 echo "== end to end generate (7B shape, installed transformers model classes)"
 timeout 600 python tools/e2e_generate.py --layers 32 --prompt 4096 --new 64 2>&1 | tail -1 | tee $OUT/${TAG}_e2e_llama7b.json
-timeout 600 python tools/e2e_generate.py --arch mistral --layers 32 --prompt 8192 --new 32 --budget 4096 --stride 16 --policy h2o 2>&1 | tail -1 | tee $OUT/${TAG}_e2e_mistral7b.json
+timeout 600 python tools/e2e_generate.py --arch mistral --layers 32 --prompt 16384 --new 16 --mode encoding --budget 0.5 --stride 16 --policy h2o --keep-attention 2>&1 | tail -1 | tee $OUT/${TAG}_e2e_mistral7b.json
 ls -la $OUT | tail -30
