@@ -192,6 +192,22 @@ def test_driver_end_to_end_gpu(name, ekv_lib):
 
 
 @pytest.mark.gpu
+def test_driver_batch_of_identical_prompts(ekv_lib):
+    """The reference is hard-wired to batch 1 (easykv.py:66-67, 290, 430); here sequences are independent units of
+    the same launches: a batch of identical prompts must evict and generate exactly what one prompt does."""
+    meta, z = replay.load_golden("gqa_mistral_auto_roco_fp32")
+    model, ids = _model_and_ids(meta, device="cuda")
+    res1, _, sess1 = _run(meta, model, ids, "cpu")
+    ev1 = [e.clone() for _, e in sess1.events]
+    res3, _, sess3 = _run(meta, model, ids.repeat(3, 1), "cpu")
+    assert res3 == [res1] * 3
+    assert len(sess3.events) == len(ev1)
+    for (_, e3), e1 in zip(sess3.events, ev1):
+        for b in range(3):
+            assert torch.equal(e3[:, b], e1[:, 0])
+
+
+@pytest.mark.gpu
 def test_driver_binds_to_installed_transformers(ekv_lib):
     """The seam binds to transformers-5.x attention modules (position_embeddings, 2-tuple return): with
     kv_policy='full' nothing is evicted, so greedy generation must equal HF's own eager generation."""
