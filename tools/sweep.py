@@ -32,10 +32,11 @@ def steady_state(cache, l, n, dev):
     cache.SQ[l][:, :, :n] = cache.S[l][:, :, :n] ** 2 / cache.Cn[l][:, :, :n] * 1.5
 
 
-def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float16, kernel=0, cluster=0, variant=0):
+def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float16, kernel=0, cluster=0, variant=0, literal_prompt=0):
     d, dev = 128, "cuda"
     torch.manual_seed(0)
-    cache = BudgetedKVCache(L, B, H, Hkv, d, n + q_len * (1 if policy != "full" else 3 + steps + 1), dtype=dtype, arith=1)
+    grow = policy == "full" or literal_prompt
+    cache = BudgetedKVCache(L, B, H, Hkv, d, n + q_len * (3 + steps + 1 if grow else 1), dtype=dtype, arith=1)
     cache.lib.ekv_debug_set_dispatch(variant, cluster)
     for l in range(L):
         cache.load_prefill(l, torch.randn(B, Hkv, n, d, device=dev, dtype=dtype), torch.randn(B, Hkv, n, d, device=dev, dtype=dtype),
@@ -51,11 +52,27 @@ def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float
         sp = StepParams(policy=policy, accumulate=policy in ("roco", "h2o_head", "tova"), evict=0 if policy == "full" else q_len,
                         counter_add=float(q_len), c_new_step=1.0, k_feasible=max(budget - recent - 4, q_len), sink_protect=4,
                         win_lo=4, win_recent=recent, range_start=4)
+    if literal_prompt:
+        # BASELINE configs[1] exactly as written: mode='decoding', the prompt's slots carry no state and are never
+        # evicted, the generated ones (< budget) are only scored (easykv.py:294-303): attention over n keys,
+        # roco accumulate over the n - prompt generated slots, no eviction
+        sp = StepParams(policy=policy, accumulate=True, evict=0, score_offset=literal_prompt, c_new0=1.0, k_feasible=700)
     q = torch.randn(L, B, H, q_len, d, device=dev, dtype=dtype) * 0.3
     kn = torch.randn(L, B, Hkv, q_len, d, device=dev, dtype=dtype)
     vn = torch.randn(L, B, Hkv, q_len, d, device=dev, dtype=dtype)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if q_len == 1 and sp.evict == 1 and kernel == 0:
+    if literal_prompt:
+        cache2 = cache                              # append mode: the cache grows by one slot per step
+        for _ in range(2):
+            for l in range(L):
+                cache2.step(l, sp, q[l], kn[l], vn[l], kernel=kernel)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            for l in range(L):
+                cache2.step(l, sp, q[l], kn[l], vn[l], kernel=kernel)
+        e1.record()
+    elif q_len == 1 and sp.evict == 1 and kernel == 0:
         # steady-state decode: one CUDA graph per step (L launches), no host work in the timed region
         from easykv_b200.cache import SteadyDecode
         sd = SteadyDecode(cache, sp, q, kn, vn).capture()
@@ -99,6 +116,7 @@ def main():
         for pol in ("h2o_head", "tova", "recency", "full"):
             run_case("13B sweep " + pol, 32, 40, 40, 2112, 1, pol)
         run_case("7B b64 bf16", 64, 32, 32, 1088, 1, "roco", dtype=torch.bfloat16)
+        run_case("C2 literal: decoding, 4096 prompt + 200 generated, no eviction", 16, 32, 32, 4296, 1, "roco", literal_prompt=4096)
         run_case("7B b32 general-kernel", 32, 32, 32, 1088, 1, "roco", kernel=1, steps=3)
     if what in ("cluster",):
         for B in (1, 2, 4, 8):
