@@ -511,10 +511,11 @@ int launch_decode(const KernelArgs& a, cudaStream_t stream) {
   if (a.st.evict <= 1) {
     const int G = a.H / a.Hkv;
     if (decode_cluster_size() > 0) return launch_decode_cluster(a, false, stream);
-    // fewer units than half the SMs: split each unit over a cluster.  g = 8: the persistent kernel's 544-thread
-    // CTAs leave 96 registers per thread and spill; the cluster kernel's 288-thread CTAs do not
-    if (decode_cluster_size() == 0 && (a.B * a.Hkv * 2 <= device_sm_count() || G >= 8)) {
-      const int rc = launch_decode_cluster(a, G < 8, stream);
+    // fewer units than half the SMs: split each unit over a cluster.  g >= 2: the persistent kernel's 544-thread
+    // CTAs leave 96 registers per thread and spill (measured 0.40-0.45 of the roofline on the Mistral layout at any
+    // cache size, 0.66 at g = 2); the cluster kernel's 288-thread CTAs do not (0.56-0.67 / 0.74, C = 1 included)
+    if (decode_cluster_size() == 0 && (a.B * a.Hkv * 2 <= device_sm_count() || G >= 2)) {
+      const int rc = launch_decode_cluster(a, G < 2, stream);
       if (rc != EKV_ERR_UNSUPPORTED) return rc;
     }
   }

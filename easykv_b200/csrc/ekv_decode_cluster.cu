@@ -921,7 +921,7 @@ static int plan_cluster(const KernelArgs& a, int sms, int force_c, int& C, int& 
     if (bytes < L.fixed + ClusterSmem<T>::min_ring(G)) bytes = L.fixed + ClusterSmem<T>::min_ring(G);
     return true;
   };
-  int best = 0;
+  int best = 0, best_fixed = 0;
   for (int c = 1; c <= 8; c *= 2) {
     if (force_c && c != force_c) continue;
     int sl, stg, bytes;
@@ -929,11 +929,15 @@ static int plan_cluster(const KernelArgs& a, int sms, int force_c, int& C, int& 
     if (best && !force_c) {
       if (TC) {
         if (slice <= 1536 && (U * c > 2 * sms || sl < 4 * Cfg::TILE_ROWS)) break;   // small enough already; keep slices non-trivial
-      } else if (U * c > sms || sl < 2 * Cfg::TILE_ROWS) {
-        break;                                                                      // keep one wave, keep slices non-trivial
+      } else {
+        // keep one wave and non-trivial slices — unless a CTA still needs more than half an SM's shared memory
+        // while there are more CTAs than SMs: then halving the slice again lets two CTAs share an SM
+        const bool crowded = G <= 4 && U * best * 2 > sms && best_fixed > 64 * 1024;
+        if (!crowded && (U * c > sms || sl < 2 * Cfg::TILE_ROWS)) break;
       }
     }
     best = c; C = c; slice = sl; stages = stg; smem = bytes;
+    best_fixed = ClusterSmem<T>(G, sl, c, TC).fixed;
   }
   return best ? EKV_OK : EKV_ERR_UNSUPPORTED;
 }
