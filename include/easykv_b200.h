@@ -112,7 +112,7 @@ typedef struct ekv_layer_io {
   int32_t*    victim_slots;  /* [B, Hkv, evict] out: physical slots freed (may alias new_slots),
                                 ordered like victim_lidx                                          */
   int32_t*    victim_lidx;   /* [B, Hkv, evict] out: the reference's eviction ids, ascending       */
-  void*       scratch;       /* >= ekv_scratch_bytes() bytes (only tova_head_mean needs any)       */
+  void*       scratch;       /* >= ekv_scratch_bytes() bytes of device memory, or NULL (see below)  */
 } ekv_layer_io;
 
 typedef struct ekv_shape {
@@ -127,7 +127,10 @@ typedef struct ekv_shape {
 EKV_API int         ekv_abi_version(void);
 EKV_API const char* ekv_last_error(void);
 
-/* Bytes of `scratch` a call with this shape/step needs (0 unless step->tova_head_mean). */
+/* Bytes of `scratch` a call with this shape/step uses.  Non-zero for (a) strided chunks (q_len > 1) in a 16-bit
+ * dtype — the tensor-core chunk kernels keep their per-split row statistics, partial outputs, column sums and
+ * selection keys there; with scratch == NULL such a call falls back to the exact CUDA-core general kernel — and
+ * (b) step->tova_head_mean (required).  Contents need not survive the call. */
 EKV_API int64_t ekv_scratch_bytes(const ekv_shape* shape, const ekv_step* step);
 
 /* Fused forward for one layer: append -> QK^T/sqrt(d) -> softmax -> PV -> GQA fold ->
@@ -135,8 +138,9 @@ EKV_API int64_t ekv_scratch_bytes(const ekv_shape* shape, const ekv_step* step);
  * Replaces: llama_patch.py:193-230 (cache append, repeat_kv, matmul, mask, softmax, matmul),
  * easykv.py:188-196 (GQA fold), :288-300/:443-457 (accumulate), :303-362/:459-499 (select),
  * :56-82 (KV compaction) and :315-333/:465-483 (state compaction).
- * `kernel`: 0 = automatic (the TMA-pipelined decode kernel when q_len == 1 and the shape is
- * supported, else the general kernel); 1 = force the general kernel. */
+ * `kernel`: 0 = automatic — q_len == 1: the persistent TMA-pipelined decode kernel (MHA) or the cluster-split
+ * decode kernel (GQA, long caches, small batches); q_len > 1 in a 16-bit dtype with scratch: the tensor-core chunk
+ * kernels; anything else: the general kernel.  1 = force the exact CUDA-core general kernel. */
 EKV_API int ekv_attend_evict(const ekv_shape* shape, const ekv_layer_io* io, const ekv_step* step,
                      int32_t kernel, void* stream);
 

@@ -42,6 +42,24 @@ def test_argument_validation_without_gpu(ekv_lib):
     assert ekv_lib.ekv_launch_count() == 0
 
 
+def test_scratch_bytes_is_host_only_and_consistent(ekv_lib):
+    """ekv_scratch_bytes needs no GPU: 0 for decode steps, > 0 (and growing with the cache) for 16-bit chunks,
+    0 for fp32 chunks (general kernel), the head-mean staging on top for tova in encoding / ppl."""
+    from easykv_b200 import _lib
+    st = _lib.Step(policy=_lib.POLICY_ROCO, accumulate=1, evict=16)
+    def need(dtype, q_len, n, step=st):
+        sh = _lib.Shape(dtype=dtype, B=2, H=32, Hkv=8, d=128, q_len=q_len, cap=n + q_len, n_before=n, n_phys=n)
+        return ekv_lib.ekv_scratch_bytes(ctypes.byref(sh), ctypes.byref(step))
+    assert need(_lib.F16, 1, 8208) == 0
+    assert need(_lib.F32, 16, 8208) == 0
+    a, b = need(_lib.F16, 16, 1024), need(_lib.F16, 16, 8208)
+    assert 0 < a < b < 1 << 30
+    assert need(_lib.BF16, 16, 8208) == b
+    tova = _lib.Step(policy=_lib.POLICY_TOVA, accumulate=1, evict=16, tova_head_mean=1)
+    assert need(_lib.F16, 16, 8208, tova) == b + 2 * 8 * (8208 + 16) * 4
+    assert need(_lib.F32, 16, 8208, tova) == 2 * 8 * (8208 + 16) * 4
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "easykv_b200")
     for dirpath, _, files in os.walk(pkg):
