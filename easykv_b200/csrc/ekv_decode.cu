@@ -23,6 +23,7 @@
 // repeat_kv, QK^T, mask, softmax, PV) and easykv.py:271-362 / :683-748 (fold, accumulate, select,
 // truncate_kv_cache_silo, state compaction) for one layer of one decode forward.
 #include "ekv_decode_common.cuh"
+#include "ekv_mma.cuh"
 
 namespace ekv {
 
@@ -267,7 +268,7 @@ decode_kernel(const KernelArgs a, const int stages) {
     stamp(k_unit, 3);
     // ---- softmax (fp32 over the model-dtype logits; llama_patch.py:210-219) ---------------------------
     {
-      float mx[G], inv[G];
+      float mx[G], inv[G], rcp[G];
       const int my_g = vi0 % G;                                  // head of the logits this lane stored
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -302,13 +303,14 @@ decode_kernel(const KernelArgs a, const int stages) {
 #pragma unroll
         for (int w = 1; w < NWARP; ++w) v += red2[g * NWARP + w];
         inv[g] = a.st.arith ? v : __fdiv_rn(1.0f, v);
+        rcp[g] = __frcp_rn(v);
       }
 #pragma unroll 5
       for (int e = tid; e < NE; e += NCONS)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float ex = expf(Tr<T>::to_f(plog[g * nep + e]) - mx[g]);
-          plog[g * nep + e] = Tr<T>::from_f(a.st.arith ? __fdiv_rn(ex, inv[g]) : __fmul_rn(ex, inv[g]));
+          plog[g * nep + e] = Tr<T>::from_f(a.st.arith ? div_rn_by(ex, inv[g], rcp[g]) : __fmul_rn(ex, inv[g]));
         }
     }
     grp.sync();

@@ -381,7 +381,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
 
   stamp(2);
   // ---- softmax across the cluster ------------------------------------------------------------------------
-  float mx[G], inv[G];
+  float mx[G], inv[G], rcp[G];
   {
     if constexpr (!TC) {
       const int my_g = bitrev_idx<16>(l16) % G;
@@ -433,12 +433,13 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       float v = xsum[g];
       for (int p = 1; p < C; ++p) v += xsum[p * G + g];                            // rank order on every CTA
       inv[g] = a.st.arith ? v : __fdiv_rn(1.0f, v);
+      rcp[g] = __frcp_rn(v);
     }
     for (int e = tid; e < NEl; e += NCONS)
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const float ex = expf(Tr<T>::to_f(plog[g * slp + e]) - mx[g]);
-        plog[g * slp + e] = Tr<T>::from_f(a.st.arith ? __fdiv_rn(ex, inv[g]) : __fmul_rn(ex, inv[g]));   // llama_patch.py:218-219
+        plog[g * slp + e] = Tr<T>::from_f(a.st.arith ? div_rn_by(ex, inv[g], rcp[g]) : __fmul_rn(ex, inv[g]));   // llama_patch.py:218-219
       }
   }
   grp.sync();

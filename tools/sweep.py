@@ -116,6 +116,9 @@ def main():
         for pol in ("h2o_head", "tova", "recency", "full"):
             run_case("13B sweep " + pol, 32, 40, 40, 2112, 1, pol)
         run_case("7B b64 bf16", 64, 32, 32, 1088, 1, "roco", dtype=torch.bfloat16)
+        # the generation phase of BASELINE configs[2] / [4] ('encoding' mode: attention over the retained cache, no policy)
+        run_case("C3 generation: mistral n8208 b16, no policy", 16, 32, 8, 8208, 1, "full")
+        run_case("C5 generation: 70B n8256 b8, no policy", 8, 64, 8, 8256, 1, "full")
         run_case("C2 literal: decoding, 4096 prompt + 200 generated, no eviction", 16, 32, 32, 4296, 1, "roco", literal_prompt=4096)
         run_case("7B b32 general-kernel", 32, 32, 32, 1088, 1, "roco", kernel=1, steps=3)
     if what in ("cluster",):
