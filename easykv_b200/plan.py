@@ -125,6 +125,8 @@ def resolve_plan(kv_mode, length, budget, stride, recent_ratio=0.1, temp_length=
         idx -= 1
     if kv_mode == "encoding":
         r_idx = idx - stride
+        if r_idx < 1:             # the reference's search range(idx-1, -1, -1) finds nothing: it would prefill 0 tokens
+            raise AssertionError("budget too small for this stride (no dense prefix left)")
     else:
         r_idx = idx % stride or stride
         if r_idx >= idx:          # the reference's search range(1, idx) comes up empty

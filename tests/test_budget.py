@@ -74,3 +74,40 @@ def test_policy_names():
         P.resolve_plan("auto", 100, 0.5, 8)                  # easykv.py:222
     with pytest.raises(AssertionError):
         P.resolve_plan("encoding_decoding", 100, 64, 1)      # stride 1 asserts in the reference (:666-669)
+
+
+def test_plan_and_schedule_match_oracle_property():
+    """Randomised: the product's integer-only host logic and the restatement agree on every resolvable
+    (mode, length, budget, stride) and raise together on the ones the reference asserts on."""
+    import random
+    rng = random.Random(7)
+    checked = 0
+    for _ in range(400):
+        mode = rng.choice(["encoding", "ppl", "auto", "decoding", "encoding_decoding"])
+        length = rng.randint(16, 3000)
+        stride = rng.choice([1, 2, 4, 7, 8, 16, 24, 64, 96])
+        budget = rng.choice([rng.randint(8, 2 * length), round(rng.uniform(0.05, 1.2), 3)])
+        if mode in ("auto", "decoding", "encoding_decoding"):
+            budget = int(budget) if isinstance(budget, int) else rng.randint(8, 2 * length)
+        try:
+            b = R.resolve_plan(mode, length, budget, stride)
+        except (AssertionError, StopIteration):
+            with pytest.raises((AssertionError, ValueError)):
+                P.resolve_plan(mode, length, budget, stride)
+            continue
+        try:
+            a = P.resolve_plan(mode, length, budget, stride)
+        except AssertionError:
+            # the reference fails later: stride 1 asserts at :666-669; an empty dense prefix (r_idx == 0) cannot be run
+            assert (b.mode == "encoding_decoding" and stride == 1) or (b.mode == "encoding" and b.r_idx == 0)
+            continue
+        assert (a.mode, a.budget, a.idx, a.r_idx, a.recent_window, a.sink) == (b.mode, b.budget, b.idx, b.r_idx, b.recent_window, b.sink)
+        pol = rng.choice(["roco", "tova", "recency"] + ([] if a.mode == "encoding_decoding" else ["h2o_head", "full"]))
+        keep = rng.random() < 0.3
+        sa, sb = list(P.schedule(a, pol, 12, keep)), list(R.schedule(b, pol, 12, keep))
+        assert len(sa) == len(sb)
+        for (ka, qa, xa), (kb, qb, xb) in zip(sa, sb):
+            assert (ka, qa) == (kb, qb)
+            _same_step(xa, xb)
+        checked += 1
+    assert checked > 150

@@ -167,6 +167,29 @@ def test_logits_adapter_matches_reference_formula():
     assert torch.equal((p > 0).sum(-1), kept)
 
 
+def test_seam_binds_to_installed_transformers_cpu(monkeypatch):
+    """The attention seam on the installed transformers (5.x) Llama classes — `position_embeddings`, 2-tuple return,
+    keyword-only decoder-layer call — with the stand-in cache: without a policy, greedy generation through
+    `easykv_generate` must equal the model's own eager generation."""
+    transformers = pytest.importorskip("transformers")
+    monkeypatch.setattr(drv, "BudgetedKVCache", OracleCache)
+    monkeypatch.setattr(torch, "multinomial", lambda p, num_samples=1, **kw: p.argmax(dim=-1, keepdim=True))
+    cfg = transformers.LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=2, head_dim=64, vocab_size=300, max_position_embeddings=512,
+                                   attn_implementation="eager")
+    torch.manual_seed(0)
+    model = transformers.LlamaForCausalLM(cfg).eval()
+    ids = torch.randint(3, 300, (1, 40), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = model.generate(ids, max_new_tokens=8, do_sample=False, pad_token_id=0)[0, 40:].tolist()
+    with contextlib.redirect_stdout(io.StringIO()):
+        easykv_b200.enable_fixed_kv(model, scaffold.StubTokenizer(), mode="decoding")
+        text = model.easykv_generate(input_ids=ids, generation_config=dict(
+            temperature=1e-9, max_new_tokens=8, budget=512, kv_policy="full", aten_arith="cpu"))
+    assert [int(t) for t in text.split()] == ref
+    assert "forward" not in model.model.layers[0].self_attn.__dict__
+
+
 # ---------------------------------------------------------------------------------------------------------
 # GPU: the same user-level calls through the CUDA library
 # ---------------------------------------------------------------------------------------------------------
