@@ -38,11 +38,13 @@ constexpr int PITCH = 272;           // bytes per shared-memory row: 256 + 16 ke
 constexpr int TILE_BYTES = TK * PITCH;
 constexpr int STAGES = 3;            // pass 1; pass 2 (K and V tiles) uses 2 so that two CTAs fit an SM
 constexpr float NEG = -1.0e30f;      // masked logit: finite, exp(NEG - max) == 0 exactly
+constexpr int TARGET_CTAS_PASS1 = 444;  // three lighter CTAs per SM in pass 1
 constexpr int TARGET_CTAS = 296;      // two CTAs per SM: their dependency stalls overlap
 }  // namespace tc
 
 struct ChunkPlan {
-  int R, RB, Rpad, NE, NEpad, ntiles, splits, tps;      // tps = tiles per split
+  int R, RB, Rpad, NE, NEpad, ntiles, splits, tps;      // tps = tiles per split (pass 2)
+  int splits1, tps1;                                    // pass 1 (lighter CTAs, three per SM): a finer split
   long long off_stats, off_opart, off_cpart, off_klj, off_ka, off_kb, off_kf, bytes;
 };
 
@@ -62,8 +64,14 @@ ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
   p.tps = (p.ntiles + want - 1) / want;
   if (p.tps < 2 && p.ntiles >= 2) p.tps = 2;             // at least two tiles per CTA: keep the pipeline worth its prologue
   p.splits = (p.ntiles + p.tps - 1) / p.tps;
+  int want1 = TARGET_CTAS_PASS1 / (U * p.RB);
+  if (want1 < 1) want1 = 1;
+  if (want1 > p.ntiles) want1 = p.ntiles;
+  p.tps1 = (p.ntiles + want1 - 1) / want1;
+  if (p.tps1 < 2 && p.ntiles >= 2) p.tps1 = 2;
+  p.splits1 = (p.ntiles + p.tps1 - 1) / p.tps1;
   long long o = 0;
-  p.off_stats = o; o += (long long)U * p.splits * p.Rpad * 2 * 4;
+  p.off_stats = o; o += (long long)U * p.splits1 * p.Rpad * 2 * 4;
   o = (o + 255) / 256 * 256;
   p.off_opart = o; o += (long long)U * p.splits * p.Rpad * D * 4;
   o = (o + 255) / 256 * 256;
@@ -86,7 +94,7 @@ long long chunk_tc_scratch_bytes(int B, int Hkv, int G, int q_len, int n_phys) {
 // that the per-element code is straight-line (as a run-time switch it cost a branch per element and the
 // IEEE-division slow-path calls of the other flavour in the instruction stream).
 template <typename T, int G, int PASS, bool ARITH>
-__global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a, const ChunkPlan pl) {
+__global__ void __launch_bounds__(tc::NT, PASS == 1 ? 3 : 2) chunk_tc_kernel(const KernelArgs a, const ChunkPlan pl) {
   using namespace tc;
   constexpr int STAGES = PASS == 2 ? 2 : tc::STAGES;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -98,12 +106,13 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
   constexpr int PFP = TK + 2;                                     // row pitch in elements: conflict-free both ways
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.x % pl.splits;
-  const int rb = (blockIdx.x / pl.splits) % pl.RB;
-  const int unit = blockIdx.x / (pl.splits * pl.RB);
+  const int nsplit = PASS == 1 ? pl.splits1 : pl.splits, tps = PASS == 1 ? pl.tps1 : pl.tps;
+  const int split = blockIdx.x % nsplit;
+  const int rb = (blockIdx.x / nsplit) % pl.RB;
+  const int unit = blockIdx.x / (nsplit * pl.RB);
   const int b = unit / a.Hkv, h = unit % a.Hkv;
   const int QL = a.q_len, n_phys = a.n_phys, NE = pl.NE, R = pl.R;
-  const int t_begin = split * pl.tps, t_end = min(pl.ntiles, t_begin + pl.tps);
+  const int t_begin = split * tps, t_end = min(pl.ntiles, t_begin + tps);
   const T* Kg = reinterpret_cast<const T*>(a.K) + (size_t)unit * a.cap * D;
   const T* Vg = reinterpret_cast<const T*>(a.V) + (size_t)unit * a.cap * D;
   const T* kn = reinterpret_cast<const T*>(a.k_new) + (size_t)unit * QL * D;
@@ -189,13 +198,13 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
   float M0 = 0.f, M1 = 0.f, L0 = 1.f, L1 = 1.f, R0 = 1.f, R1 = 1.f;
   if (PASS == 2) {
     float m0 = NEG, m1 = NEG;
-    for (int s = 0; s < pl.splits; ++s) {
-      const float2* st = stats + ((size_t)unit * pl.splits + s) * pl.Rpad;
+    for (int s = 0; s < pl.splits1; ++s) {
+      const float2* st = stats + ((size_t)unit * pl.splits1 + s) * pl.Rpad;
       m0 = fmaxf(m0, st[rb * MR + rr0].x); m1 = fmaxf(m1, st[rb * MR + rr1].x);
     }
     float l0 = 0.f, l1 = 0.f;
-    for (int s = 0; s < pl.splits; ++s) {                         // split order on every CTA
-      const float2* st = stats + ((size_t)unit * pl.splits + s) * pl.Rpad;
+    for (int s = 0; s < pl.splits1; ++s) {                        // split order on every CTA
+      const float2* st = stats + ((size_t)unit * pl.splits1 + s) * pl.Rpad;
       const float2 x0 = st[rb * MR + rr0], x1 = st[rb * MR + rr1];
       l0 += x0.y * expf(x0.x - m0);
       l1 += x1.y * expf(x1.x - m1);
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(tc::NT, 2) chunk_tc_kernel(const KernelArgs a,
     }
     if ((lane & 3) == 0) {
       float2* st = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_stats) +
-                   ((size_t)unit * pl.splits + split) * pl.Rpad;
+                   ((size_t)unit * pl.splits1 + split) * pl.Rpad;
       st[rb * MR + rr0] = make_float2(mrun0, lrun0);
       st[rb * MR + rr1] = make_float2(mrun1, lrun1);
     }
@@ -563,9 +572,9 @@ template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, 
     configured[dev] = 1;
   }
   const int U = a.B * a.Hkv;
-  const int grid = U * pl.RB * pl.splits;
-  if (a.st.arith) chunk_tc_kernel<T, G, 1, true><<<grid, NT, smem1, stream>>>(a, pl);
-  else chunk_tc_kernel<T, G, 1, false><<<grid, NT, smem1, stream>>>(a, pl);
+  const int grid = U * pl.RB * pl.splits, grid1 = U * pl.RB * pl.splits1;
+  if (a.st.arith) chunk_tc_kernel<T, G, 1, true><<<grid1, NT, smem1, stream>>>(a, pl);
+  else chunk_tc_kernel<T, G, 1, false><<<grid1, NT, smem1, stream>>>(a, pl);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<1> launch", err);
   count_launch();
   if (a.st.arith) chunk_tc_kernel<T, G, 2, true><<<grid, NT, smem2, stream>>>(a, pl);
