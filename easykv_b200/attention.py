@@ -60,6 +60,16 @@ def budgeted_attention_forward(self, hidden_states, attention_mask=None, positio
     H, Hkv, d = self._ekv_geometry
     b, ql, _ = hidden_states.shape
     q_in, k_in, v_in = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+    if sess.streaming:
+        # streaming variant (llama_patch.py:251-379): un-rotated keys in the cache, every key rotated at its index in
+        # the arrival-ordered cache and the queries at n_before .. n_before + q_len - 1, on every forward
+        cos, sin = sess.stream_table(self, v_in, sess.cache.n[l] + ql)
+        out, victims = sess.cache.step_stream(l, sess.step, q_in, k_in, v_in, cos, sin)
+        sess.record(l, victims)
+        attn_output = self.o_proj(out.transpose(1, 2).reshape(b, ql, H * d))
+        if position_embeddings is not None or sess.two_tuple:
+            return attn_output, None
+        return attn_output, None, past_key_value
     if position_embeddings is not None:                       # transformers >= 4.48: the model computed them, per token
         cos, sin = position_embeddings
         pos = None

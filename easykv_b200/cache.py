@@ -52,6 +52,7 @@ class BudgetedKVCache:
         self.n_phys = [0] * num_layers     # streamed physical extent
         self.free = [None] * num_layers    # int32 [B, Hkv, f]: free physical slots inside [0, n_phys)
         self.scratch = None
+        self.K_raw = None                  # streaming variant: the un-rotated keys, same physical layout as K
         self._shape_cache = [self._shape(l, 1) for l in range(num_layers)]
         self._io_cache = [self._io(l) for l in range(num_layers)]
         self._rope_shape = self._shape(0, 1)
@@ -86,6 +87,8 @@ class BudgetedKVCache:
         if n > self.cap:
             raise ValueError(f"prefill of {n} slots exceeds capacity {self.cap}")
         self.K[l][:, :, :n].copy_(K)
+        if self.K_raw is not None:
+            self.K_raw[l][:, :, :n].copy_(K)
         self.V[l][:, :, :n].copy_(V)
         self.S[l].zero_(); self.SQ[l].zero_(); self.Cn[l].zero_()
         if C_init is not None and len(C_init):
@@ -130,6 +133,47 @@ class BudgetedKVCache:
                                         sin.data_ptr(), None if pos is None else pos.data_ptr(), q.data_ptr(), k.data_ptr(),
                                         v.data_ptr(), torch.cuda.current_stream().cuda_stream))
         return q, k, v
+
+    # ---- streaming variant (generation_config['streaming'], llama_forward_stream) -----------------------------------
+    def enable_streaming(self, adopt_rotated=False):
+        """Keep un-rotated keys in a second buffer `K_raw`; `step_stream` re-rotates the whole cache at
+        cache-relative positions before every forward (easykv/llama_patch.py:310-327).  `adopt_rotated`: take the
+        rows currently in K as the un-rotated ones — what the reference does in 'decoding' mode, where the prompt is
+        prefilled by the stock forward (rotated at true positions) before the streaming forward is patched in
+        (easykv.py:232 vs :253) and then rotated again on every step."""
+        if self.K_raw is None:
+            self.K_raw = [torch.zeros_like(k) for k in self.K]
+        if adopt_rotated:
+            for kr, k in zip(self.K_raw, self.K):
+                kr.copy_(k)
+
+    def step_stream(self, l, sp: StepParams, q_in, k_in, v_in, cos, sin, apply=True, kernel=0):
+        """One streaming forward of layer `l`.  q_in `[B, q_len, H*d]`, k_in / v_in `[B, q_len, Hkv*d]` are the
+        projections' UN-rotated outputs; cos / sin `[rows, d]` the model's table."""
+        if self.K_raw is None:
+            raise RuntimeError("enable_streaming() first")
+        B, ql = q_in.shape[0], q_in.shape[1]
+        if self.free_count(l) > ql or 0 < self.free_count(l) < ql:
+            self.defragment(l)
+        if cos.dtype != self.dtype:
+            cos, sin = cos.to(self.dtype), sin.to(self.dtype)
+        cos, sin = cos.contiguous(), sin.contiguous()
+        n = self.n[l]
+        if n:                                             # K = rope(K_raw, position = logical index)
+            shape = self._shape(l, 0)
+            io = self._io(l)
+            _lib.check(self.lib.ekv_rope_cache(C.byref(shape), C.byref(io), self.K_raw[l].data_ptr(), cos.data_ptr(),
+                                               sin.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        pos = torch.arange(n, n + ql, dtype=torch.int32, device=self.device)[None].expand(B, -1)
+        q, k_rot, v = self.rope_qkv(q_in, k_in, v_in, cos, sin, pos)
+        if self.free_count(l) == ql:                      # the slots the fused kernel will append to
+            slots = self.free[l].long()
+        else:
+            slots = torch.arange(self.n_phys[l], self.n_phys[l] + ql, device=self.device).expand(B, self.Hkv, ql)
+        out, vl = self.step(l, sp, q, k_rot, v, apply=apply, kernel=kernel)
+        k_raw = k_in.view(B, ql, self.Hkv, self.d).transpose(1, 2)
+        self.K_raw[l].scatter_(2, slots[..., None].expand(B, self.Hkv, ql, self.d), k_raw)
+        return out, vl
 
     def round_state(self, l):
         """Round S / SQ to the model dtype once (what `torch.sum(attention_map, dim=1)` does for the whole dense
@@ -220,6 +264,8 @@ class BudgetedKVCache:
         st = [torch.empty(self.B, self.Hkv, n, dtype=torch.float32, device=self.device) for _ in range(3)] if with_state else [None] * 3
         shape = self._shape(l, 0)
         io = self._io(l)
+        if self.K_raw is not None:                        # streaming: the cache's keys are the un-rotated ones
+            io.K = self.K_raw[l].data_ptr()
         _lib.check(self.lib.ekv_export_logical(C.byref(shape), C.byref(io), _ptr(Ko), _ptr(Vo), _ptr(st[0]),
                                                _ptr(st[1]), _ptr(st[2]), self._stream()))
         return (Ko, Vo, *st) if with_state else (Ko, Vo)
@@ -230,7 +276,7 @@ class BudgetedKVCache:
         slots that a one-token-per-step decode loop would otherwise stream forever)."""
         n = self.n[l]
         Ko, Vo, S, SQ, Cn = self.export(l, with_state=True)
-        self.K[l][:, :, :n].copy_(Ko); self.V[l][:, :, :n].copy_(Vo)
+        (self.K if self.K_raw is None else self.K_raw)[l][:, :, :n].copy_(Ko); self.V[l][:, :, :n].copy_(Vo)
         self.S[l][:, :, :n].copy_(S); self.SQ[l][:, :, :n].copy_(SQ); self.Cn[l][:, :, :n].copy_(Cn)
         self.lidx[l].fill_(-1)
         self.lidx[l][:, :, :n] = torch.arange(n, dtype=torch.int32, device=self.device)

@@ -194,6 +194,17 @@ int ekv_rope_qk(const ekv_shape* sh, const void* q_in, const void* k_in, const v
                         sh->q_len, sh->d, (cudaStream_t)stream);
 }
 
+int ekv_rope_cache(const ekv_shape* sh, const ekv_layer_io* io, const void* K_raw, const void* cos_t, const void* sin_t,
+                   void* stream) {
+  KernelArgs a;
+  int rc = build_args(sh, io, nullptr, a);
+  if (rc) return rc;
+  if (!io->K || !io->lidx || !K_raw || !cos_t || !sin_t) return set_error(EKV_ERR_INVALID, "null tensor pointer");
+  if (sh->d & 1) return set_error(EKV_ERR_INVALID, "odd head dim %d", sh->d);
+  return launch_rope_cache(sh->dtype, K_raw, io->K, io->lidx, cos_t, sin_t, sh->B * sh->Hkv, sh->cap, sh->n_phys, sh->d,
+                           (cudaStream_t)stream);
+}
+
 int ekv_export_logical(const ekv_shape* sh, const ekv_layer_io* io, void* K_out, void* V_out, float* S_out,
                        float* SQ_out, float* C_out, void* stream) {
   KernelArgs a;

@@ -249,3 +249,60 @@ int launch_rope_qk(int dtype, const void* q_in, const void* k_in, const void* v_
 }
 
 }  // namespace ekv
+
+// ---- streaming variant: re-rotate the whole cache at cache-relative positions --------------------
+// llama_forward_stream / mistral_forward_stream (easykv/llama_patch.py:251-379, mistral_patch.py:189-286) keep
+// UN-rotated keys in the cache and apply RoPE to all of them at positions 0..kv_len-1 — their index in the
+// arrival-ordered cache, which shifts with every eviction — on every forward (:310-327).  Here the un-rotated rows
+// live in a second buffer K_raw (same physical layout); this kernel writes K[slot] = rope(K_raw[slot], lidx[slot])
+// for every valid slot, after which the attention kernels run unchanged.  Same arithmetic as rope_qk_kernel.
+namespace ekv {
+
+template <typename T>
+__global__ void rope_cache_kernel(const T* __restrict__ K_raw, T* __restrict__ K, const int32_t* __restrict__ lidx,
+                                  const T* __restrict__ cos_t, const T* __restrict__ sin_t, int units, int cap, int n_phys, int d) {
+  const int half = d >> 1;
+  const long long total = (long long)units * n_phys * half;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % half);
+    const int slot = (int)((idx / half) % n_phys);
+    const int unit = (int)(idx / ((long long)half * n_phys));
+    const int row = lidx[(size_t)unit * cap + slot];
+    if (row < 0) continue;
+    const T* x = K_raw + ((size_t)unit * cap + slot) * d;
+    T* y = K + ((size_t)unit * cap + slot) * d;
+    const float x1 = Tr<T>::to_f(x[j]), x2 = Tr<T>::to_f(x[j + half]);
+    const float c1 = Tr<T>::to_f(cos_t[(size_t)row * d + j]), c2 = Tr<T>::to_f(cos_t[(size_t)row * d + j + half]);
+    const float s1 = Tr<T>::to_f(sin_t[(size_t)row * d + j]), s2 = Tr<T>::to_f(sin_t[(size_t)row * d + j + half]);
+    const float a1 = Tr<T>::round_f(__fmul_rn(x1, c1)), b1 = Tr<T>::round_f(__fmul_rn(-x2, s1));
+    const float a2 = Tr<T>::round_f(__fmul_rn(x2, c2)), b2 = Tr<T>::round_f(__fmul_rn(x1, s2));
+    y[j] = Tr<T>::from_f(__fadd_rn(a1, b1));
+    y[j + half] = Tr<T>::from_f(__fadd_rn(a2, b2));
+  }
+}
+
+int launch_rope_cache(int dtype, const void* K_raw, void* K, const int32_t* lidx, const void* cos_t, const void* sin_t,
+                      int units, int cap, int n_phys, int d, cudaStream_t stream) {
+  const long long total = (long long)units * n_phys * (d / 2);
+  if (total <= 0) return EKV_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  switch (dtype) {
+    case EKV_F16:
+      rope_cache_kernel<__half><<<(int)blocks, 256, 0, stream>>>((const __half*)K_raw, (__half*)K, lidx, (const __half*)cos_t,
+                                                                (const __half*)sin_t, units, cap, n_phys, d); break;
+    case EKV_BF16:
+      rope_cache_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)K_raw, (__nv_bfloat16*)K, lidx,
+          (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, units, cap, n_phys, d); break;
+    case EKV_F32:
+      rope_cache_kernel<float><<<(int)blocks, 256, 0, stream>>>((const float*)K_raw, (float*)K, lidx, (const float*)cos_t,
+                                                               (const float*)sin_t, units, cap, n_phys, d); break;
+    default: return set_error(EKV_ERR_INVALID, "dtype %d", dtype);
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("rope_cache_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+}  // namespace ekv

@@ -38,6 +38,8 @@ int launch_evict_explicit(const KernelArgs& a, const int32_t* victims, int evict
 int launch_rope_qk(int dtype, const void* q_in, const void* k_in, const void* v_in, const void* cos_t, const void* sin_t,
                    const int32_t* positions, void* q_out, void* k_out, void* v_out, int B, int H, int Hkv, int QL, int d,
                    cudaStream_t stream);
+int launch_rope_cache(int dtype, const void* K_raw, void* K, const int32_t* lidx, const void* cos_t, const void* sin_t,
+                      int units, int cap, int n_phys, int d, cudaStream_t stream);
 int launch_export(const KernelArgs& a, void* K_out, void* V_out, float* S_out, float* SQ_out, float* C_out,
                   cudaStream_t stream);
 

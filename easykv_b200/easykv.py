@@ -57,6 +57,9 @@ class Session:
         self.q_len = 0
         self.max_position = 0
         self.two_tuple = False
+        self.streaming = False
+        self.rotary = getattr(getattr(model, "model", model), "rotary_emb", None)   # transformers 5.x: model-level RoPE module
+        self._table = None
         self.fwd = 0
         self.events = [] if record else None     # (forward index, int32 [L, B, Hkv, evict] victim ids)
         self._cur = None
@@ -66,6 +69,17 @@ class Session:
         self.max_position = max(self.max_position, pos0 + q_len - 1)
         self.fwd += 1
         self._cur = [] if (self.events is not None and step.evict) else None
+
+    def stream_table(self, module, x, rows):
+        """cos / sin `[rows, d]` for cache-relative positions 0..rows-1 (streaming variant)."""
+        if hasattr(module, "rotary_emb") and self.rotary is None:          # 4.36-style per-module table
+            return module.rotary_emb(x, seq_len=rows)
+        if self._table is None or self._table[0].shape[0] < rows:
+            want = max(rows, self.cache.cap + 1)
+            pos = torch.arange(want, device=x.device)[None]
+            cos, sin = self.rotary(x, pos)
+            self._table = (cos[0], sin[0])
+        return self._table
 
     def position_ids(self, device):
         return torch.arange(self.pos0, self.pos0 + self.q_len, device=device)[None]
@@ -95,8 +109,7 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
     recent_ratio = cfg.get("recent_ratio", 0.1)
     keep_attention = cfg.get("keep_attention", False)
     eos_token_ids = cfg.get("eos_token_ids", [self.tokenizer.eos_token_id])
-    if cfg.get("streaming", False):
-        raise NotImplementedError("streaming=True (llama_forward_stream) is not part of this path yet (SURVEY §8f row 3)")
+    streaming = bool(cfg.get("streaming", False))             # llama_forward_stream / mistral_forward_stream
     policy = P.canonical_policy(policy)
     if input_ids.dim() == 1:
         input_ids = input_ids[None]
@@ -120,6 +133,10 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
     cache = BudgetedKVCache(len(mods), bsz, H, Hkv, d, capacity, dtype=dtype, device=device, arith=arith)
     sess = Session(self, cache, record=cfg.get("record_evictions", True))
     self.easykv_last = sess                                   # eviction trace / cache of the last call
+    if streaming and plan.mode != "decoding":
+        # un-rotated keys in the cache, RoPE re-applied at cache-relative positions on every forward
+        cache.enable_streaming()
+        sess.streaming = True
 
     def forward(ids, pos0, step):
         if step.policy == "random" and step.evict:
@@ -161,6 +178,12 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
         # ---- prompt --------------------------------------------------------------------------------------
         n_dense = length if plan.mode in ("decoding", "dense") else plan.r_idx
         logits = dense_prefill(n_dense)
+        if streaming and plan.mode == "decoding":
+            # the reference prefills the prompt with the stock forward BEFORE patching (easykv.py:232 vs :253): the
+            # cache holds keys rotated at their true positions, which the streaming forward then treats as
+            # un-rotated and rotates again on every step — reproduced as is
+            cache.enable_streaming(adopt_rotated=True)
+            sess.streaming = True
         C0 = P.initial_counter(plan, keep_attention)
         if C0 is not None:                                     # strided modes keep state for the prompt
             for l in range(cache.L):

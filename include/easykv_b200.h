@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define EKV_ABI_VERSION 5
+#define EKV_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define EKV_API __attribute__((visibility("default")))
@@ -178,6 +178,16 @@ EKV_API int ekv_export_logical(const ekv_shape* shape, const ekv_layer_io* io, v
  * llama_patch.py:169-171. */
 EKV_API int ekv_rope_qk(const ekv_shape* shape, const void* q_in, const void* k_in, const void* v_in, const void* cos,
                 const void* sin, const int32_t* positions, void* q_out, void* k_out, void* v_out, void* stream);
+
+/* Streaming variant (generation_config['streaming'], llama_forward_stream / mistral_forward_stream,
+ * easykv/llama_patch.py:251-379, mistral_patch.py:189-286): the cache keeps UN-rotated keys and every forward
+ * rotates all of them at their cache-relative positions.  K_raw [B, Hkv, cap, d] holds the un-rotated rows in the
+ * physical layout of io->K; this call writes io->K[slot] = rope(K_raw[slot], position = io->lidx[slot]) for every
+ * valid slot in [0, n_phys) (cos / sin: [rows, d] tables, model dtype), after which ekv_attend_evict runs unchanged
+ * with q and the new k rotated at positions n_before .. n_before + q_len - 1 (ekv_rope_qk).  The caller stores the
+ * new tokens' un-rotated k rows into K_raw at the slots ekv_attend_evict appended them to. */
+EKV_API int ekv_rope_cache(const ekv_shape* shape, const ekv_layer_io* io, const void* K_raw, const void* cos, const void* sin,
+                   void* stream);
 
 /* Number of kernels launched by this library in the calling process since load (bench.py's
  * gpu_launches claim). */

@@ -63,6 +63,17 @@ CASES = {
     "llama_enc_random_fp32": dict(arch="llama", L=1, H=4, Hkv=2, d=128, seq=120, dtype="float32",
                                   mode="encoding", stride=8, max_new_tokens=2,
                                   gen=dict(budget=0.5, kv_policy="random")),
+    # streaming=True (llama_forward_stream / mistral_forward_stream): un-rotated keys in the cache, RoPE re-applied at
+    # cache-relative positions every forward; q / k in these traces are UN-rotated
+    "llama_auto_roco_stream_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=96, dtype="float32",
+                                        mode="auto", stride=8, max_new_tokens=12,
+                                        gen=dict(budget=40, kv_policy="roco", streaming=True)),
+    "llama_decoding_roco_stream_fp32": dict(arch="llama", L=1, H=4, Hkv=2, d=128, seq=32, dtype="float32",
+                                            mode="decoding", stride=1, max_new_tokens=64,
+                                            gen=dict(budget=36, kv_policy="roco", streaming=True)),
+    "gqa_mistral_enc_h2o_stream_fp16": dict(arch="mistral", L=1, H=8, Hkv=2, d=128, seq=132, dtype="float16",
+                                            mode="encoding", stride=4, max_new_tokens=3,
+                                            gen=dict(budget=0.5, kv_policy="h2o_head", streaming=True)),
     # keep_attention=True: state seeded from the dense prefill's attention map (h2o_head_score, easykv.py:173-186)
     "llama_enc_roco_keep_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=128, seq=200, dtype="float32",
                                      mode="encoding", stride=8, max_new_tokens=2,

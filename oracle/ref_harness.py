@@ -120,6 +120,16 @@ def _patched(model, trace: Trace, record_tensors=True):
             cur["q"] = qe
             return qe, ke
         mod.apply_rotary_pos_emb = rope_spy
+        # streaming variant: q and k are rotated by two separate calls (q first, llama_patch.py:326-327); the replay
+        # needs the UN-rotated q (the keys in the cache are un-rotated too)
+        save(mod, "apply_rotary_pos_emb_sep")
+        orig_sep = saved[(mod, "apply_rotary_pos_emb_sep")]
+
+        def sep_spy(x, cos, sin, position_ids, *a, _orig=orig_sep, **kw):
+            if "q" not in cur:
+                cur["q"] = x
+            return _orig(x, cos, sin, position_ids, *a, **kw)
+        mod.apply_rotary_pos_emb_sep = sep_spy
     save(scaffold.DynamicCache, "update")
     orig_update = scaffold.DynamicCache.update
 

@@ -50,8 +50,8 @@ class OracleEngine:
         if S_init is not None:                       # keep_attention seeding (h2o_head_score)
             self.layers[l].S, self.layers[l].SQ = S_init.clone().float(), SQ_init.clone().float()
 
-    def forward(self, l, st, q, k, v, force=None):
-        return self.layers[l].forward(st, q, k, v, self.scale_mul, force=force)
+    def forward(self, l, st, q, k, v, force=None, stream_table=None):
+        return self.layers[l].forward(st, q, k, v, self.scale_mul, force=force, stream_table=stream_table)
 
     def export(self, l):
         return self.layers[l].K, self.layers[l].V
@@ -86,6 +86,20 @@ def case_plan(meta):
     return plan, gen["kv_policy"], c["max_new_tokens"]
 
 
+def case_stream_table(meta):
+    """(cos, sin) [rows, d] in the case's dtype for generation_config['streaming'] runs, else None — the table the
+    scaffold's rotary module hands the reference (fp32 build, one cast)."""
+    c = meta["case"]
+    if not c["gen"].get("streaming", False):
+        return None
+    d, dtype = c["d"], getattr(torch, c["dtype"])
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    inv_freq = inv_freq.to(dtype).float()        # the scaffold's inv_freq buffer was cast with the model (`.to(dtype)`)
+    emb = torch.outer(torch.arange(4096, dtype=torch.float32), inv_freq)
+    emb = torch.cat((emb, emb), dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
 def case_keep_attention(meta):
     return bool(meta["case"]["gen"].get("keep_attention", False))
 
@@ -105,6 +119,8 @@ def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0) -> Repor
     rep = Report(name)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
     keep = case_keep_attention(meta)
+    table = case_stream_table(meta)
+    skw = {} if table is None else {"stream_table": table}
     C0 = restate.initial_counter(plan, keep)
     for l in range(L):
         K, V = T(z[f"prefill_K_{l}"]), T(z[f"prefill_V_{l}"])
@@ -141,13 +157,13 @@ def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0) -> Repor
             if policy == "random" and ev is not None:      # the range is the host's draw: replay the reference's
                 st.range_start = int(ev[1][0]) - st.score_offset
             force = ref_ids if resync else None
-            out, vic = eng.forward(l, st, q, k, v, force=force)
+            out, vic = eng.forward(l, st, q, k, v, force=force, **skw)
             o_ref = o.view(ql, H, d).transpose(0, 1).float()
             rep.max_out_err = max(rep.max_out_err, (out.float().cpu() - o_ref).abs().max().item())
             margin = None
             meng = sh if sh is not None else (eng if hasattr(eng, "margin") else None)
             if sh is not None:
-                sh.forward(l, st, q, k, v, force=ref_ids)
+                sh.forward(l, st, q, k, v, force=ref_ids, **skw)
             if meng is not None and st.evict:
                 margin = meng.margin(l)
                 rep.min_margin = (min(rep.min_margin[0], margin[0]), min(rep.min_margin[1], margin[1]))

@@ -107,6 +107,15 @@ def attend(q, K, V, scale_mul=False):
     return o[0], p[0]
 
 
+def rope(x, cos, sin, pos):
+    """apply_rotary_pos_emb_sep, easykv/llama_patch.py:74-98: x [heads, rows, d] at positions pos [rows], evaluated
+    in the model dtype."""
+    c, s_ = cos[pos][None], sin[pos][None]
+    h = x.shape[-1] // 2
+    rot = torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+    return (x * c) + (rot * s_)
+
+
 def fold_gqa(p, Hkv):
     """process_for_mqa_gqa, easykv/easykv.py:188-196: mean over the g query heads of a KV head,
     evaluated in the model dtype."""
@@ -256,10 +265,14 @@ class LayerOracle:
         self.S, self.SQ = torch.zeros(self.Hkv, n_s), torch.zeros(self.Hkv, n_s)
         self.C = torch.zeros(self.Hkv, n_s) if C_init is None else C_init.clone().float().expand(self.Hkv, n_s).clone()
 
-    def forward(self, st: Step, q, k_new, v_new, scale_mul=False, force=None):
+    def forward(self, st: Step, q, k_new, v_new, scale_mul=False, force=None, stream_table=None):
         """q [H,ql,d]; k_new, v_new [Hkv,ql,d].  Returns (out [H,ql,d], victims [Hkv,evict] or None).
         Victim ids index the cache after the append and before the deletion.
-        `force` ([Hkv,evict] cache-relative ids): delete these instead of the selected ones."""
+        `force` ([Hkv,evict] cache-relative ids): delete these instead of the selected ones.
+        `stream_table` = (cos, sin) [rows, d] in the model dtype: the streaming variant
+        (llama_forward_stream, easykv/llama_patch.py:251-379) — q and k_new arrive UN-rotated, the cache holds
+        un-rotated keys, and every forward rotates all keys at their cache-relative positions 0..n-1 and the
+        queries at n_before..n-1 (:310-327)."""
         ql = q.shape[1]
         self.K = torch.cat([self.K, k_new], dim=1)           # DynamicCache.update, llama_patch.py:195
         self.V = torch.cat([self.V, v_new], dim=1)
@@ -267,7 +280,13 @@ class LayerOracle:
         self.S = torch.cat([self.S, torch.zeros(self.Hkv, ql)], dim=1)
         self.SQ = torch.cat([self.SQ, torch.zeros(self.Hkv, ql)], dim=1)
         self.C = torch.cat([self.C, new_c.repeat(self.Hkv, 1)], dim=1)
-        out, p = attend(q, self.K, self.V, scale_mul)
+        if stream_table is not None:
+            n = self.K.shape[1]
+            cos, sin = stream_table
+            kpos = torch.arange(n)
+            out, p = attend(rope(q, cos, sin, kpos[n - ql:]), rope(self.K, cos, sin, kpos), self.V, scale_mul)
+        else:
+            out, p = attend(q, self.K, self.V, scale_mul)
         if st.accumulate and st.policy in ("roco", "h2o_head", "tova"):
             accumulate(st, self.S, self.SQ, fold_gqa(p, self.Hkv))
         if not st.evict:

@@ -22,10 +22,17 @@ class CudaEngine:
             self.cache.S[l][0, :, :n] = S_init.cuda().float()
             self.cache.SQ[l][0, :, :n] = SQ_init.cuda().float()
 
-    def forward(self, l, st, q, k, v, force=None):
+    def forward(self, l, st, q, k, v, force=None, stream_table=None):
         sp = StepParams.from_fields(st)
-        out, vl = self.cache.step(l, sp, q[None].cuda(), k[None].cuda(), v[None].cuda(),
-                                  apply=(force is None), kernel=self.kernel)
+        if stream_table is not None:                 # streaming golden: q / k are un-rotated (oracle/replay.py)
+            if self.cache.K_raw is None:
+                self.cache.enable_streaming(adopt_rotated=True)      # what load_prefill put into K is the raw cache
+            flat = lambda x: x.transpose(0, 1).reshape(1, x.shape[1], -1).cuda()       # [heads, ql, d] -> [1, ql, heads*d]
+            out, vl = self.cache.step_stream(l, sp, flat(q), flat(k), flat(v), stream_table[0].cuda(), stream_table[1].cuda(),
+                                             apply=(force is None), kernel=self.kernel)
+        else:
+            out, vl = self.cache.step(l, sp, q[None].cuda(), k[None].cuda(), v[None].cuda(),
+                                      apply=(force is None), kernel=self.kernel)
         if force is not None and st.evict:
             self.cache.evict(l, force[None])
         return out[0].cpu(), (None if vl is None else vl[0].cpu().long())

@@ -29,7 +29,33 @@ class OracleCache:
         self.L, self.Hkv = L, Hkv
         self.layers = [restate.LayerOracle(Hkv, d, dtype) for _ in range(L)]
         self.n = [0] * L
+        self.cap = capacity
+        self.K_raw = None
         self.scale_mul = bool(arith)
+
+    def enable_streaming(self, adopt_rotated=False):
+        self.K_raw = True                             # the layers' K simply IS the (un-rotated) cache from now on
+
+    def step_stream(self, l, sp, q_in, k_in, v_in, cos, sin, apply=True, kernel=0):
+        lo = self.layers[l]
+        b, ql = q_in.shape[:2]
+        q = q_in.view(b, ql, -1, lo.d).transpose(1, 2)[0]
+        k = k_in.view(b, ql, -1, lo.d).transpose(1, 2)[0]
+        v = v_in.view(b, ql, -1, lo.d).transpose(1, 2)[0]
+        table = (cos.to(lo.dtype), sin.to(lo.dtype))
+        if sp.policy == "full":
+            lo.K, lo.V = torch.cat([lo.K, k], 1), torch.cat([lo.V, v], 1)
+            n = lo.K.shape[1]
+            pos = torch.arange(n)
+            out, _ = restate.attend(restate.rope(q, *table, pos[n - ql:]), restate.rope(lo.K, *table, pos), lo.V, self.scale_mul)
+            ids = None
+        else:
+            st = restate.Step(**{f: getattr(sp, f) for f in restate.Step.__dataclass_fields__})
+            out, ids = lo.forward(st, q, k, v, self.scale_mul, stream_table=table)
+            if ids is not None:
+                ids = torch.sort(ids, dim=-1)[0][None].int()
+        self.n[l] = lo.K.shape[1]
+        return out[None], ids
 
     def set_counter(self, l, values):
         lo, n = self.layers[l], len(values)
