@@ -104,6 +104,47 @@ def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float
     torch.cuda.empty_cache()
 
 
+def run_stream_case(name, B, H, Hkv, n, L=4, steps=10, dtype=torch.float16):
+    """Decode step of the streaming variant (generation_config['streaming']): ekv_rope_cache (re-rotate the whole
+    cache at cache-relative positions) + ekv_rope_qk + ekv_attend_evict + the raw-row scatter, per layer.
+    Algorithmic bytes = the non-streaming step's + one extra read and one write of K."""
+    d, dev = 128, "cuda"
+    torch.manual_seed(0)
+    cache = BudgetedKVCache(L, B, H, Hkv, d, n + 1, dtype=dtype, arith=1)
+    cache.enable_streaming()
+    for l in range(L):
+        cache.load_prefill(l, torch.randn(B, Hkv, n, d, device=dev, dtype=dtype), torch.randn(B, Hkv, n, d, device=dev, dtype=dtype),
+                           n, [float(n - i) for i in range(n)])
+        steady_state(cache, l, n, dev)
+    recent = int(n * 0.3)
+    sp = StepParams(policy="roco", accumulate=True, evict=1, counter_add=1.0, k_feasible=n - recent)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, d, 2, device=dev).float() / d))
+    emb = torch.cat([torch.outer(torch.arange(n + 8, device=dev).float(), inv)] * 2, dim=-1)
+    cos, sin = emb.cos().to(dtype), emb.sin().to(dtype)
+    q = torch.randn(L, B, 1, H * d, device=dev, dtype=dtype) * 0.3
+    kn = torch.randn(L, B, 1, Hkv * d, device=dev, dtype=dtype)
+    vn = torch.randn(L, B, 1, Hkv * d, device=dev, dtype=dtype)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        for l in range(L):
+            cache.step_stream(l, sp, q[l], kn[l], vn[l], cos, sin)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        for l in range(L):
+            cache.step_stream(l, sp, q[l], kn[l], vn[l], cos, sin)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (steps * L)
+    ba = bytes_alg(B, H, Hkv, d, n + 1, 1, "roco", 1) + 2 * B * Hkv * n * d * 2
+    gbs = ba / us / 1e3
+    print(json.dumps(dict(case=name, B=B, H=H, Hkv=Hkv, n=n, q_len=1, policy="roco", dtype=str(dtype).split(".")[1], kernel=0, cluster=0,
+                          variant=0, streaming=True, us_per_launch=round(us, 1), bytes_alg=ba, GBps=round(gbs, 1),
+                          frac_of_measured=round(gbs / PEAK, 3))), flush=True)
+    del cache
+    torch.cuda.empty_cache()
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("decode", "all"):
@@ -120,6 +161,7 @@ def main():
         run_case("C3 generation: mistral n8208 b16, no policy", 16, 32, 8, 8208, 1, "full")
         run_case("C5 generation: 70B n8256 b8, no policy", 8, 64, 8, 8256, 1, "full")
         run_case("C2 literal: decoding, 4096 prompt + 200 generated, no eviction", 16, 32, 32, 4296, 1, "roco", literal_prompt=4096)
+        run_stream_case("7B b64 streaming variant (4 launches per layer-step)", 64, 32, 32, 1088)
         run_case("7B b32 general-kernel", 32, 32, 32, 1088, 1, "roco", kernel=1, steps=3)
     if what in ("cluster",):
         for B in (1, 2, 4, 8):
