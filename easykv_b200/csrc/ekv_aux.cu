@@ -281,19 +281,66 @@ __global__ void rope_cache_kernel(const T* __restrict__ K_raw, T* __restrict__ K
   }
 }
 
+// 16-bit dtypes: one thread per (slot, 8 dims of the lower half + the matching 8 of the upper half), 128-bit loads
+// and stores — the pass is pure streaming (read K_raw, write K) and the table rows come from L2.
+template <typename T>
+__global__ void rope_cache_vec_kernel(const T* __restrict__ K_raw, T* __restrict__ K, const int32_t* __restrict__ lidx,
+                                      const T* __restrict__ cos_t, const T* __restrict__ sin_t, int units, int cap, int n_phys) {
+  constexpr int D = 128, CH = D / 2 / 8;             // 8 chunks of 8 dims per half row
+  const long long total = (long long)units * n_phys * CH;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % CH);
+    const int slot = (int)((idx / CH) % n_phys);
+    const int unit = (int)(idx / ((long long)CH * n_phys));
+    const int row = lidx[(size_t)unit * cap + slot];
+    if (row < 0) continue;
+    const T* x = K_raw + ((size_t)unit * cap + slot) * D + c * 8;
+    T* y = K + ((size_t)unit * cap + slot) * D + c * 8;
+    const T* cr = cos_t + (size_t)row * D + c * 8;
+    const T* sr = sin_t + (size_t)row * D + c * 8;
+    const uint4 xl = *reinterpret_cast<const uint4*>(x), xh = *reinterpret_cast<const uint4*>(x + D / 2);
+    const uint4 cl = *reinterpret_cast<const uint4*>(cr), ch = *reinterpret_cast<const uint4*>(cr + D / 2);
+    const uint4 sl = *reinterpret_cast<const uint4*>(sr), sh = *reinterpret_cast<const uint4*>(sr + D / 2);
+    const T* xlp = reinterpret_cast<const T*>(&xl); const T* xhp = reinterpret_cast<const T*>(&xh);
+    const T* clp = reinterpret_cast<const T*>(&cl); const T* chp = reinterpret_cast<const T*>(&ch);
+    const T* slp = reinterpret_cast<const T*>(&sl); const T* shp = reinterpret_cast<const T*>(&sh);
+    uint4 ol, oh;
+    T* olp = reinterpret_cast<T*>(&ol); T* ohp = reinterpret_cast<T*>(&oh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x1 = Tr<T>::to_f(xlp[i]), x2 = Tr<T>::to_f(xhp[i]);
+      const float a1 = Tr<T>::round_f(__fmul_rn(x1, Tr<T>::to_f(clp[i]))), b1 = Tr<T>::round_f(__fmul_rn(-x2, Tr<T>::to_f(slp[i])));
+      const float a2 = Tr<T>::round_f(__fmul_rn(x2, Tr<T>::to_f(chp[i]))), b2 = Tr<T>::round_f(__fmul_rn(x1, Tr<T>::to_f(shp[i])));
+      olp[i] = Tr<T>::from_f(__fadd_rn(a1, b1));
+      ohp[i] = Tr<T>::from_f(__fadd_rn(a2, b2));
+    }
+    *reinterpret_cast<uint4*>(y) = ol;
+    *reinterpret_cast<uint4*>(y + D / 2) = oh;
+  }
+}
+
 int launch_rope_cache(int dtype, const void* K_raw, void* K, const int32_t* lidx, const void* cos_t, const void* sin_t,
                       int units, int cap, int n_phys, int d, cudaStream_t stream) {
   const long long total = (long long)units * n_phys * (d / 2);
   if (total <= 0) return EKV_OK;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
+  const bool vec = d == 128 && dtype != EKV_F32;
+  long long vblocks = ((long long)units * n_phys * 8 + 255) / 256;
+  if (vblocks > 148 * 32) vblocks = 148 * 32;
   switch (dtype) {
     case EKV_F16:
-      rope_cache_kernel<__half><<<(int)blocks, 256, 0, stream>>>((const __half*)K_raw, (__half*)K, lidx, (const __half*)cos_t,
-                                                                (const __half*)sin_t, units, cap, n_phys, d); break;
+      if (vec) rope_cache_vec_kernel<__half><<<(int)vblocks, 256, 0, stream>>>((const __half*)K_raw, (__half*)K, lidx, (const __half*)cos_t,
+                                                                              (const __half*)sin_t, units, cap, n_phys);
+      else rope_cache_kernel<__half><<<(int)blocks, 256, 0, stream>>>((const __half*)K_raw, (__half*)K, lidx, (const __half*)cos_t,
+                                                                     (const __half*)sin_t, units, cap, n_phys, d);
+      break;
     case EKV_BF16:
-      rope_cache_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)K_raw, (__nv_bfloat16*)K, lidx,
-          (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, units, cap, n_phys, d); break;
+      if (vec) rope_cache_vec_kernel<__nv_bfloat16><<<(int)vblocks, 256, 0, stream>>>((const __nv_bfloat16*)K_raw, (__nv_bfloat16*)K, lidx,
+          (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, units, cap, n_phys);
+      else rope_cache_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)K_raw, (__nv_bfloat16*)K, lidx,
+          (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, units, cap, n_phys, d);
+      break;
     case EKV_F32:
       rope_cache_kernel<float><<<(int)blocks, 256, 0, stream>>>((const float*)K_raw, (float*)K, lidx, (const float*)cos_t,
                                                                (const float*)sin_t, units, cap, n_phys, d); break;

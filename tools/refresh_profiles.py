@@ -1,0 +1,78 @@
+"""Copy one gpu_round.sh visit (gpurun_out/<tag>_*) into profiles/ under the round's names and regenerate the ncu
+summaries bench.py and the README refer to.      python tools/refresh_profiles.py <tag> [round, default r01]"""
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1]
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
+COPIES = {"bench.json": "bench_b64.json", "bench_b32.json": "bench_b32.json", "bench_ref.json": "bench_reference_arm.json",
+          "pytest.txt": "pytest_gpu.txt", "sweep_decode.jsonl": "sweep_decode.jsonl", "sweep_cluster.jsonl": "sweep_decode_cluster.jsonl",
+          "sweep_chunk.jsonl": "sweep_chunk_tensorcore.jsonl", "chunk_launches.csv": "chunk_launches.csv", "launches.csv": "launches.csv",
+          "e2e_llama7b.json": "e2e_generate_llama7b.json", "e2e_mistral7b.json": "e2e_generate_mistral7b_c3_literal.json"}
+for src, dst in COPIES.items():
+    s = os.path.join(G, f"{tag}_{src}")
+    if os.path.exists(s) and os.path.getsize(s):
+        shutil.copy(s, os.path.join(P, f"{rnd}_{dst}"))
+KEEP = ("Kernel Name", "Grid Size", "Block Size", "gpu__time_duration", "dram__bytes", "dram__throughput", "gpu__dram_throughput",
+        "dram__cycles_active", "sm__warps_active", "launch__", "sm__throughput", "lts__t_sector_hit_rate", "lts__t_bytes",
+        "smsp__issue_active", "sm__inst_executed_pipe", "l1tex__data_bank_conflicts", "smsp__cycles_active", "sm__cycles_elapsed",
+        "sm__pipe_tensor", "smsp__average_warp", "smsp__inst_executed.sum")
+
+
+def raw(rep, dst):
+    if not os.path.exists(rep):
+        return None
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(dst, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(rows) - 2)])
+        for h in hdr:
+            if any(k in h for k in KEEP):
+                w.writerow([h, units[idx[h]]] + [r[idx[h]] for r in rows[2:]])
+    return rows, idx, units
+
+
+r = raw(os.path.join(G, f"{tag}_decode.ncu-rep"), os.path.join(P, f"{rnd}_decode_ncu_raw.csv"))
+if r:
+    rows, idx, units = r
+    val = lambda row, h: float(row[idx[h]].replace(",", ""))
+    tb = lambda row, h: val(row, h) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[idx[h]]]
+    tr = [tb(x, "dram__bytes_read.sum") + tb(x, "dram__bytes_write.sum") for x in rows[2:]]
+    json.dump({"round": int(rnd[1:]), "kernel": "ekv::decode_kernel<__half,1,2>", "seqs_per_gpu": 64,
+               "dram_bytes_per_launch": sum(tr) / len(tr),
+               "dram_bytes_read": [tb(x, "dram__bytes_read.sum") for x in rows[2:]],
+               "dram_bytes_write": [tb(x, "dram__bytes_write.sum") for x in rows[2:]],
+               "gpu_time_us": [val(x, "gpu__time_duration.sum") for x in rows[2:]], "bytes_alg_per_launch": 1197531136,
+               "source": "ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 40 -c 3 python bench.py "
+                         "--steps 2 --warmup 3 --no-graph --no-cpu-baseline --layers 8 (gpurun, 1x B200, tools/gpu_round.sh)"},
+              open(os.path.join(P, f"traffic_{rnd}.json"), "w"), indent=1)
+    print("decode: traffic", sum(tr) / len(tr), "us", [val(x, "gpu__time_duration.sum") for x in rows[2:]])
+r = raw(os.path.join(G, f"{tag}_chunk_tc.ncu-rep"), os.path.join(P, f"{rnd}_chunk_tc_ncu_raw.csv"))
+if r:
+    rows, idx, units = r
+    for x in rows[2:]:
+        print(x[idx["Kernel Name"]][:70], x[idx["gpu__time_duration.sum"]], "us; hmma",
+              x[idx["sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"]], "% issue",
+              x[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]], "% regs", x[idx["launch__registers_per_thread"]])
+for f in ("bench_b64.json", "bench_b32.json", "bench_reference_arm.json"):
+    p = os.path.join(P, f"{rnd}_{f}")
+    if os.path.exists(p):
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        print(f, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "frac", (d.get("roofline") or {}).get("frac"),
+              d.get("clocks"), (d.get("cpu_baseline") or {}).get("value"))
+for f in ("sweep_decode.jsonl", "sweep_chunk_tensorcore.jsonl"):
+    p = os.path.join(P, f"{rnd}_{f}")
+    if os.path.exists(p):
+        for l in open(p):
+            if l.startswith("{"):
+                d = json.loads(l)
+                print(f"  {d['case'][:62]:62s} {d['us_per_launch']:9.1f} us {d['frac_of_measured']:.3f}")
