@@ -28,6 +28,31 @@ def test_abi_version_and_struct_layout(ekv_lib):
     assert ctypes.sizeof(_lib.LayerIO) == 14 * 8
 
 
+def test_ctypes_structs_mirror_the_header_field_for_field():
+    """Field names, order and C types of ekv_step / ekv_shape / ekv_layer_io in include/easykv_b200.h == the ctypes
+    mirrors in easykv_b200/_lib.py (an ABI drift would otherwise only show up as wrong results on the GPU)."""
+    from easykv_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "easykv_b200.h")).read()
+    ctype = {"int32_t": ctypes.c_int32, "float": ctypes.c_float}
+
+    def fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(\w+(?:\s*,\s*\w+)*)$", decl)      # `int32_t B, H, Hkv, d`
+            assert m, decl
+            for fname in re.split(r"\s*,\s*", m.group(4)):
+                out.append((fname, ctypes.c_void_p if m.group(3) else ctype[m.group(2)]))
+        return out
+
+    for cname, mirror in (("ekv_step", _lib.Step), ("ekv_shape", _lib.Shape), ("ekv_layer_io", _lib.LayerIO)):
+        assert fields(cname) == list(mirror._fields_), cname
+
+
 def test_argument_validation_without_gpu(ekv_lib):
     """Bad shapes are rejected before any CUDA call (reference: ValueError, llama_patch.py:204-228)."""
     from easykv_b200 import _lib
