@@ -30,12 +30,13 @@ def _cases():
         else:
             gen = dict(budget=round(rng.uniform(0.35, 0.7), 2), kv_policy=policy, keep_attention=rng.random() < 0.4)
             new = 0 if mode == "ppl" else 2
-        out.append(dict(arch=rng.choice(["llama", "mistral"]), L=1, H=H, Hkv=Hkv, d=128, seq=seq, dtype="float32", mode=mode,
+        dtype = "float16" if i % 3 == 2 else "float32"        # the 16-bit rounding points too
+        out.append(dict(arch=rng.choice(["llama", "mistral"]), L=1, H=H, Hkv=Hkv, d=128, seq=seq, dtype=dtype, mode=mode,
                         stride=stride, max_new_tokens=new, gen=gen))
     return out
 
 
-@pytest.mark.parametrize("case", _cases(), ids=lambda c: f"{c['mode']}-{c['gen']['kv_policy']}-s{c['stride']}-n{c['seq']}")
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: f"{c['mode']}-{c['gen']['kv_policy']}-s{c['stride']}-n{c['seq']}-{c['dtype']}")
 def test_restatement_matches_a_fresh_reference_run(case, tmp_path, monkeypatch):
     from oracle import gen_golden, replay
     monkeypatch.setattr(gen_golden, "OUT", str(tmp_path))
