@@ -97,6 +97,9 @@ CASES = {
     "gqa8_mistral_enc_h2o_fp16": dict(arch="mistral", L=1, H=8, Hkv=1, d=128, seq=144, dtype="float16",
                                       mode="encoding", stride=16, max_new_tokens=2,
                                       gen=dict(budget=0.5, kv_policy="h2o_head")),
+    "gqa_llama_enc_tova_fp16": dict(arch="llama", L=1, H=4, Hkv=2, d=128, seq=120, dtype="float16",
+                                    mode="encoding", stride=8, max_new_tokens=2,
+                                    gen=dict(budget=0.5, kv_policy="tova")),
     "llama_ppl_roco_bf16": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=136, dtype="bfloat16",
                                 mode="ppl", stride=8, max_new_tokens=0,
                                 gen=dict(budget=0.4, kv_policy="roco")),
