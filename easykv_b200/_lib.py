@@ -10,14 +10,14 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeasykv_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 F16, BF16, F32 = 0, 1, 2
 POLICY_NONE, POLICY_ROCO, POLICY_H2O, POLICY_TOVA, POLICY_RANGE = 0, 1, 2, 3, 4
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 
 EXPORTS = ("ekv_abi_version", "ekv_last_error", "ekv_scratch_bytes", "ekv_attend_evict", "ekv_select",
-           "ekv_evict_explicit", "ekv_export_logical", "ekv_launch_count", "ekv_debug_set_timeline", "ekv_debug_set_dispatch", "ekv_rope_qk", "ekv_rope_cache")
+           "ekv_evict_explicit", "ekv_export_logical", "ekv_launch_count", "ekv_debug_set_timeline", "ekv_debug_set_dispatch", "ekv_rope_qk", "ekv_rope_cache", "ekv_sample_top_p", "ekv_token_nll")
 
 
 class Step(C.Structure):
@@ -71,6 +71,11 @@ def load():
     lib.ekv_rope_qk.argtypes = [C.POINTER(Shape)] + [C.c_void_p] * 10
     lib.ekv_rope_cache.restype = C.c_int
     lib.ekv_rope_cache.argtypes = [C.POINTER(Shape), C.POINTER(LayerIO), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ekv_sample_top_p.restype = C.c_int
+    lib.ekv_sample_top_p.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ekv_token_nll.restype = C.c_int
+    lib.ekv_token_nll.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.ekv_debug_set_dispatch.restype = None
     lib.ekv_debug_set_dispatch.argtypes = [C.c_int32, C.c_int32]
     lib.ekv_debug_set_timeline.restype = None

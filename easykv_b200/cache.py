@@ -175,6 +175,18 @@ class BudgetedKVCache:
         self.K_raw[l].scatter_(2, slots[..., None].expand(B, self.Hkv, ql, self.d), k_raw)
         return out, vl
 
+    # ---- sampling / perplexity tail (easykv_b200/sampling.py) --------------------------------------
+    def sample(self, logits, temperature, top_p):
+        """Next token `[rows, 1]` int64 from `logits [rows, vocab]`: logits_adapter + torch.multinomial
+        (easykv/easykv.py:115-134, :258) as one launch, drawing from torch's CUDA generator exactly as multinomial does."""
+        from . import sampling
+        return sampling.sample_top_p(logits, temperature, top_p, arith=self.arith)[0]
+
+    def token_nll(self, logits, targets):
+        """Per-row cross entropy of one chunk's logits (easykv.py:896-899) — nothing `[prompt, vocab]`-sized is kept."""
+        from . import sampling
+        return sampling.token_nll(logits, targets)
+
     def round_state(self, l):
         """Round S / SQ to the model dtype once (what `torch.sum(attention_map, dim=1)` does for the whole dense
         map in h2o_head_score, easykv.py:183-184) after a dense prefill issued with `raw_colsum` chunks."""

@@ -215,4 +215,19 @@ int ekv_export_logical(const ekv_shape* sh, const ekv_layer_io* io, void* K_out,
   return launch_export(a, K_out, V_out, S_out, SQ_out, C_out, (cudaStream_t)stream);
 }
 
+int ekv_sample_top_p(const float* logits, int32_t rows, int32_t vocab, float temperature, float top_p, int32_t arith,
+                     const float* q_exp, float* prob, float* raw_prob, int64_t* token, void* stream) {
+  if (!logits || rows < 1 || vocab < 1) return set_error(EKV_ERR_INVALID, "logits / rows (%d) / vocab (%d)", rows, vocab);
+  if (!(temperature > 0.f) || !(top_p >= 0.f)) return set_error(EKV_ERR_INVALID, "need temperature > 0 and top_p >= 0 (%g, %g)", temperature, top_p);
+  if (!prob && !token) return set_error(EKV_ERR_INVALID, "no output requested");
+  if (token && !q_exp) return set_error(EKV_ERR_INVALID, "token draw needs q_exp (one Exp(1) variate per logit)");
+  return launch_logits_adapter(logits, rows, vocab, temperature, top_p, arith, q_exp, prob, raw_prob, (long long*)token,
+                               (cudaStream_t)stream);
+}
+
+int ekv_token_nll(const float* logits, const int64_t* targets, int32_t rows, int32_t vocab, float* nll, void* stream) {
+  if (!logits || !targets || !nll || rows < 1 || vocab < 1) return set_error(EKV_ERR_INVALID, "null pointer or empty shape");
+  return launch_token_nll(logits, (const long long*)targets, rows, vocab, nll, (cudaStream_t)stream);
+}
+
 }  // extern "C"

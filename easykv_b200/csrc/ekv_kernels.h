@@ -40,6 +40,9 @@ int launch_rope_qk(int dtype, const void* q_in, const void* k_in, const void* v_
                    cudaStream_t stream);
 int launch_rope_cache(int dtype, const void* K_raw, void* K, const int32_t* lidx, const void* cos_t, const void* sin_t,
                       int units, int cap, int n_phys, int d, cudaStream_t stream);
+int launch_logits_adapter(const float* logits, int rows, int V, float temperature, float top_p, int arith, const float* q_exp,
+                          float* prob, float* raw, long long* token, cudaStream_t stream);   // ekv_sample.cu
+int launch_token_nll(const float* logits, const long long* targets, int rows, int V, float* nll, cudaStream_t stream);
 int launch_export(const KernelArgs& a, void* K_out, void* V_out, float* S_out, float* SQ_out, float* C_out,
                   cudaStream_t stream);
 

@@ -15,7 +15,8 @@ sampled token.
 Mode loops mirrored (control flow only — sequencing and sampling are host glue):
   decoding           :228-366     encoding            :367-529
   encoding_decoding  :530-753     ppl                 :754-901     auto dispatch :220-227
-Sampling (`logits_adapter`, torch.multinomial; :115-134, :258) stays in PyTorch.
+Sampling (`logits_adapter` + torch.multinomial; :115-134, :258) and the perplexity loss (:896-899) are one launch each
+(easykv_b200/sampling.py).
 """
 from __future__ import annotations
 
@@ -33,17 +34,10 @@ from .cache import BudgetedKVCache
 
 
 def logits_adapter(logits: torch.Tensor, temperature: float, top_p: float):
-    """Temperature scaling and top-p renormalisation; returns (sampling distribution, raw softmax).
-    Same arithmetic as easykv/easykv.py:115-134."""
-    shape = logits.shape
-    logits = logits.reshape(-1, shape[-1])
-    prob = torch.softmax(logits / temperature, dim=-1)
-    sorted_prob, sorted_idx = torch.sort(prob, descending=True, dim=-1)
-    cumsum = torch.cumsum(sorted_prob, dim=-1)
-    sorted_prob[(cumsum - sorted_prob) > top_p] = 0.0
-    sorted_prob.div_(sorted_prob.sum(dim=-1, keepdim=True))
-    final = torch.gather(sorted_prob, -1, torch.argsort(sorted_idx, dim=-1))
-    return final.reshape(shape), torch.softmax(logits, dim=-1).reshape(shape)
+    """Temperature scaling and top-p renormalisation; returns (sampling distribution, raw softmax) — the contract of
+    easykv/easykv.py:115-134, computed by one `ekv_sample_top_p` launch (easykv_b200/sampling.py; CUDA tensors only)."""
+    from . import sampling
+    return sampling.logits_adapter(logits, temperature, top_p)
 
 
 class Session:
@@ -162,19 +156,25 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
                 cache.round_state(l)
         return logits
 
-    def sample(prob):
-        return torch.multinomial(prob, num_samples=1)          # easykv.py:258
+    def sample(last_logits):
+        # logits_adapter + torch.multinomial (easykv.py:115-134, :258): one launch, same generator draw, no host sync
+        return cache.sample(last_logits, temperature, top_p)
 
     with patched_attention(self, sess):
         sched = list(P.schedule(plan, policy, max_new_tokens, keep_attention))
         chunks = [s for s in sched if s[0] == "chunk"]
         decodes = [s for s in sched if s[0] == "decode"]
-        all_logits, all_ids = [], []
+        all_nll = []
+
+        def next_ids(t0, q_len):
+            """Targets of rows t0 .. t0+q_len-1: the following token; the prompt's last row has none (dropped, :899)."""
+            t = input_ids[0, t0 + 1:t0 + q_len + 1]
+            return t if t.numel() == q_len else torch.cat([t, t.new_zeros(q_len - t.numel())])
+
         if ppl_mode and plan.mode == "dense":                 # easykv.py:759-765
-            logits = torch.cat([forward(input_ids[:, t0:t0 + DENSE_CHUNK], t0, P.StepParams())
-                                for t0 in range(0, length, DENSE_CHUNK)], dim=1).float()
-            lp = torch.nn.functional.cross_entropy(logits[0, :-1], input_ids[0, 1:], reduction="none")
-            return math.exp(statistics.mean(lp.cpu().numpy().tolist()))
+            lp = [cache.token_nll(forward(input_ids[:, t0:t0 + DENSE_CHUNK], t0, P.StepParams())[0].float(),
+                                  next_ids(t0, min(DENSE_CHUNK, length - t0))) for t0 in range(0, length, DENSE_CHUNK)]
+            return math.exp(statistics.mean(torch.cat(lp)[:-1].cpu().numpy().tolist()))
         # ---- prompt --------------------------------------------------------------------------------------
         n_dense = length if plan.mode in ("decoding", "dense") else plan.r_idx
         logits = dense_prefill(n_dense)
@@ -191,35 +191,31 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
         cur = n_dense
         for _, q_len, st in chunks:                            # easykv.py:426-500 / :587-661 / :816-892
             logits = forward(input_ids[:, cur:cur + q_len], cur, st)
-            if ppl_mode:
-                all_logits.append(logits[0].float())
-                all_ids.append(input_ids[0, cur:cur + q_len])
+            if ppl_mode:                                       # easykv.py:826-827: this chunk's rows of the final loss
+                all_nll.append(cache.token_nll(logits[0].float(), next_ids(cur, q_len)))
             cur += q_len
         retained = cache.n[0]
         if plan.mode in ("encoding", "ppl"):
             print(f"KV cache budget ratio: {retained / length * 100:.2f}%({retained}/{length})")
         if ppl_mode:                                           # easykv.py:896-901
-            ids, lg = torch.cat(all_ids), torch.cat(all_logits, dim=0)
-            lp = torch.nn.functional.cross_entropy(lg[:-1], ids[1:], reduction="none")
-            return math.exp(statistics.mean(lp.cpu().numpy().tolist()))
+            return math.exp(statistics.mean(torch.cat(all_nll)[:-1].cpu().numpy().tolist()))
         # ---- generation ------------------------------------------------------------------------------------
         if cfg.get("record_timing", False):                    # for benchmarks: when the prompt phase was complete
             torch.cuda.synchronize(device)
             sess.t_prompt_done = time.perf_counter()
-        prob, _ = logits_adapter(logits[:, -1, :].float(), temperature, top_p)
+        last = logits[:, -1, :]
         output_ids, times = [], []
         cur_pos = length
         if plan.mode == "encoding_decoding" and policy == "random" and decodes:
             # the reference itself fails here (UnboundLocalError: positions_tensor, easykv.py:744)
             raise NotImplementedError("kv_policy='random' has no decode phase in encoding_decoding / auto mode")
         for _, _, st in decodes:                               # easykv.py:257-363 / :508-526 / :670-748
-            nxt = sample(prob)
+            nxt = sample(last)
             output_ids.append(nxt[:, 0].tolist())
             if bsz == 1 and output_ids[-1][0] in eos_token_ids:
                 break
             t0 = time.time()
-            logits = forward(nxt, cur_pos, st)
-            prob, _ = logits_adapter(logits[:, -1, :].float(), temperature, top_p)
+            last = forward(nxt, cur_pos, st)[:, -1, :]
             if report_decoding_latency:
                 torch.cuda.synchronize(device)
                 times.append(time.time() - t0)

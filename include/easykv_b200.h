@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define EKV_ABI_VERSION 6
+#define EKV_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define EKV_API __attribute__((visibility("default")))
@@ -188,6 +188,23 @@ EKV_API int ekv_rope_qk(const ekv_shape* shape, const void* q_in, const void* k_
  * new tokens' un-rotated k rows into K_raw at the slots ekv_attend_evict appended them to. */
 EKV_API int ekv_rope_cache(const ekv_shape* shape, const ekv_layer_io* io, const void* K_raw, const void* cos, const void* sin,
                    void* stream);
+
+/* Sampling tail (replaces logits_adapter, easykv/easykv.py:115-134, and the torch.multinomial call at :258 / :509 /
+ * :671): for each of `rows` rows of fp32 logits [rows, vocab] compute softmax(logits / temperature), keep in
+ * descending order every token whose exclusive cumulative mass is <= top_p, renormalise -> prob [rows, vocab]
+ * (nullable when only the token is wanted and vocab * 4 <= 200 KB).  raw_prob (nullable) receives softmax(logits).
+ * With q_exp [rows, vocab] (one Exp(1) variate per logit — `torch.empty_like(prob).exponential_(1)` is exactly the draw
+ * torch.multinomial makes) token[row] = argmax(prob / q_exp), first index on ties: the token torch.multinomial(prob, 1)
+ * returns from the same generator state, without its two host syncs.  arith as in ekv_step.arith (how logits /
+ * temperature is formed: 1 = multiply by the fp32 reciprocal, ATen's CUDA flavour; 0 = true division).
+ * One launch, no scratch; floating point: agrees with the ATen composition to fp32 rounding (summation order). */
+EKV_API int ekv_sample_top_p(const float* logits, int32_t rows, int32_t vocab, float temperature, float top_p, int32_t arith,
+                     const float* q_exp, float* prob, float* raw_prob, int64_t* token, void* stream);
+
+/* Perplexity tail (replaces CrossEntropyLoss(reduction='none') over the concatenated chunk logits, easykv/easykv.py:
+ * 826-827, 896-899): nll[row] = -(log_softmax(logits[row])[targets[row]]), fp32 logits [rows, vocab], int64 targets
+ * (NaN for a target outside [0, vocab)).  Called once per prompt chunk, so no [prompt, vocab] tensor is ever kept. */
+EKV_API int ekv_token_nll(const float* logits, const int64_t* targets, int32_t rows, int32_t vocab, float* nll, void* stream);
 
 /* Number of kernels launched by this library in the calling process since load (bench.py's
  * gpu_launches claim). */

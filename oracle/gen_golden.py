@@ -147,9 +147,38 @@ def run_case(name, c):
     return tr
 
 
+SAMPLING_CASES = [  # (vocab, rows, temperature, top_p, logit scale)
+    (1000, 3, 0.7, 0.9, 3.0), (4096, 2, 1.0, 0.95, 2.0), (512, 2, 1e-9, 1.0, 3.0), (2000, 2, 0.3, 0.5, 1.0),
+    (777, 2, 1.3, 0.0, 2.0), (3000, 2, 1.0, 1.0, 4.0), (32000, 1, 0.8, 0.9, 2.5)]
+
+
+def sampling_tail():
+    """The reference's own `logits_adapter` (easykv/easykv.py:115-134) and the loss it feeds the perplexity with
+    (:782, :896-899) on seeded logits -> tests/golden/sampling_tail.npz."""
+    ref_main, _, _ = ref_harness.import_reference()
+    g = torch.Generator().manual_seed(RNG_SEED)
+    arrs, meta = {}, []
+    for i, (V, R, T, tp, sc) in enumerate(SAMPLING_CASES):
+        x = torch.randn(R, V, generator=g) * sc
+        x[:, 5] = x[:, 9]                                  # an exact tie in every row
+        x[0, V // 2:V // 2 + 8] = x[0].max()               # a run of equal maxima the nucleus boundary can cut
+        final, raw = ref_main.logits_adapter(x.clone(), T, tp)
+        t = torch.randint(0, V, (R,), generator=g)
+        nll = torch.nn.CrossEntropyLoss(reduction="none")(x, t)
+        arrs[f"c{i}_logits"], arrs[f"c{i}_final"], arrs[f"c{i}_raw"] = x.numpy(), final.numpy(), raw.numpy()
+        arrs[f"c{i}_targets"], arrs[f"c{i}_nll"] = t.numpy(), nll.numpy()
+        meta.append(dict(vocab=V, rows=R, temperature=T, top_p=tp))
+    arrs["meta"] = np.frombuffer(json.dumps(dict(cases=meta, torch=torch.__version__,
+                                                 reference_commit="a1d71cae3b562d9a709dda3741bd63e46a09ad31")).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "sampling_tail.npz"), **arrs)
+    print(f"sampling_tail: {len(meta)} cases, {os.path.getsize(os.path.join(OUT, 'sampling_tail.npz')) / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
+    if not only or "sampling_tail" in only:
+        sampling_tail()
     for name, c in CASES.items():
         if only and name not in only:
             continue

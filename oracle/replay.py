@@ -29,7 +29,16 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 
 
 def list_golden():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Recorded reference runs (sampling_tail.npz holds function-level vectors, not a run: `load_sampling_tail`)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "sampling_tail.npz")
+
+
+def load_sampling_tail():
+    """Cases of tests/golden/sampling_tail.npz (oracle/gen_golden.py: the reference's logits_adapter / loss outputs)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "sampling_tail.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    return [dict(m, **{k: torch.from_numpy(z[f"c{i}_{k}"]) for k in ("logits", "final", "raw", "targets", "nll")})
+            for i, m in enumerate(meta["cases"])]
 
 
 def load_golden(name):

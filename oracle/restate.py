@@ -367,3 +367,49 @@ def initial_counter(plan: Plan, keep_attention=False):
     if keep_attention:                                                       # :413-414
         return (plan.idx - torch.arange(n0, dtype=torch.float32))
     return torch.zeros(n0)                                                   # :416
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sampling / perplexity tail
+# ---------------------------------------------------------------------------------------------------------------
+def logits_adapter(logits, temperature, top_p, scale_mul=False):
+    """easykv/easykv.py:115-134 restated without the two sorts' round trip: softmax(logits / temperature), then in
+    descending order (stable, i.e. index ascending among equals) keep every token whose EXCLUSIVE cumulative mass is
+    <= top_p (:125-127), zero the rest and renormalise by the kept mass (:128).  Returns (final, raw softmax) like
+    the reference.  `scale_mul`: ATen's CUDA kernels divide by a host scalar as a multiply by the fp32 reciprocal."""
+    shape = logits.shape
+    x = logits.reshape(-1, shape[-1])
+    if scale_mul:      # ATen BinaryDivTrueKernel.cu: opmath_t(1.0) / scalar_value<opmath_t>() — both already fp32
+        scaled = x * (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(temperature, dtype=torch.float32)).to(x.dtype)
+    else:
+        scaled = x / temperature
+    prob = torch.softmax(scaled, dim=-1)
+    order = torch.sort(prob, dim=-1, descending=True, stable=True).indices
+    sp = torch.gather(prob, -1, order)
+    excl = torch.cumsum(sp, dim=-1) - sp
+    keep_sorted = ~(excl > top_p)
+    keep = torch.zeros_like(keep_sorted).scatter_(-1, order, keep_sorted)
+    kept = torch.where(keep, prob, torch.zeros_like(prob))
+    # the reference sums the sorted, masked vector (:128); same values, same order as `sp` with the tail zeroed
+    z = torch.where(keep_sorted, sp, torch.zeros_like(sp)).sum(dim=-1, keepdim=True)
+    return (kept / z).reshape(shape), torch.softmax(x, dim=-1).reshape(shape)
+
+
+def top_p_margin(logits, temperature, top_p):
+    """Smallest |exclusive cumulative mass - top_p| over a row's tokens: when it is within fp32 summation noise the
+    kept set is decided by rounding and two correct implementations may differ by the boundary token."""
+    x = logits.reshape(-1, logits.shape[-1])
+    sp = torch.sort(torch.softmax(x / temperature, dim=-1), dim=-1, descending=True).values
+    return ((torch.cumsum(sp, -1) - sp) - top_p).abs().min(dim=-1).values
+
+
+def draw_from_exponentials(prob, q_exp):
+    """torch.multinomial(prob, 1) (easykv.py:258, :509, :671) as ATen computes it for one draw: argmax(prob / q) with
+    q ~ Exp(1) drawn per element (ATen/native/Sampling: the 'gumbel' fast path), first index on ties."""
+    return torch.argmax(prob / q_exp, dim=-1, keepdim=True)
+
+
+def token_nll(logits, targets):
+    """CrossEntropyLoss(reduction='none')(all_logits[:-1], all_ids[1:]) (easykv.py:896-899), one row per target."""
+    lse = torch.logsumexp(logits.float(), dim=-1)
+    return lse - logits.float().gather(-1, targets.view(-1, 1).long())[:, 0]

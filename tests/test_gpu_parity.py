@@ -197,6 +197,38 @@ def test_chunk_random_vs_oracle(engines, dtype, H, Hkv, stride, policy, n0, kern
     assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
 
 
+def test_keep_attention_seeding_tensorcore_vs_general(ekv_lib):
+    """keep_attention seeding (h2o_head_score, easykv.py:173-186): a dense causal prefill issued as chunks with
+    `raw_colsum` accumulates the attention map's column sums in fp32 and rounds once at the end — the tensor-core
+    chunk path and the exact CUDA-core kernel must agree (up to one fp16 ulp of summation order), and both must
+    equal the column sums of the materialised map."""
+    from easykv_b200.cache import BudgetedKVCache
+    from easykv_b200.plan import StepParams
+    B, H, Hkv, n, d, dev = 1, 8, 2, 192, 128, "cuda"
+    torch.manual_seed(12)
+    q = torch.randn(B, H, n, d, device=dev).half() * 0.3
+    k = torch.randn(B, Hkv, n, d, device=dev).half(); v = torch.randn(B, Hkv, n, d, device=dev).half()
+    sp = StepParams(policy="roco", accumulate=True, raw_colsum=True)
+    res = []
+    for kernel in (0, 1):
+        c = BudgetedKVCache(1, B, H, Hkv, d, n, dtype=torch.float16)
+        for t in range(0, n, 64):
+            c.step(0, sp, q[:, :, t:t + 64], k[:, :, t:t + 64], v[:, :, t:t + 64], kernel=kernel)
+        c.round_state(0)
+        res.append((c.S[0][0, :, :n].clone(), c.SQ[0][0, :, :n].clone()))
+    g = H // Hkv
+    w = (q.float() @ k.float().repeat_interleave(g, 1).transpose(2, 3)) / math.sqrt(d)
+    w = torch.softmax(w + torch.full((n, n), float("-inf"), device=dev).triu(1), -1).half()        # [1, H, n, n]
+    fold = w.view(B, Hkv, g, n, n).float().mean(2).half()                                           # easykv.py:188-196
+    S_ref = fold.float().sum(2).half().float()[0]                                                    # :183
+    SQ_ref = (fold ** 2).float().sum(2).half().float()[0]                                            # :184
+    for (S, SQ) in res:
+        assert (S - S_ref).abs().max().item() <= 5e-3 * S_ref.abs().max().item()
+        assert (SQ - SQ_ref).abs().max().item() <= 5e-3 * SQ_ref.abs().max().item() + 1e-6
+    assert (res[0][0] - res[1][0]).abs().max().item() <= 1e-3 * S_ref.abs().max().item()
+    assert (res[0][1] - res[1][1]).abs().max().item() <= 1e-3 * SQ_ref.abs().max().item() + 1e-7
+
+
 def test_chunk_full_size_tensorcore_vs_general(ekv_lib):
     """BASELINE configs[2] geometry (Mistral: H=32, Hkv=8, stride 16, 8208 retained, h2o_head) and the 7B
     stride-64 chunk: the tensor-core path against the exact CUDA-core kernel on the same state — same victims

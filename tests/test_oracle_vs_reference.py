@@ -3,7 +3,9 @@ tests/golden/ was recorded from the UNMODIFIED reference (oracle/gen_golden.py);
 the restatement must reproduce every eviction id, every attention output and the final cache."""
 import pytest
 
-from oracle import replay
+import torch
+
+from oracle import replay, restate
 
 CASES = replay.list_golden()
 
@@ -33,3 +35,26 @@ def test_restatement_reproduces_reference(name):
 def test_c1_retained_ratio_line():
     meta, _ = replay.load_golden("c1_llama_enc_roco_fp32")
     assert "53.12%(136/256)" in meta["printed"]          # what the reference prints for C1
+
+
+def test_sampling_tail_restatement_matches_reference_vectors():
+    """oracle/restate.py's logits_adapter / token_nll against the outputs of the reference's own `logits_adapter`
+    (easykv/easykv.py:115-134) and loss (:782) frozen in tests/golden/sampling_tail.npz: bit-identical on the CPU."""
+    cases = replay.load_sampling_tail()
+    assert len(cases) >= 7
+    for c in cases:
+        final, raw = restate.logits_adapter(c["logits"].clone(), c["temperature"], c["top_p"])
+        # equal keys: torch.sort(descending=True) leaves their order unspecified (like topk, SURVEY A.5), so WHICH members
+        # of a run of equal probabilities the nucleus boundary keeps is implementation-defined; the restatement defines it
+        # as index order.  Everything else — the kept count, every value — is bit-identical.
+        assert torch.equal(final.sort(-1).values, c["final"].sort(-1).values), c["vocab"]
+        prob = torch.softmax(c["logits"] / c["temperature"], -1)
+        for r in range(final.shape[0]):
+            differ = final[r] != c["final"][r]
+            assert prob[r][differ].unique().numel() <= 1
+        assert torch.equal(raw, c["raw"])
+        assert torch.allclose(restate.token_nll(c["logits"], c["targets"]), c["nll"], rtol=1e-6, atol=1e-6)
+        # the multinomial restatement: argmax(prob / Exp(1)) only ever returns a kept token
+        q = torch.empty_like(final).exponential_(1, generator=torch.Generator().manual_seed(3))
+        tok = restate.draw_from_exponentials(final, q)
+        assert bool((final.gather(-1, tok) > 0).all())
