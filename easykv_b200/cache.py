@@ -39,6 +39,7 @@ class BudgetedKVCache:
         capacity = (int(capacity) + 7) // 8 * 8      # 16-byte aligned per-head rows of the int32/fp32 arrays
         self.L, self.B, self.H, self.Hkv, self.d, self.cap = num_layers, batch, num_heads, num_kv_heads, head_dim, capacity
         self.dtype, self.device, self.arith = dtype, dev, arith
+        self._steady = None                              # (free-slot views, victim-id views) once enable_steady() ran
         kv = dict(dtype=dtype, device=dev)
         st = dict(dtype=torch.float32, device=dev)
         self.K = [torch.zeros(batch, num_kv_heads, capacity, head_dim, **kv) for _ in range(num_layers)]
@@ -208,7 +209,11 @@ class BudgetedKVCache:
         out = torch.empty_like(q)
         evict = int(sp.evict)
         vs = vl = None
-        if evict:
+        if evict and self._steady is not None and new_slots is self._steady[0][l] and evict == 1 and apply:
+            # steady decode (enable_steady): this step's victim slot overwrites the slot id it appended at, in place, so
+            # every pointer of the launch is the same from step to step and the step can be replayed from a CUDA graph
+            vs, vl = new_slots, self._steady[1][l]
+        elif evict:
             vv = torch.empty(2, self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
             vs, vl = vv[0], vv[1]
         # the C structs are cached (per layer / per StepParams object) and only the fields that change are
@@ -240,6 +245,24 @@ class BudgetedKVCache:
             self.n[l] -= evict
             self.free[l] = vs
         return out, vl
+
+    def enable_steady(self):
+        """Pin the per-layer free-slot / victim buffers for the steady state of decoding (append one, evict one, per
+        step — easykv.py:257-363 once the budget is reached, :670-748): needs exactly one free slot per (sequence, kv
+        head) in every layer.  From here on `step()` launches with identical pointers and shapes every step, which is
+        what lets `easykv.generate` capture the whole model step into one CUDA graph.  Returns the `[L, B, Hkv, 1]`
+        buffer that holds each step's victim ids."""
+        if any(self.free_count(l) != 1 for l in range(self.L)):
+            raise RuntimeError("enable_steady needs exactly one free slot per (sequence, kv head) in every layer")
+        slots = torch.empty(self.L, self.B, self.Hkv, 1, dtype=torch.int32, device=self.device)
+        victims = torch.empty_like(slots)
+        views = ([slots[l] for l in range(self.L)], [victims[l] for l in range(self.L)])
+        for l in range(self.L):
+            views[0][l].copy_(self.free[l])
+            self.free[l] = views[0][l]
+        self._steady = views
+        self.steady_victims = victims
+        return victims
 
     def evict(self, l, victims):
         """Delete logical ids `victims` `[B, Hkv, e]` (what truncate_kv_cache_* did)."""

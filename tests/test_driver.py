@@ -280,3 +280,36 @@ def test_driver_binds_to_installed_transformers(ekv_lib):
         temperature=1e-9, max_new_tokens=40, budget=16, kv_policy="roco"))
     assert model.easykv_last.cache.n[0] == 70 + 16
     assert len(model.easykv_last.events) == 40 - 16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,mode,policy,bsz", [("float32", "decoding", "roco", 1), ("float16", "auto", "roco", 2),
+                                                   ("float16", "decoding", "tova", 1), ("bfloat16", "auto", "recency", 1)])
+def test_graph_captured_decode_step_equals_eager(ekv_lib, dtype, mode, policy, bsz):
+    """Steady-state decode steps replayed from one CUDA graph of the whole model step (GraphedDecodeStep) must generate
+    the same tokens and evict the same slots as the eager loop, on the installed transformers Llama classes."""
+    transformers = pytest.importorskip("transformers")
+    cfg = transformers.LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=2, head_dim=128, vocab_size=512, max_position_embeddings=1024,
+                                   attn_implementation="eager")
+    torch.manual_seed(0)
+    model = transformers.LlamaForCausalLM(cfg).to(getattr(torch, dtype)).cuda().eval()
+    ids = torch.randint(3, 512, (bsz, 70), generator=torch.Generator().manual_seed(1)).cuda()
+    easykv_b200.enable_fixed_kv(model, scaffold.StubTokenizer(), mode=mode, stride=8)
+    budget = 16 if mode == "decoding" else 40
+    runs = []
+    for graph in (False, True):
+        torch.manual_seed(7)
+        text = model.easykv_generate(input_ids=ids, generation_config=dict(
+            temperature=0.8, top_p=0.9, max_new_tokens=90, budget=budget, kv_policy=policy, cuda_graph=graph, cuda_graph_min_steps=8))
+        sess = model.easykv_last
+        runs.append((text, [(f, e.clone()) for f, e in sess.events], sess.cache.n[0], sess.graphed_steps, sess.graph_error,
+                     [sess.cache.export(l)[0].clone() for l in range(2)]))
+    (t0, ev0, n0, g0, _, k0), (t1, ev1, n1, g1, err1, k1) = runs
+    assert g0 == 0 and err1 is None and g1 >= 40, (g1, err1)
+    assert t1 == t0
+    assert n1 == n0 and len(ev1) == len(ev0)
+    for (f0, e0), (f1, e1) in zip(ev0, ev1):
+        assert f0 == f1 and torch.equal(e0, e1)
+    for a, b in zip(k0, k1):
+        assert torch.equal(a, b)                        # the retained keys, in logical order

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--keep-attention", action="store_true")
     ap.add_argument("--stride", type=int, default=64)
     ap.add_argument("--policy", default="roco")
+    ap.add_argument("--no-graph", action="store_true", help="eager decode loop (no CUDA-graph replay of the steady decode step)")
     args = ap.parse_args()
     import transformers
     if args.arch == "llama":
@@ -63,7 +64,8 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         easykv_b200.enable_fixed_kv(model, Tok(), mode=args.mode, stride=args.stride)
     budget = args.budget if args.budget < 1 else int(args.budget)
-    gen = dict(temperature=1e-9, top_p=1.0, budget=budget, kv_policy=args.policy, keep_attention=args.keep_attention)
+    gen = dict(temperature=1e-9, top_p=1.0, budget=budget, kv_policy=args.policy, keep_attention=args.keep_attention,
+               cuda_graph=not args.no_graph)
     out = {}
     with contextlib.redirect_stdout(io.StringIO()):           # untimed warm-up (cuBLAS handles, kernel attributes)
         model.easykv_generate(input_ids=ids[:, :max(2 * args.stride, 256)], generation_config=dict(gen, budget=budget if budget < 1 else min(budget, 64), max_new_tokens=2))
@@ -77,11 +79,17 @@ def main():
     sess = model.easykv_last
     out = {"prefill_only": sess.t_prompt_done - t0, "printed": buf.getvalue().strip()}
     dec = t1 - sess.t_prompt_done
-    print(json.dumps(dict(arch=args.arch, layers=args.layers, prompt=args.prompt, new_tokens=args.new, budget=budget, mode=args.mode,
+    tt = sess.token_times
+    gaps = sorted((b - a) * 1e3 for a, b in zip(tt[:-1], tt[1:]))
+    pct = lambda f: round(gaps[min(len(gaps) - 1, int(f * len(gaps)))], 3) if gaps else None   # noqa: E731
+    first = [round((b - a) * 1e3, 2) for a, b in zip(tt[:6], tt[1:7])]
+    print(json.dumps(dict(arch=args.arch, token_gap_ms=dict(p10=pct(0.1), p50=pct(0.5), p90=pct(0.9), max=pct(1.0), first=first), layers=args.layers, prompt=args.prompt, new_tokens=args.new, budget=budget, mode=args.mode,
                           keep_attention=args.keep_attention, stride=args.stride, policy=args.policy, prefill_s=round(out["prefill_only"], 3),
                           decode_tokens_per_s=round(args.new / dec, 2), decode_ms_per_token=round(dec / args.new * 1e3, 2),
                           retained=sess.cache.n[0], eviction_events=len(sess.events), printed=out["printed"],
-                          launches=int(sess.cache.lib.ekv_launch_count()))))
+                          launches=int(sess.cache.lib.ekv_launch_count()), graphed_steps=sess.graphed_steps, graph_capture_s=round(sess.graph_capture_s, 3),
+                          steady_ms_per_token=round((dec - sess.graph_capture_s) / args.new * 1e3, 2),
+                          graph_error=sess.graph_error)))
 
 
 if __name__ == "__main__":
