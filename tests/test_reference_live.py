@@ -58,3 +58,33 @@ def test_restatement_matches_a_fresh_reference_run(case, tmp_path, monkeypatch):
     assert rep.final_cache_equal
     assert rep.max_out_err == 0.0
     assert rep.n_events == len(tr.events)
+
+
+def test_sampling_tail_restatement_matches_the_reference_live():
+    """oracle/restate.py's logits_adapter against the reference's own function (easykv/easykv.py:115-134) on fresh
+    random logits: identical kept counts and values; which members of a run of equal probabilities survive is the
+    reference's unstable sort's choice (see test_oracle_vs_reference.py)."""
+    from oracle import restate
+    from oracle.ref_harness import import_reference
+    ref_main, _, _ = import_reference()
+    rng = random.Random(7)
+    for trial in range(12):
+        V = rng.choice([64, 333, 1000, 4096, 32000])
+        R = rng.randint(1, 4)
+        T = rng.choice([1e-9, 0.3, 0.7, 1.0, 1.6])
+        top_p = rng.choice([0.0, 0.3, 0.5, 0.9, 0.95, 1.0])
+        x = torch.randn(R, V, generator=torch.Generator().manual_seed(trial)) * rng.choice([1.0, 3.0, 6.0])
+        if trial % 3 == 0:
+            x[:, 1] = x[:, 2] = x[:, 3]
+        ref, ref_raw = ref_main.logits_adapter(x.clone(), T, top_p)
+        got, raw = restate.logits_adapter(x.clone(), T, top_p)
+        assert torch.equal(raw, ref_raw)
+        assert torch.equal(got.sort(-1).values, ref.sort(-1).values), (V, T, top_p)
+        prob = torch.softmax(x / T, -1)
+        for r in range(R):
+            assert prob[r][got[r] != ref[r]].unique().numel() <= 1
+    # and the 3-D call shape of the perplexity path (:119-123, :133)
+    x = torch.randn(2, 5, 100, generator=torch.Generator().manual_seed(1))
+    ref, _ = ref_main.logits_adapter(x.clone(), 0.9, 0.8)
+    got, _ = restate.logits_adapter(x.clone(), 0.9, 0.8)
+    assert got.shape == ref.shape and torch.equal(got, ref)
