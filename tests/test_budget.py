@@ -111,3 +111,27 @@ def test_plan_and_schedule_match_oracle_property():
             _same_step(xa, xb)
         checked += 1
     assert checked > 150
+
+
+@pytest.mark.parametrize("mode,length,budget,stride,policy", [
+    ("decoding", 70, 16, 1, "roco"), ("decoding", 70, 16, 1, "tova"), ("decoding", 70, 16, 1, "recency"),
+    ("decoding", 70, 16, 1, "h2o_head"), ("auto", 70, 40, 8, "roco"), ("auto", 70, 40, 8, "recency"),
+    ("auto", 4096, 1024, 64, "roco"), ("auto", 70, 200, 8, "roco")])
+def test_decode_schedule_reaches_a_steady_state(mode, length, budget, stride, policy):
+    """What `easykv.GraphedDecodeStep` relies on: once eviction has started, every remaining decode step carries the SAME
+    parameters (easykv.py:303-362: `C += 1`, one victim per step, constant `k`; :708-748) — so the step's launches are
+    identical from token to token and can be replayed from a CUDA graph.  In `decoding` mode that state begins when the
+    generated tokens exceed the budget (:303); in `encoding_decoding` it holds from the first decode step."""
+    new = 200
+    plan = P.resolve_plan(mode, length, budget, stride)
+    decodes = [s for s in P.schedule(plan, policy, new) if s[0] == "decode"]
+    assert len(decodes) == new
+    tail = decodes[-1][2]
+    assert tail.evict == 1
+    first_steady = next(i for i, s in enumerate(decodes) if s[2] == tail)
+    assert all(s[2] == tail for s in decodes[first_steady:])
+    assert all(s[2].evict == 0 for s in decodes[:first_steady])
+    if plan.mode == "decoding":
+        assert first_steady == int(plan.budget)
+    else:
+        assert first_steady == 0
