@@ -33,10 +33,28 @@ def _cases():
         dtype = "float16" if i % 3 == 2 else "float32"        # the 16-bit rounding points too
         out.append(dict(arch=rng.choice(["llama", "mistral"]), L=1, H=H, Hkv=Hkv, d=128, seq=seq, dtype=dtype, mode=mode,
                         stride=stride, max_new_tokens=new, gen=gen))
+    # the streaming variant (llama_forward_stream / mistral_forward_stream): un-rotated cache, cache-relative RoPE
+    for i in range(4):
+        mode = ["auto", "encoding", "decoding", "auto"][i]
+        stride = rng.choice([2, 4, 8])
+        H, Hkv = rng.choice([(2, 2), (4, 2), (4, 1)])
+        seq = rng.randint(40, 90)
+        policy = rng.choice(["roco", "tova"] + (["h2o_head"] if mode != "auto" else []))
+        if mode == "decoding":
+            gen = dict(budget=rng.randint(20, 30), kv_policy=policy, streaming=True)
+            new, stride = rng.randint(40, 50), 1
+        elif mode == "auto":
+            gen = dict(budget=rng.randint(16, seq - 8), kv_policy=policy, streaming=True)
+            new = rng.randint(4, 10)
+        else:
+            gen = dict(budget=round(rng.uniform(0.35, 0.7), 2), kv_policy=policy, streaming=True)
+            new = 2
+        out.append(dict(arch=["llama", "mistral"][i % 2], L=1, H=H, Hkv=Hkv, d=128, seq=seq, dtype="float32", mode=mode,
+                        stride=stride, max_new_tokens=new, gen=gen))
     return out
 
 
-@pytest.mark.parametrize("case", _cases(), ids=lambda c: f"{c['mode']}-{c['gen']['kv_policy']}-s{c['stride']}-n{c['seq']}-{c['dtype']}")
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: f"{c['mode']}-{c['gen']['kv_policy']}-s{c['stride']}-n{c['seq']}-{c['dtype']}" + ("-stream" if c['gen'].get('streaming') else ""))
 def test_restatement_matches_a_fresh_reference_run(case, tmp_path, monkeypatch):
     from oracle import gen_golden, replay
     monkeypatch.setattr(gen_golden, "OUT", str(tmp_path))
