@@ -195,18 +195,24 @@ def test_sampling_tail_has_no_cpu_path():
         drv.logits_adapter(torch.randn(2, 50), 0.7, 0.9)
 
 
-def test_seam_binds_to_installed_transformers_cpu(monkeypatch):
-    """The attention seam on the installed transformers (5.x) Llama classes — `position_embeddings`, 2-tuple return,
-    keyword-only decoder-layer call — with the stand-in cache: without a policy, greedy generation through
-    `easykv_generate` must equal the model's own eager generation."""
+@pytest.mark.parametrize("arch", ["llama", "mistral", "mistral_sliding"])
+def test_seam_binds_to_installed_transformers_cpu(monkeypatch, arch):
+    """The attention seam on the installed transformers (5.x) Llama / Mistral classes — `position_embeddings`, 2-tuple
+    return, keyword-only decoder-layer call, the already-4D mask that skips their causal-mask construction — with the
+    stand-in cache: without a policy, greedy generation through `easykv_generate` must equal the model's own eager
+    generation."""
     transformers = pytest.importorskip("transformers")
     monkeypatch.setattr(drv, "BudgetedKVCache", OracleCache)
     monkeypatch.setattr(torch, "multinomial", lambda p, num_samples=1, **kw: p.argmax(dim=-1, keepdim=True))
-    cfg = transformers.LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
-                                   num_key_value_heads=2, head_dim=64, vocab_size=300, max_position_embeddings=512,
-                                   attn_implementation="eager")
+    kw = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+              head_dim=64, vocab_size=300, max_position_embeddings=512, attn_implementation="eager")
+    if arch == "llama":
+        cfg, cls = transformers.LlamaConfig(**kw), transformers.LlamaForCausalLM
+    else:       # a window longer than the sequence: same attention, but the sliding-window mask constructor is the one bypassed
+        cfg = transformers.MistralConfig(sliding_window=None if arch == "mistral" else 256, **kw)
+        cls = transformers.MistralForCausalLM
     torch.manual_seed(0)
-    model = transformers.LlamaForCausalLM(cfg).eval()
+    model = cls(cfg).eval()
     ids = torch.randint(3, 300, (1, 40), generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         ref = model.generate(ids, max_new_tokens=8, do_sample=False, pad_token_id=0)[0, 40:].tolist()
@@ -216,6 +222,7 @@ def test_seam_binds_to_installed_transformers_cpu(monkeypatch):
             temperature=1e-9, max_new_tokens=8, budget=512, kv_policy="full", aten_arith="cpu"))
     assert [int(t) for t in text.split()] == ref
     assert "forward" not in model.model.layers[0].self_attn.__dict__
+    assert model.easykv_last.model_kwargs["attention_mask"].dim() == 4
 
 
 # ---------------------------------------------------------------------------------------------------------
