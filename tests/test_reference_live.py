@@ -30,7 +30,7 @@ def _cases():
         else:
             gen = dict(budget=round(rng.uniform(0.35, 0.7), 2), kv_policy=policy, keep_attention=rng.random() < 0.4)
             new = 0 if mode == "ppl" else 2
-        dtype = "float16" if i % 3 == 2 else "float32"        # the 16-bit rounding points too
+        dtype = "float16" if i % 3 == 2 else ("bfloat16" if i % 5 == 4 else "float32")   # the 16-bit rounding points too
         out.append(dict(arch=rng.choice(["llama", "mistral"]), L=1, H=H, Hkv=Hkv, d=128, seq=seq, dtype=dtype, mode=mode,
                         stride=stride, max_new_tokens=new, gen=gen))
     # the streaming variant (llama_forward_stream / mistral_forward_stream): un-rotated cache, cache-relative RoPE
