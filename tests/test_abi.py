@@ -91,3 +91,19 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("test oracle", ""), f
+
+
+def test_integration_doc_quotes_the_current_abi():
+    """INTEGRATION.md's stub and function count follow the header (they went stale once)."""
+    import re
+    from easykv_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    hdr = open(os.path.join(root, "include", "easykv_b200.h")).read()
+    assert int(re.search(r"ekv_abi_version\(\) == (\d+)", doc).group(1)) == _lib.ABI_VERSION
+    assert int(re.search(r"#define EKV_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION
+    words = ["zero", "one", "two", "three", "four", "five", "six", "seven", "eight", "nine", "ten", "eleven", "twelve",
+             "thirteen", "fourteen", "fifteen", "sixteen", "seventeen", "eighteen", "nineteen", "twenty"]
+    n_api = len(re.findall(r"^EKV_API ", hdr, flags=re.M))
+    assert n_api == len(_lib.EXPORTS)
+    assert f"{words[n_api]} functions" in doc
