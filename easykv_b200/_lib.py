@@ -17,7 +17,7 @@ POLICY_NONE, POLICY_ROCO, POLICY_H2O, POLICY_TOVA, POLICY_RANGE = 0, 1, 2, 3, 4
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 
 EXPORTS = ("ekv_abi_version", "ekv_last_error", "ekv_scratch_bytes", "ekv_attend_evict", "ekv_select",
-           "ekv_evict_explicit", "ekv_export_logical", "ekv_launch_count", "ekv_debug_set_timeline", "ekv_debug_set_dispatch", "ekv_rope_qk", "ekv_rope_cache", "ekv_sample_top_p", "ekv_token_nll")
+           "ekv_evict_explicit", "ekv_export_logical", "ekv_launch_count", "ekv_debug_set_timeline", "ekv_debug_set_dispatch", "ekv_rope_qk", "ekv_rope_cache", "ekv_sample_top_p", "ekv_token_nll", "ekv_debug_umma_probe", "ekv_debug_set_chunk_variant")
 
 
 class Step(C.Structure):
@@ -76,6 +76,10 @@ def load():
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ekv_token_nll.restype = C.c_int
     lib.ekv_token_nll.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.ekv_debug_umma_probe.restype = C.c_int
+    lib.ekv_debug_umma_probe.argtypes = [C.c_int32] + [C.c_void_p] * 7
+    lib.ekv_debug_set_chunk_variant.restype = None
+    lib.ekv_debug_set_chunk_variant.argtypes = [C.c_int32]
     lib.ekv_debug_set_dispatch.restype = None
     lib.ekv_debug_set_dispatch.argtypes = [C.c_int32, C.c_int32]
     lib.ekv_debug_set_timeline.restype = None

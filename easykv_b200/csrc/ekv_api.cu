@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "ekv_kernels.h"
+#include "ekv_chunk_plan.h"
 
 namespace ekv {
 
@@ -30,6 +31,8 @@ unsigned long long* debug_timeline() { return g_timeline.load(std::memory_order_
 // kernel-selection overrides (development / test hook): environment at load, ekv_debug_set_dispatch later
 static std::atomic<int> g_variant{[] { const char* e = getenv("EKV_DECODE_VARIANT"); return e ? atoi(e) : 0; }()};
 static std::atomic<int> g_cluster{[] { const char* e = getenv("EKV_DECODE_CLUSTER"); return e ? atoi(e) : 0; }()};
+static std::atomic<int> g_chunk{[] { const char* e = getenv("EKV_CHUNK_VARIANT"); return e ? atoi(e) : 0; }()};
+int chunk_variant() { return g_chunk.load(std::memory_order_relaxed); }   // 0 = automatic, 1 = tcgen05 path, 2 = mma.sync two-pass path
 int decode_variant() { return g_variant.load(std::memory_order_relaxed); }
 int decode_cluster_size() { return g_cluster.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -93,6 +96,7 @@ void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size) {
   g_variant.store(decode_variant, std::memory_order_relaxed);
   g_cluster.store(cluster_size, std::memory_order_relaxed);
 }
+void ekv_debug_set_chunk_variant(int32_t chunk_variant) { g_chunk.store(chunk_variant, std::memory_order_relaxed); }
 void ekv_debug_set_timeline(void* device_buffer) { g_timeline.store((unsigned long long*)device_buffer, std::memory_order_relaxed); }
 
 static bool chunk_tc_shape(const ekv_shape* sh) {
@@ -100,8 +104,14 @@ static bool chunk_tc_shape(const ekv_shape* sh) {
   return sh->q_len > 1 && sh->d == 128 && (sh->dtype == EKV_F16 || sh->dtype == EKV_BF16) &&
          (G == 1 || G == 2 || G == 4 || G == 8);
 }
+// scratch of the 16-bit chunk paths: the larger of the tcgen05 cluster path's and the two-pass mma.sync path's plans
 static int64_t tc_bytes(const ekv_shape* sh) {
-  return chunk_tc_shape(sh) ? (int64_t)chunk_tc_scratch_bytes(sh->B, sh->Hkv, sh->H / sh->Hkv, sh->q_len, sh->n_phys) : 0;
+  if (!chunk_tc_shape(sh)) return 0;
+  const int G = sh->H / sh->Hkv;
+  int64_t b = (int64_t)chunk_tc_scratch_bytes(sh->B, sh->Hkv, G, sh->q_len, sh->n_phys);
+  ChunkPlan up;
+  if (make_umma_plan(sh->B, sh->Hkv, G, sh->q_len, sh->n_phys, umma_sm_count(), up) && up.bytes > b) b = up.bytes;
+  return b;
 }
 
 int64_t ekv_scratch_bytes(const ekv_shape* sh, const ekv_step* st) {
@@ -116,7 +126,11 @@ int64_t ekv_scratch_bytes(const ekv_shape* sh, const ekv_step* st) {
 // else, or kernel == 1 -> the exact-arithmetic general kernel
 static int launch_chunk_auto(const KernelArgs& a, const ekv_shape* sh, int32_t kernel, cudaStream_t s) {
   if (kernel == 0 && chunk_tc_shape(sh) && a.scratch) {
-    const int rc = launch_chunk_tc(a, s);
+    // 16-bit chunks: the tcgen05 / TMEM / tensor-map-TMA cluster kernel; the two-pass mma.sync kernels serve what
+    // it declines (more than 8 x 10 key tiles per unit) and chunk_variant 2 (development / A-B comparisons)
+    int rc = chunk_variant() == 2 ? EKV_ERR_UNSUPPORTED : launch_chunk_umma(a, s);
+    if (rc != EKV_ERR_UNSUPPORTED) return rc;
+    rc = launch_chunk_tc(a, s);
     if (rc != EKV_ERR_UNSUPPORTED) return rc;
   }
   return launch_general(a, s);
@@ -223,6 +237,12 @@ int ekv_sample_top_p(const float* logits, int32_t rows, int32_t vocab, float tem
   if (token && !q_exp) return set_error(EKV_ERR_INVALID, "token draw needs q_exp (one Exp(1) variate per logit)");
   return launch_logits_adapter(logits, rows, vocab, temperature, top_p, arith, q_exp, prob, raw_prob, (long long*)token,
                                (cudaStream_t)stream);
+}
+
+int ekv_debug_umma_probe(int32_t dtype, const void* K, const void* V, const void* Q, const void* Pt, float* St, float* Ot,
+                         void* stream) {
+  if (!K || !V || !Q || !Pt || !St || !Ot) return set_error(EKV_ERR_INVALID, "null tensor pointer");
+  return launch_umma_probe(dtype, K, V, Q, Pt, St, Ot, (cudaStream_t)stream);
 }
 
 int ekv_token_nll(const float* logits, const int64_t* targets, int32_t rows, int32_t vocab, float* nll, void* stream) {

@@ -26,6 +26,7 @@
 #include "ekv_mma.cuh"
 #include "ekv_select.cuh"
 #include "ekv_kernels.h"
+#include "ekv_chunk_plan.h"
 
 namespace ekv {
 
@@ -42,15 +43,9 @@ constexpr int TARGET_CTAS_PASS1 = 444;  // three lighter CTAs per SM in pass 1
 constexpr int TARGET_CTAS = 296;      // two CTAs per SM: their dependency stalls overlap
 }  // namespace tc
 
-struct ChunkPlan {
-  int R, RB, Rpad, NE, NEpad, ntiles, splits, tps;      // tps = tiles per split (pass 2)
-  int splits1, tps1;                                    // pass 1 (lighter CTAs, three per SM): a finer split
-  long long off_stats, off_opart, off_cpart, off_klj, off_ka, off_kb, off_kf, bytes;
-};
-
 ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
   using namespace tc;
-  ChunkPlan p;
+  ChunkPlan p = {};
   p.R = q_len * G;
   p.RB = (p.R + MR - 1) / MR;
   p.Rpad = p.RB * MR;
@@ -489,13 +484,15 @@ template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a
 constexpr int TAIL_NT = 1024;
 struct TailSmem {
   int off_ns, off_lj, off_pool, total;
-  __host__ __device__ TailSmem(int NE, int q_len, int evict) {
+  // evicting == false: the tail only appends the rows and publishes the new slots' logical indices — no per-entry
+  // select scratch, hence no ceiling on the cache length (dense prefill / policy 'full' / 'decoding' prompts)
+  __host__ __device__ TailSmem(int NE, int q_len, int evict, bool evicting) {
     int o = 0;
     off_ns = o; o += (q_len * 4 + 15) / 16 * 16;
-    off_lj = o; o += (NE * 4 + 15) / 16 * 16;
+    off_lj = o; o += evicting ? (NE * 4 + 15) / 16 * 16 : 0;
     o = (o + 127) / 128 * 128;
     off_pool = o;
-    total = o + (int)SelScratch::bytes(NE, evict);
+    total = o + (evicting ? (int)SelScratch::bytes(NE, evict) : 0);
   }
 };
 
@@ -503,7 +500,8 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
   using namespace tc;
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_phys = a.n_phys, QL = a.q_len, NE = pl.NE;
-  const TailSmem L(NE, QL, a.st.evict);
+  const bool evicting = a.st.evict > 0 && a.st.policy != EKV_POLICY_NONE;
+  const TailSmem L(NE, QL, a.st.evict, evicting);
   int32_t* ns = reinterpret_cast<int32_t*>(smem + L.off_ns);
   int32_t* lj = reinterpret_cast<int32_t*>(smem + L.off_lj);
   const int unit = blockIdx.x, tid = threadIdx.x;
@@ -522,6 +520,11 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
       Vw[(size_t)ns[i] * CPR + c] = vn[(size_t)i * CPR + c];
     }
   }
+  if (!evicting) {                                                // the state was written by the chip-wide update
+    int32_t* lidx = a.lidx + (size_t)unit * a.cap;
+    for (int i = tid; i < QL; i += TAIL_NT) lidx[ns[i]] = a.n_before + i;
+    return;
+  }
   SelScratch sc;
   sc.lj = lj;
   sc.carve(smem + L.off_pool, NE, a.st.evict);
@@ -535,8 +538,7 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
   u.new_slots = ns;
   u.victim_slots = a.victim_slots ? a.victim_slots + (size_t)unit * a.st.evict : nullptr;
   u.victim_lidx = a.victim_lidx ? a.victim_lidx + (size_t)unit * a.st.evict : nullptr;
-  const bool evicting = a.st.evict > 0 && a.st.policy != EKV_POLICY_NONE;
-  if (evicting) {                                                 // the keys the chip-wide state update left in scratch
+  {                                                               // the keys the chip-wide state update left in scratch
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(a.scratch);
     const int32_t* klj = reinterpret_cast<const int32_t*>(sb + pl.off_klj) + (size_t)unit * pl.NEpad;
     const uint32_t* ka = reinterpret_cast<const uint32_t*>(sb + pl.off_ka) + (size_t)unit * pl.NEpad;
@@ -550,37 +552,38 @@ template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kern
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------------------------------------
-template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, cudaStream_t stream) {
+static bool tail_evicting(const KernelArgs& a) { return a.st.evict > 0 && a.st.policy != EKV_POLICY_NONE; }
+
+template <typename T, int G> static int configure_chunk_tc() {
   using namespace tc;
-  const ChunkPlan pl = make_chunk_plan(a.B, a.Hkv, G, a.q_len, a.n_phys);
-  const TailSmem TL(pl.NE, a.q_len, a.st.evict);
-  if (TL.total > 227 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "chunk tail: %d bytes of shared memory needed", TL.total);
-  const int smem1 = MR * PITCH + STAGES * TILE_BYTES + STAGES * TK * 4;
-  const int smem2 = MR * PITCH + 2 * 2 * TILE_BYTES + 2 * TK * 4 + MR * (TK + 2) * 2;
   static thread_local int configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 16) dev = 15;
+  if (configured[dev]) return EKV_OK;
+  const int smem1 = MR * PITCH + STAGES * TILE_BYTES + STAGES * TK * 4;
+  const int smem2 = MR * PITCH + 2 * 2 * TILE_BYTES + 2 * TK * 4 + MR * (TK + 2) * 2;
+  cudaError_t err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(chunk_tc)", err);
+  configured[dev] = 1;
+  return EKV_OK;
+}
+
+// 3 + 4: partial outputs -> out, chip-wide policy-state update, per-unit tail.  Shared by the tcgen05 path.
+template <typename T, int G> static int launch_finish_tg(const KernelArgs& a, const ChunkPlan& pl, cudaStream_t stream) {
+  using namespace tc;
+  const TailSmem TL(pl.NE, a.q_len, a.st.evict, tail_evicting(a));
+  if (TL.total > 227 * 1024)
+    return set_error(EKV_ERR_UNSUPPORTED, "chunk tail: selecting victims among %d entries needs %d bytes of shared memory (limit 227 KB, "
+                     "about 17.6K retained slots); larger caches are served only without eviction", pl.NE, TL.total);
+  int rc = configure_chunk_tc<T, G>();
+  if (rc) return rc;
   cudaError_t err;
-  if (!configured[dev]) {
-    err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tc_kernel<T, G, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(chunk_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(chunk_tc)", err);
-    configured[dev] = 1;
-  }
   const int U = a.B * a.Hkv;
-  const int grid = U * pl.RB * pl.splits, grid1 = U * pl.RB * pl.splits1;
-  if (a.st.arith) chunk_tc_kernel<T, G, 1, true><<<grid1, NT, smem1, stream>>>(a, pl);
-  else chunk_tc_kernel<T, G, 1, false><<<grid1, NT, smem1, stream>>>(a, pl);
-  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<1> launch", err);
-  count_launch();
-  if (a.st.arith) chunk_tc_kernel<T, G, 2, true><<<grid, NT, smem2, stream>>>(a, pl);
-  else chunk_tc_kernel<T, G, 2, false><<<grid, NT, smem2, stream>>>(a, pl);
-  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<2> launch", err);
-  count_launch();
   const int out_blocks = (U * pl.R * (D / 4) + 255) / 256;
   const int col_blocks = (U * pl.NEpad + 255) / 256;               // state update: always (new slots need their state)
   chunk_out_kernel<T, G><<<out_blocks + col_blocks, 256, 0, stream>>>(a, pl, out_blocks);
@@ -592,12 +595,52 @@ template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, 
   return EKV_OK;
 }
 
+template <typename T, int G> static int launch_chunk_tc_tg(const KernelArgs& a, cudaStream_t stream) {
+  using namespace tc;
+  const ChunkPlan pl = make_chunk_plan(a.B, a.Hkv, G, a.q_len, a.n_phys);
+  const TailSmem TL(pl.NE, a.q_len, a.st.evict, tail_evicting(a));
+  if (TL.total > 227 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "chunk tail: %d bytes of shared memory needed", TL.total);
+  const int smem1 = MR * PITCH + STAGES * TILE_BYTES + STAGES * TK * 4;
+  const int smem2 = MR * PITCH + 2 * 2 * TILE_BYTES + 2 * TK * 4 + MR * (TK + 2) * 2;
+  int rc = configure_chunk_tc<T, G>();
+  if (rc) return rc;
+  cudaError_t err;
+  const int U = a.B * a.Hkv;
+  const int grid = U * pl.RB * pl.splits, grid1 = U * pl.RB * pl.splits1;
+  if (a.st.arith) chunk_tc_kernel<T, G, 1, true><<<grid1, NT, smem1, stream>>>(a, pl);
+  else chunk_tc_kernel<T, G, 1, false><<<grid1, NT, smem1, stream>>>(a, pl);
+  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<1> launch", err);
+  count_launch();
+  if (a.st.arith) chunk_tc_kernel<T, G, 2, true><<<grid, NT, smem2, stream>>>(a, pl);
+  else chunk_tc_kernel<T, G, 2, false><<<grid, NT, smem2, stream>>>(a, pl);
+  if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tc_kernel<2> launch", err);
+  count_launch();
+  return launch_finish_tg<T, G>(a, pl, stream);
+}
+
 template <typename T> static int launch_chunk_tc_t(const KernelArgs& a, cudaStream_t stream) {
   switch (a.H / a.Hkv) {
     case 1: return launch_chunk_tc_tg<T, 1>(a, stream);
     case 2: return launch_chunk_tc_tg<T, 2>(a, stream);
     case 4: return launch_chunk_tc_tg<T, 4>(a, stream);
     case 8: return launch_chunk_tc_tg<T, 8>(a, stream);
+    default: return EKV_ERR_UNSUPPORTED;
+  }
+}
+template <typename T> static int launch_finish_t(const KernelArgs& a, const ChunkPlan& pl, cudaStream_t stream) {
+  switch (a.H / a.Hkv) {
+    case 1: return launch_finish_tg<T, 1>(a, pl, stream);
+    case 2: return launch_finish_tg<T, 2>(a, pl, stream);
+    case 4: return launch_finish_tg<T, 4>(a, pl, stream);
+    case 8: return launch_finish_tg<T, 8>(a, pl, stream);
+    default: return EKV_ERR_UNSUPPORTED;
+  }
+}
+
+int launch_chunk_finish(const KernelArgs& a, const ChunkPlan& pl, cudaStream_t stream) {
+  switch (a.dtype) {
+    case EKV_F16: return launch_finish_t<__half>(a, pl, stream);
+    case EKV_BF16: return launch_finish_t<__nv_bfloat16>(a, pl, stream);
     default: return EKV_ERR_UNSUPPORTED;
   }
 }

@@ -1,0 +1,559 @@
+// Strided-prefill chunk (q_len = stride query rows per head) on the Blackwell tensor cores: tcgen05.mma with the
+// accumulators in tensor memory, K / V tiles by tensor-map TMA (cp.async.bulk.tensor, 128-byte swizzle) through an
+// mbarrier ring, warp-specialised (TMA producer / MMA issuer / 8 softmax warps), one thread-block CLUSTER per
+// (sequence, kv head, block of 64 (query, head) rows) so that every K and V byte is read from HBM exactly once and
+// the [H, q, n] probability tensor of the reference (easykv/llama_patch.py:244-246) never exists anywhere.
+//
+// Orientation.  Both contractions are issued TRANSPOSED so that a tensor-memory lane is a KEY:
+//     S^T [128 keys x 64 rows] = K_tile [128 x 128] . Q^T            A = K tile (K-major, from TMA), B = Q (K-major)
+//     O^T [128 dims x 64 rows] += V_tile^T [128 x 128 keys] . P^T     A = V tile (MN-major, from TMA), B = P^T (MN-major)
+// A softmax thread (tcgen05.ld 32x32b: one lane = one key) therefore owns one key and sees that key's logit for every
+// row of the block in its registers: the per-key column statistics the eviction policies need (GQA fold over the g
+// heads, sum over the chunk's queries of p and p^2 — easykv/easykv.py:188-196, :443-457) are thread-local, and so is
+// the write of a key's P^T row (one 128-byte swizzled row of the B operand).  Row statistics (max, sum) go across
+// lanes once per CTA, not per tile.
+//
+// Exact two-phase softmax (the reference rounds p = dtype(exp(x - max) / sum) AFTER normalising with the global
+// row statistics, so an online rescaling softmax cannot reproduce it bit for bit):
+//   K phase   the CTA's slice of the keys (<= 10 tiles): S^T by tcgen05.mma into a double-buffered TMEM accumulator,
+//             logits rounded at the reference's rounding points (llama_patch.py:201-202), masked, packed to the model
+//             dtype and PARKED IN TENSOR MEMORY (the 320 columns the accumulators leave free hold 10 tiles), row
+//             maxima kept as packed 16-bit maxima in registers;
+//   exchange  per-row slice maxima all-to-all over distributed shared memory (st.shared::cluster + remote mbarrier
+//             arrives: only the softmax warps take part, the TMA / MMA warps run ahead into the V stream);
+//   L pass    sum of exp(x - max) from the parked logits; second exchange; every CTA adds the slices in rank order,
+//             so the denominators are bit-identical across the cluster;
+//   V phase   p = dtype(exp(x - max) / sum) exactly as softmax + .to(dtype) form it (llama_patch.py:218-219), column
+//             statistics -> scratch, P^T tile -> shared memory (double-buffered), O^T += V^T P^T by tcgen05.mma;
+//   epilogue  the CTA's partial O^T: TMEM -> registers -> scratch; chunk_out_kernel / chunk_tail_kernel
+//             (ekv_chunk_tc.cu) sum the partials, fold the column statistics into the policy state, select and evict.
+//
+// Replaces: llama_patch.py:193-230 / mistral_patch.py:137-170 and easykv.py:439-457 / :599-618 / :830-848 for one
+// layer of one strided forward (and the dense prefill issued as causal chunks, h2o_head_score :173-186).
+#include "ekv_chunk_plan.h"
+#include "ekv_mma.cuh"
+#include "ekv_umma.cuh"
+
+namespace ekv {
+
+namespace cu {
+constexpr int D = 128;
+constexpr int TKEYS = 128;               // keys per tile = MMA M
+constexpr int NROWS = 64;                // (query, head) rows per cluster = MMA N
+constexpr int NSOFT = 256;               // 8 softmax warps
+constexpr int NT = NSOFT + 64;           // + TMA producer warp + MMA warp
+constexpr int STAGE_BYTES = 32768;       // one K or V tile: 2 boxes of [128 keys][64 dims]
+constexpr int NSTAGE = 4;
+constexpr int MAX_TILES = 10;            // logits parked in TMEM: 10 tiles x 32 columns
+constexpr int MAX_CLUSTER = 8;
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_LOG = 192, TM_COLS = 512;
+// shared memory (after 1024-byte alignment)
+constexpr int OFF_RING = 0;
+constexpr int OFF_Q = OFF_RING + NSTAGE * STAGE_BYTES;
+constexpr int OFF_P = OFF_Q + 16384;
+constexpr int OFF_BAR = OFF_P + 2 * 16384;                // 32 mbarriers
+constexpr int OFF_TMEM = OFF_BAR + 32 * 8;
+constexpr int OFF_REDMAX = OFF_TMEM + 16;                 // [8 warps][16] packed maxima
+constexpr int OFF_REDSUM = OFF_REDMAX + 8 * 16 * 4;       // [8 warps][32] sums
+constexpr int OFF_XMAX = OFF_REDSUM + 8 * 32 * 4;         // [MAX_CLUSTER][64]
+constexpr int OFF_XSUM = OFF_XMAX + MAX_CLUSTER * 64 * 4;
+constexpr int OFF_ROWM = OFF_XSUM + MAX_CLUSTER * 64 * 4; // [64] max | [64] sum or 1/sum | [64] rcp(sum)
+constexpr int SMEM_BYTES = OFF_ROWM + 3 * 64 * 4;
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
+// barrier indices
+constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_SFULL = 2 * NSTAGE, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2,
+              B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_XCH = B_OFULL + 1;
+static_assert(B_XCH + 2 <= 32, "barrier block");
+}  // namespace cu
+
+template <typename T> __device__ __forceinline__ uint32_t neg_inf2();
+template <> __device__ __forceinline__ uint32_t neg_inf2<__half>() { return 0xfc00fc00u; }
+template <> __device__ __forceinline__ uint32_t neg_inf2<__nv_bfloat16>() { return 0xff80ff80u; }
+template <typename T> __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t max2<__half>(uint32_t a, uint32_t b) {
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <typename T, int G, bool ARITH>
+__global__ void __launch_bounds__(cu::NT, 1)
+chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant__ CUtensorMap mapK,
+                  const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapKn,
+                  const __grid_constant__ CUtensorMap mapVn) {
+  using namespace cu;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* ring = smem + OFF_RING;
+  unsigned char* Qs = smem + OFF_Q;
+  unsigned char* Ps = smem + OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  uint32_t* redmax = reinterpret_cast<uint32_t*>(smem + OFF_REDMAX);
+  float* redsum = reinterpret_cast<float*>(smem + OFF_REDSUM);
+  float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
+  float* xsum = reinterpret_cast<float*>(smem + OFF_XSUM);
+  float* rowM = reinterpret_cast<float*>(smem + OFF_ROWM);
+  float* rowL = rowM + 64;
+  float* rowR = rowL + 64;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = pl.splits;
+  const int rank = blockIdx.x % C;
+  const int rb = (blockIdx.x / C) % pl.RB;
+  const int unit = blockIdx.x / (C * pl.RB);
+  const int b = unit / a.Hkv, h = unit % a.Hkv;
+  const int QL = a.q_len, n_phys = a.n_phys;
+  const int nct = pl.nct, nt = pl.nct + pl.nnt;
+  const int t0 = min(nt, rank * pl.tps), t1 = min(nt, t0 + pl.tps);
+  const int T_ = t1 - t0;
+
+  // ---- setup -----------------------------------------------------------------------------------------------------------
+  if (tid == NSOFT) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars[B_SFULL + s], 1); mbar_init(&bars[B_SEMPTY + s], NSOFT / 32);
+      mbar_init(&bars[B_PFULL + s], NSOFT / 32); mbar_init(&bars[B_PEMPTY + s], 1);
+      mbar_init(&bars[B_XCH + s], 64 * C);
+    }
+    mbar_init(&bars[B_OFULL], 1);
+    mbar_fence_init();
+    umma::tma_prefetch_desc(&mapK); umma::tma_prefetch_desc(&mapV);
+    umma::tma_prefetch_desc(&mapKn); umma::tma_prefetch_desc(&mapVn);
+  }
+  if (warp == NSOFT / 32 + 1) umma::tmem_alloc(tmem_slot, TM_COLS);
+  {
+    // Q block as the K-major B operand: row `col` of the block is (query qi, head g) with qi = (rb*64 + col) / G
+    const T* qg = reinterpret_cast<const T*>(a.q) + (size_t)b * a.H * QL * D;
+    for (int i = tid; i < NROWS * 16; i += NT) {
+      const int col = i >> 4, c = i & 15;
+      const int r = rb * NROWS + col, qi = r / G, g = r % G;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (qi < QL) v = reinterpret_cast<const uint4*>(qg + ((size_t)(h * G + g) * QL + qi) * D)[c];
+      *reinterpret_cast<uint4*>(Qs + (c >> 3) * 8192 + umma::swz128(col, c & 7)) = v;
+    }
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                                            // every CTA's barriers exist before any remote arrive
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == NSOFT / 32) {
+    // ===== TMA producer ==================================================================================================
+    if (lane == 0) {
+      // several row blocks (clusters) of a unit read the same K / V: keep those lines in L2; a single reader streams
+      const uint64_t pol = pl.RB > 1 ? umma::l2_policy_evict_last() : l2_policy_evict_first();
+      int it = 0;
+      for (int phase = 0; phase < 2; ++phase) {
+        for (int i = 0; i < T_; ++i, ++it) {
+          const int slot = it % NSTAGE, use = it / NSTAGE;
+          if (use > 0) mbar_wait(&bars[B_EMPTY + slot], (use - 1) & 1);
+          const int t = t0 + i;
+          const bool is_new = t >= nct;
+          const CUtensorMap* map = phase == 0 ? (is_new ? &mapKn : &mapK) : (is_new ? &mapVn : &mapV);
+          const int row = is_new ? unit * QL + (t - nct) * TKEYS : unit * a.cap + t * TKEYS;
+          unsigned char* dst = ring + (size_t)slot * STAGE_BYTES;
+          mbar_arrive_expect_tx(&bars[B_FULL + slot], STAGE_BYTES);
+          umma::tma_load_2d(dst, map, 0, row, &bars[B_FULL + slot], pol);
+          umma::tma_load_2d(dst + 16384, map, 64, row, &bars[B_FULL + slot], pol);
+        }
+      }
+    }
+  } else if (warp == NSOFT / 32 + 1) {
+    // ===== MMA issuer ====================================================================================================
+    if (lane == 0) {
+      const uint32_t id_qk = umma::instr_desc<T>(TKEYS, NROWS, false, false);
+      const uint32_t id_pv = umma::instr_desc<T>(D, NROWS, true, true);
+      const uint32_t ring_a = smem_u32(ring), q_a = smem_u32(Qs), p_a = smem_u32(Ps);
+      int it = 0;
+      for (int i = 0; i < T_; ++i, ++it) {                       // S^T(tile) = K_tile . Q^T
+        const int slot = it % NSTAGE, sb = i & 1;
+        mbar_wait(&bars[B_FULL + slot], (it / NSTAGE) & 1);
+        if (i >= 2) mbar_wait(&bars[B_SEMPTY + sb], ((i >> 1) - 1) & 1);
+        umma::fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                            // k-step: dims [16j, 16j+16)
+          const uint64_t da = umma::smem_desc(ring_a + slot * STAGE_BYTES + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024);
+          const uint64_t db = umma::smem_desc(q_a + (j >> 2) * 8192 + (j & 3) * 32, 16, 1024);
+          umma::mma_ss(tmem + TM_S + sb * NROWS, da, db, id_qk, j > 0);
+        }
+        umma::commit(&bars[B_EMPTY + slot]);
+        umma::commit(&bars[B_SFULL + sb]);
+      }
+      for (int i = 0; i < T_; ++i, ++it) {                       // O^T += V_tile^T . P^T(tile)
+        const int slot = it % NSTAGE, pb = i & 1;
+        mbar_wait(&bars[B_FULL + slot], (it / NSTAGE) & 1);
+        mbar_wait(&bars[B_PFULL + pb], (i >> 1) & 1);
+        umma::fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                            // k-step: keys [16j, 16j+16)
+          const uint64_t da = umma::smem_desc(ring_a + slot * STAGE_BYTES + j * 2048, 16384, 1024);
+          const uint64_t db = umma::smem_desc(p_a + pb * 16384 + j * 2048, 1024, 1024);
+          umma::mma_ss(tmem + TM_O, da, db, id_pv, (i > 0 || j > 0) ? 1u : 0u);
+        }
+        umma::commit(&bars[B_EMPTY + slot]);
+        umma::commit(&bars[B_PEMPTY + pb]);
+      }
+      umma::commit(&bars[B_OFULL]);
+    }
+  } else {
+    // ===== softmax warps: lane of TMEM = key ==================================================================================
+    const int q4 = warp & 3, hf = warp >> 2;                     // TMEM lane quarter; which 32 of the 64 rows
+    const int kl = q4 * 32 + lane;                               // key inside the tile
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int32_t* lg = a.lidx + (size_t)unit * a.cap;
+    const int qbase = rb * (NROWS / G);                          // first query of this row block
+    auto tile_key = [&](int t, bool& is_new, int& e, bool& valid, int& jn) {
+      is_new = t >= nct;
+      if (is_new) {
+        jn = (t - nct) * TKEYS + kl;                             // index among the chunk's own keys
+        e = n_phys + jn;
+        valid = jn < QL;
+      } else {
+        const int key = t * TKEYS + kl;
+        e = key;
+        jn = -1;
+        valid = key < n_phys && lg[key] >= 0;                    // free slots inside [0, n_phys) are streamed and masked
+      }
+    };
+
+    // ---- K phase: logits -> TMEM, running row maxima ------------------------------------------------------------------
+    uint32_t rmax[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rmax[j] = neg_inf2<T>();
+    for (int i = 0; i < T_; ++i) {
+      bool is_new, valid;
+      int e, jn;
+      tile_key(t0 + i, is_new, e, valid, jn);
+      const int sb = i & 1;
+      mbar_wait(&bars[B_SFULL + sb], (i >> 1) & 1);
+      umma::fence_after_sync();
+      uint32_t r[32];
+      umma::tmem_ld32(tmem + lane_base + TM_S + sb * NROWS + hf * 32, r);
+      umma::tmem_wait_ld();
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
+        round2<T>(x0, x1);                                       // llama_patch.py:201: the matmul's result is a model-dtype tensor
+        x0 = ARITH ? __fmul_rn(x0, a.scale_mul) : __fdiv_rn(x0, a.scale_div);    // :202
+        x1 = ARITH ? __fmul_rn(x1, a.scale_mul) : __fdiv_rn(x1, a.scale_div);
+        w[j] = pack2<T>(x0, x1);
+      }
+      if (!valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = neg_inf2<T>();
+      } else if (is_new) {                                       // causal among the chunk's own keys (:210-215)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int q0 = qbase + (hf * 32 + 2 * j) / G, q1 = qbase + (hf * 32 + 2 * j + 1) / G;
+          if (jn > q0) w[j] = (w[j] & 0xffff0000u) | (neg_inf2<T>() & 0xffffu);
+          if (jn > q1) w[j] = (w[j] & 0x0000ffffu) | (neg_inf2<T>() & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rmax[j] = max2<T>(rmax[j], w[j]);
+      umma::tmem_st16(tmem + lane_base + TM_LOG + i * 32 + hf * 16, w);
+    }
+    umma::tmem_wait_st();
+
+    // ---- row maxima: lanes -> warps -> cluster ------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rmax[j] = max2<T>(rmax[j], __shfl_xor_sync(0xffffffffu, rmax[j], o));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) redmax[warp * 16 + j] = rmax[j];
+    }
+    named_bar_sync(1, NSOFT);
+    if (tid < 64) {
+      const int hfr = tid >> 5, j = tid & 31;
+      float m = -INFINITY;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const uint32_t u = redmax[(hfr * 4 + qq) * 16 + (j >> 1)];
+        const float2 f = Tr<T>::to_f2(u);
+        m = fmaxf(m, (j & 1) ? f.y : f.x);
+      }
+      for (int p = 0; p < C; ++p) {
+        st_cluster_f32(map_to_rank(&xmax[rank * 64 + tid], p), m);
+        umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 0], p));
+      }
+    }
+    umma::mbar_wait_cluster(&bars[B_XCH + 0], 0);
+    if (tid < 64) {
+      float m = xmax[tid];
+      for (int p = 1; p < C; ++p) m = fmaxf(m, xmax[p * 64 + tid]);
+      rowM[tid] = m;
+    }
+    named_bar_sync(1, NSOFT);
+    float negM[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(&rowM[hf * 32 + j]);
+      negM[j] = -v.x; negM[j + 1] = -v.y; negM[j + 2] = -v.z; negM[j + 3] = -v.w;
+    }
+
+    // ---- L pass: sum of exp(x - max) over the parked logits ------------------------------------------------------------------
+    float L[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) L[j] = 0.f;
+    for (int i = 0; i < T_; ++i) {
+      uint32_t w[16];
+      umma::tmem_ld16(tmem + lane_base + TM_LOG + i * 32 + hf * 16, w);
+      umma::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 x = Tr<T>::to_f2(w[j]);
+        L[2 * j] += expf(x.x + negM[2 * j]);
+        L[2 * j + 1] += expf(x.y + negM[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) L[j] += __shfl_xor_sync(0xffffffffu, L[j], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) redsum[warp * 32 + j] = L[j];
+    }
+    named_bar_sync(1, NSOFT);
+    if (tid < 64) {
+      const int hfr = tid >> 5, j = tid & 31;
+      float s = redsum[(hfr * 4) * 32 + j];
+#pragma unroll
+      for (int qq = 1; qq < 4; ++qq) s += redsum[(hfr * 4 + qq) * 32 + j];
+      for (int p = 0; p < C; ++p) {
+        st_cluster_f32(map_to_rank(&xsum[rank * 64 + tid], p), s);
+        umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 1], p));
+      }
+    }
+    umma::mbar_wait_cluster(&bars[B_XCH + 1], 0);
+    if (tid < 64) {
+      float s = xsum[tid];
+      for (int p = 1; p < C; ++p) s += xsum[p * 64 + tid];        // rank order on every CTA: identical denominators
+      if (s == 0.f) s = 1.f;
+      rowL[tid] = ARITH ? s : __fdiv_rn(1.0f, s);
+      rowR[tid] = __frcp_rn(s);
+    }
+    named_bar_sync(1, NSOFT);
+    float Rc[ARITH ? 32 : 1];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(&rowL[hf * 32 + j]);
+      L[j] = v.x; L[j + 1] = v.y; L[j + 2] = v.z; L[j + 3] = v.w;
+      if (ARITH) {
+        const float4 u = *reinterpret_cast<const float4*>(&rowR[hf * 32 + j]);
+        Rc[j] = u.x; Rc[j + 1] = u.y; Rc[j + 2] = u.z; Rc[j + 3] = u.w;
+      }
+    }
+
+    // ---- V phase: probabilities, column statistics, P^T tiles ---------------------------------------------------------------
+    const bool want_stats = a.st.accumulate != 0;
+    const bool tova = a.st.policy == EKV_POLICY_TOVA;
+    const float inv_g = 1.0f / (float)G;
+    float2* cg = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_cpart) +
+                 ((size_t)unit * (2 * pl.RB) + 2 * rb + hf) * pl.NEpad;
+    for (int i = 0; i < T_; ++i) {
+      bool is_new, valid;
+      int e, jn;
+      tile_key(t0 + i, is_new, e, valid, jn);
+      const int pb = i & 1;
+      uint32_t w[16];
+      umma::tmem_ld16(tmem + lane_base + TM_LOG + i * 32 + hf * 16, w);
+      umma::tmem_wait_ld();
+      float pr[32];                                               // the key's probabilities for this CTA's 32 rows
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 x = Tr<T>::to_f2(w[j]);
+        const float e0 = expf(x.x + negM[2 * j]), e1 = expf(x.y + negM[2 * j + 1]);
+        float p0 = ARITH ? div_rn_by(e0, L[2 * j], Rc[ARITH ? 2 * j : 0]) : __fmul_rn(e0, L[2 * j]);              // llama_patch.py:218
+        float p1 = ARITH ? div_rn_by(e1, L[2 * j + 1], Rc[ARITH ? 2 * j + 1 : 0]) : __fmul_rn(e1, L[2 * j + 1]);
+        round2<T>(p0, p1);                                        // :219 .to(dtype)
+        pr[2 * j] = p0; pr[2 * j + 1] = p1;
+        w[j] = pack2<T>(p0, p1);
+      }
+      float cs = 0.f, csq = 0.f;
+      if (want_stats) {
+        // GQA fold in the model dtype (process_for_mqa_gqa, easykv.py:188-196), then each query's share of the
+        // chunk's row sums of p and model-dtype(p^2) (:450-451); tova keeps the last query only (:454)
+#pragma unroll
+        for (int u = 0; u < 32 / G; ++u) {                        // one query: its G heads are adjacent rows
+          float fsum = pr[u * G];
+#pragma unroll
+          for (int g = 1; g < G; ++g) fsum += pr[u * G + g];
+          const int qi = qbase + hf * (32 / G) + u;
+          if (qi < QL && (!tova || qi == QL - 1)) {
+            const float pf = G == 1 ? fsum : Tr<T>::round_f(__fmul_rn(fsum, inv_g));
+            cs += pf;
+            csq += Tr<T>::round_f(__fmul_rn(pf, pf));
+          }
+        }
+      }
+      if (want_stats && (is_new ? jn < QL : e < n_phys)) cg[e] = make_float2(cs, csq);
+      if (i >= 2) mbar_wait(&bars[B_PEMPTY + pb], ((i >> 1) - 1) & 1);
+      unsigned char* prow = Ps + pb * 16384;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(prow + umma::swz128(kl, hf * 4 + c)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      umma::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_PFULL + pb]);
+    }
+
+    // ---- epilogue: this CTA's partial O^T -> scratch ---------------------------------------------------------------------------
+    float* op = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_opart) +
+                (((size_t)unit * pl.splits + rank) * pl.Rpad + rb * NROWS + hf * 32) * D + kl;     // kl = output dim here
+    if (T_ > 0) {
+      mbar_wait(&bars[B_OFULL], 0);
+      umma::fence_after_sync();
+      uint32_t r[32];
+      umma::tmem_ld32(tmem + lane_base + TM_O + hf * 32, r);
+      umma::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) op[(size_t)j * D] = __uint_as_float(r[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) op[(size_t)j * D] = 0.f;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == NSOFT / 32 + 1) umma::tmem_dealloc(tmem, TM_COLS);
+}
+
+// ---- plan ----------------------------------------------------------------------------------------------------------------
+bool make_umma_plan(int B, int Hkv, int G, int q_len, int n_phys, int sms, ChunkPlan& out) {
+  using namespace cu;
+  ChunkPlan p = make_chunk_plan(B, Hkv, G, q_len, n_phys);       // R, RB, Rpad, NE, NEpad and the scratch carve-up
+  p.nct = (n_phys + TKEYS - 1) / TKEYS;
+  p.nnt = (q_len + TKEYS - 1) / TKEYS;
+  const int nt = p.nct + p.nnt;
+  const int cmin = (nt + MAX_TILES - 1) / MAX_TILES;
+  if (cmin > MAX_CLUSTER) return false;
+  const long long groups = (long long)B * Hkv * p.RB;
+  int best = 0;
+  double best_cost = 0;
+  for (int c = cmin; c <= MAX_CLUSTER; ++c) {
+    if (c != 1 && c != 2 && c != 4 && c != 8) continue;          // power-of-two clusters pack the GPCs best
+    const int tps = (nt + c - 1) / c;
+    if (tps > MAX_TILES) continue;
+    const long long ctas = groups * c;
+    const double waves = (double)((ctas + sms - 1) / sms);
+    const double cost = waves * (tps + 2.5);                     // per-CTA fixed work ~ 2.5 tiles (setup, exchanges, epilogue)
+    if (!best || cost < best_cost - 1e-9) { best = c; best_cost = cost; }
+  }
+  if (!best) return false;
+  p.splits = best;
+  p.tps = (nt + best - 1) / best;
+  // re-carve the scratch for `splits` partial outputs (the row statistics block of the two-pass path is unused)
+  const long long U = (long long)B * Hkv;
+  long long o = 0;
+  p.off_stats = 0;
+  p.off_opart = o; o += U * p.splits * p.Rpad * D * 4;
+  o = (o + 255) / 256 * 256;
+  p.off_cpart = o; o += U * (2 * p.RB) * p.NEpad * 2 * 4;
+  o = (o + 255) / 256 * 256;
+  p.off_klj = o; o += U * p.NEpad * 4;
+  p.off_ka = o; o += U * p.NEpad * 4;
+  p.off_kb = o; o += U * p.NEpad * 4;
+  p.off_kf = o; o += U * p.NEpad;
+  p.bytes = (o + 255) / 256 * 256;
+  out = p;
+  return true;
+}
+
+// ---- launch --------------------------------------------------------------------------------------------------------------
+static int device_sms() {
+  static thread_local int sm_count[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
+  if (!sm_count[dev] && cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count[dev] = 148;
+  return sm_count[dev];
+}
+int umma_sm_count() { return device_sms(); }
+
+template <typename T, int G, bool ARITH>
+static int launch_umma_k(const KernelArgs& a, const ChunkPlan& pl, const CUtensorMap* maps, cudaStream_t stream) {
+  using namespace cu;
+  static thread_local int configured[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16) dev = 15;
+  cudaError_t err;
+  if (!configured[dev]) {
+    err = cudaFuncSetAttribute(chunk_umma_kernel<T, G, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(chunk_umma)", err);
+    configured[dev] = 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a.B * a.Hkv * pl.RB * pl.splits), 1, 1);
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_ALLOC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)pl.splits;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  err = cudaLaunchKernelEx(&cfg, chunk_umma_kernel<T, G, ARITH>, a, pl, maps[0], maps[1], maps[2], maps[3]);
+  if (err != cudaSuccess) return set_cuda_error("chunk_umma_kernel launch", err);
+  count_launch();
+  return EKV_OK;
+}
+
+template <typename T, int G> static int launch_umma_tg(const KernelArgs& a, cudaStream_t stream) {
+  ChunkPlan pl;
+  if (!make_umma_plan(a.B, a.Hkv, G, a.q_len, a.n_phys, device_sms(), pl)) return EKV_ERR_UNSUPPORTED;
+  // tensor maps over the caller's buffers viewed as [rows][128]: the cache (all units' slots) and the chunk's new rows
+  CUtensorMap maps[4];
+  const unsigned long long rows_c = (unsigned long long)a.B * a.Hkv * a.cap, rows_n = (unsigned long long)a.B * a.Hkv * a.q_len;
+  int rc = make_tensor_map_rows128(&maps[0], a.K, rows_c, cu::TKEYS, a.dtype);
+  if (!rc) rc = make_tensor_map_rows128(&maps[1], a.V, rows_c, cu::TKEYS, a.dtype);
+  if (!rc) rc = make_tensor_map_rows128(&maps[2], a.k_new, rows_n, cu::TKEYS, a.dtype);
+  if (!rc) rc = make_tensor_map_rows128(&maps[3], a.v_new, rows_n, cu::TKEYS, a.dtype);
+  if (rc) return rc;
+  rc = a.st.arith ? launch_umma_k<T, G, true>(a, pl, maps, stream) : launch_umma_k<T, G, false>(a, pl, maps, stream);
+  if (rc) return rc;
+  return launch_chunk_finish(a, pl, stream);
+}
+
+template <typename T> static int launch_umma_t(const KernelArgs& a, cudaStream_t stream) {
+  switch (a.H / a.Hkv) {
+    case 1: return launch_umma_tg<T, 1>(a, stream);
+    case 2: return launch_umma_tg<T, 2>(a, stream);
+    case 4: return launch_umma_tg<T, 4>(a, stream);
+    case 8: return launch_umma_tg<T, 8>(a, stream);
+    default: return EKV_ERR_UNSUPPORTED;
+  }
+}
+
+// 16-bit dtypes, head_dim 128, needs scratch; EKV_ERR_UNSUPPORTED when the key range does not fit 8 CTAs x 10 tiles
+// (more than 10 240 cached slots + the chunk): the caller then takes the two-pass mma.sync path.
+int launch_chunk_umma(const KernelArgs& a, cudaStream_t stream) {
+  if (a.d != cu::D || !a.scratch || a.q_len < 1) return EKV_ERR_UNSUPPORTED;
+  // the tensor maps address rows of 256 bytes from 16-byte aligned bases
+  if ((reinterpret_cast<uintptr_t>(a.K) | reinterpret_cast<uintptr_t>(a.V) | reinterpret_cast<uintptr_t>(a.k_new) |
+       reinterpret_cast<uintptr_t>(a.v_new)) & 15) return EKV_ERR_UNSUPPORTED;
+  switch (a.dtype) {
+    case EKV_F16: return launch_umma_t<__half>(a, stream);
+    case EKV_BF16: return launch_umma_t<__nv_bfloat16>(a, stream);
+    default: return EKV_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace ekv

@@ -43,6 +43,8 @@ int launch_rope_cache(int dtype, const void* K_raw, void* K, const int32_t* lidx
 int launch_logits_adapter(const float* logits, int rows, int V, float temperature, float top_p, int arith, const float* q_exp,
                           float* prob, float* raw, long long* token, cudaStream_t stream);   // ekv_sample.cu
 int launch_token_nll(const float* logits, const long long* targets, int rows, int V, float* nll, cudaStream_t stream);
+int launch_umma_probe(int dtype, const void* K, const void* V, const void* Q, const void* Pt, float* St, float* Ot,
+                      cudaStream_t stream);   // ekv_umma_probe.cu
 int launch_export(const KernelArgs& a, void* K_out, void* V_out, float* S_out, float* SQ_out, float* C_out,
                   cudaStream_t stream);
 

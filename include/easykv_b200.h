@@ -224,6 +224,18 @@ EKV_API void ekv_debug_set_timeline(void* device_buffer);
  *                 this many CTAs per (sequence, kv head) (ekv_decode_cluster.cu). */
 EKV_API void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size);
 
+/* Strided-chunk kernel selection (development / test hook): 0 = automatic (the tcgen05 cluster kernel, falling back to
+ * the two-pass mma.sync kernels for key ranges beyond 8 x 10 tiles), 1 = same as 0, 2 = always the mma.sync kernels. */
+EKV_API void ekv_debug_set_chunk_variant(int32_t chunk_variant);
+
+/* Primitive-level probe of the tensor-core path the strided-prefill chunk kernel is built from (development / test
+ * hook, not part of the data path): one CTA loads K, V [128, 128] (16-bit, row-major) by tensor-map TMA, stages
+ * Q [64, 128] and Pt [128 keys, 64 rows] in shared memory and computes with tcgen05.mma into tensor memory
+ *   St [128 keys, 64 rows] = K . Q^T      Ot [128 dims, 64 rows] = V^T . Pt      (fp32).
+ * tests/test_gpu_umma.py pins both against torch. */
+EKV_API int ekv_debug_umma_probe(int32_t dtype, const void* K, const void* V, const void* Q, const void* Pt, float* St, float* Ot,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

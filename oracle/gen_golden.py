@@ -109,14 +109,21 @@ CASES = {
 }
 
 
-def run_case(name, c):
+def run_trace(c, device="cpu"):
+    """One traced run of the unmodified reference on the scaffold (`device`: 'cpu', or 'cuda' on the GPU box)."""
     dtype = getattr(torch, c["dtype"])
-    model = scaffold.build(c["arch"], seed=0, dtype=dtype, L=c["L"], H=c["H"], Hkv=c["Hkv"], d=c["d"], vocab=512)
-    ids = torch.randint(3, 512, (1, c["seq"]), generator=torch.Generator().manual_seed(1))
+    model = scaffold.build(c["arch"], seed=0, dtype=dtype, device=device, L=c["L"], H=c["H"], Hkv=c["Hkv"], d=c["d"],
+                           vocab=512, inter=c.get("inter"), max_pos=c.get("max_pos", 4096))
+    ids = torch.randint(3, 512, (1, c["seq"]), generator=torch.Generator().manual_seed(1)).to(device)
     gen = dict(temperature=1e-9, top_p=1.0, max_new_tokens=c["max_new_tokens"], **c["gen"])
     ppl = c["mode"] == "ppl"
     torch.manual_seed(RNG_SEED)                      # the global CPU generator the reference's 'random' policy draws from
-    tr = ref_harness.run_reference(model, ids, gen, mode="encoding" if ppl else c["mode"], stride=c["stride"], ppl=ppl)
+    return ref_harness.run_reference(model, ids, gen, mode="encoding" if ppl else c["mode"], stride=c["stride"], ppl=ppl)
+
+
+def trace_arrays(name, c, tr, device="cpu"):
+    """(meta, arrays) of one traced run — what a golden file holds."""
+    dtype = getattr(torch, c["dtype"])
     arrs = {}
     npdt = np.float32 if dtype in (torch.float32, torch.bfloat16) else np.float16      # bf16 values are exact in fp32
     for l, (k, v) in enumerate(tr.prefill_cache):
@@ -137,13 +144,23 @@ def run_case(name, c):
     if tr.seed is not None:
         arrs["seed_S"], arrs["seed_SQ"] = tr.seed[0].numpy().astype(np.float32), tr.seed[1].numpy().astype(np.float32)
     for l, kv in enumerate(tr.final_cache):
-        arrs[f"final_K_{l}"], arrs[f"final_V_{l}"] = kv[0][0].float().numpy().astype(npdt), kv[1][0].float().numpy().astype(npdt)
+        arrs[f"final_K_{l}"], arrs[f"final_V_{l}"] = (kv[0][0].detach().cpu().float().numpy().astype(npdt),
+                                                      kv[1][0].detach().cpu().float().numpy().astype(npdt))
     meta = dict(name=name, case=c, rng_seed=RNG_SEED, forwards=fmeta, events=emeta, printed=tr.printed, tokens=tr.tokens,
-                result=tr.result if isinstance(tr.result, float) else str(tr.result),
+                result=tr.result if isinstance(tr.result, float) else str(tr.result), device=str(device),
                 torch=torch.__version__, reference_commit="a1d71cae3b562d9a709dda3741bd63e46a09ad31")
+    if str(device).startswith("cuda"):
+        meta["gpu"] = torch.cuda.get_device_name(0)
+    return meta, arrs
+
+
+def run_case(name, c, device="cpu", out_dir=None):
+    tr = run_trace(c, device)
+    meta, arrs = trace_arrays(name, c, tr, device)
     arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
-    os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    out_dir = out_dir or OUT
+    os.makedirs(out_dir, exist_ok=True)
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrs)
     return tr
 
 

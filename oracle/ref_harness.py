@@ -15,8 +15,10 @@ need (SURVEY.md §8c "Shims needed"):
   * `torch.multinomial` replaced by argmax so token choice is deterministic
     (every reference script runs `temperature=1e-9`, e.g. `test_decoding.py:41`).
 
-`/root/reference` does not exist on the GPU box: nothing imported by `-m gpu` tests,
-`smoke()` or `bench.py` may import this file.
+`/root/reference` does not exist on the GPU box.  `tools/vendor_ref.sh` (also run by `__graft_entry__.build()`) copies the
+reference's `easykv/*.py` UNMODIFIED into `oracle/_ref/` (git-ignored, travels with gpurun) so that the same harness can
+run the reference on the B200 itself — fp16 / bf16 on CUDA, the arithmetic the product's default (`arith=1`) reproduces.
+Importers: `tests/`, `oracle/gen_golden*.py`, `bench.py --impl reference` / its `gpu_reference` leg.  Never the product.
 """
 from __future__ import annotations
 
@@ -26,12 +28,27 @@ import sys
 
 import torch
 
-REF_ROOT = "/root/reference"
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_CANDIDATES = ("/root/reference", os.path.join(_HERE, "_ref"))
+
+
+def reference_root():
+    """Where the unmodified reference package lives: the mounted checkout (build container) or the vendored copy."""
+    for r in REF_CANDIDATES:
+        if os.path.isfile(os.path.join(r, "easykv", "easykv.py")):
+            return r
+    return None
 
 
 def import_reference():
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("the reference is neither mounted at /root/reference nor vendored into oracle/_ref "
+                           "(run tools/vendor_ref.sh in the build container)")
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import easykv  # noqa: F401  (the reference package)
     import easykv.easykv as ref_main
     import easykv.llama_patch as ref_llama

@@ -41,8 +41,18 @@ def load_sampling_tail():
             for i, m in enumerate(meta["cases"])]
 
 
-def load_golden(name):
-    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+GOLDEN_GPU_DIR = os.path.join(os.path.dirname(GOLDEN_DIR), "golden_gpu")
+
+
+def list_golden_gpu():
+    """Runs of the unmodified reference recorded ON A B200 (fp16 / bf16 on CUDA; oracle/gen_golden_gpu.py)."""
+    if not os.path.isdir(GOLDEN_GPU_DIR):
+        return []
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_GPU_DIR) if f.endswith(".npz"))
+
+
+def load_golden(name, golden_dir=None):
+    z = np.load(os.path.join(golden_dir or GOLDEN_DIR, name + ".npz"))
     meta = json.loads(bytes(z["meta"]).decode())
     return meta, z
 
@@ -113,12 +123,13 @@ def case_keep_attention(meta):
     return bool(meta["case"]["gen"].get("keep_attention", False))
 
 
-def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0) -> Report:
+def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0, golden_dir=None, trace=None) -> Report:
     """`resync`: after comparing, apply the REFERENCE's victims so every later step is again
     tested on identical state.  `shadow`: an OracleEngine factory run in lock-step (always
     forced to the reference's victims) whose decision margins classify a mismatch as
-    tie-ambiguous (margin <= tie_eps) or real."""
-    meta, z = load_golden(name)
+    tie-ambiguous (margin <= tie_eps) or real.  `trace`: (meta, arrays) of a run recorded in this
+    process (oracle/gen_golden.trace_arrays) instead of a file."""
+    meta, z = trace if trace is not None else load_golden(name, golden_dir)
     c = meta["case"]
     dtype = getattr(torch, c["dtype"])
     L, H, Hkv, d = c["L"], c["H"], c["Hkv"], c["d"]
