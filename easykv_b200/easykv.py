@@ -180,7 +180,11 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
     param = next(self.parameters())
     device, dtype = param.device, param.dtype
     input_ids = input_ids.to(device)
-    capacity = plan.capacity + (max_new_tokens if plan.mode in ("dense", "encoding") else 0) + 1
+    sched = list(P.schedule(plan, policy, max_new_tokens, keep_attention))
+    n_dense = length if plan.mode in ("decoding", "dense") else plan.r_idx
+    # the largest cache length any forward reaches (a schedule that never evicts — kv_policy='full' — grows to the prompt)
+    capacity = max(plan.capacity + (max_new_tokens if plan.mode in ("dense", "encoding") else 0),
+                   P.required_capacity(n_dense, sched)) + 1
     # "aten_arith": which ATen flavour's two non-associative spots to reproduce (include/easykv_b200.h,
     # ekv_step.arith): the CUDA kernels' (default — what the reference does on a GPU) or the CPU kernels'
     arith = {"cuda": 1, "cpu": 0}[cfg.get("aten_arith", "cuda")]
@@ -226,7 +230,6 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
         return cache.sample(last_logits, temperature, top_p)
 
     with patched_attention(self, sess):
-        sched = list(P.schedule(plan, policy, max_new_tokens, keep_attention))
         chunks = [s for s in sched if s[0] == "chunk"]
         decodes = [s for s in sched if s[0] == "decode"]
         all_nll = []
@@ -241,7 +244,6 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
                                   next_ids(t0, min(DENSE_CHUNK, length - t0))) for t0 in range(0, length, DENSE_CHUNK)]
             return math.exp(statistics.mean(torch.cat(lp)[:-1].cpu().numpy().tolist()))
         # ---- prompt --------------------------------------------------------------------------------------
-        n_dense = length if plan.mode in ("decoding", "dense") else plan.r_idx
         logits = dense_prefill(n_dense)
         if streaming and plan.mode == "decoding":
             # the reference prefills the prompt with the stock forward BEFORE patching (easykv.py:232 vs :253): the
@@ -260,7 +262,8 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
                 all_nll.append(cache.token_nll(logits[0].float(), next_ids(cur, q_len)))
             cur += q_len
         retained = cache.n[0]
-        if plan.mode in ("encoding", "ppl"):
+        if plan.mode in ("encoding", "ppl") or (plan.mode == "dense" and kv_mode == "encoding"):
+            # easykv.py:501-503 sits outside the budget if/else: 'encoding' prints the line for a dense prefill too
             print(f"KV cache budget ratio: {retained / length * 100:.2f}%({retained}/{length})")
         if ppl_mode:                                           # easykv.py:896-901
             return math.exp(statistics.mean(torch.cat(all_nll)[:-1].cpu().numpy().tolist()))

@@ -91,6 +91,19 @@ class Plan:
         return self.idx + self.stride
 
 
+def required_capacity(n_dense: int, sched) -> int:
+    """Physical slots per (sequence, kv head) a run needs: the largest cache length any forward reaches right after
+    its append, over the dense prefill (n_dense tokens) and the schedule `sched` (a list of `schedule()` items).  With
+    kv_policy='full' (or whenever the schedule never evicts, e.g. the summarisation / ppl baselines the reference
+    runs with a budget below the prompt length, easykv.py:459, :850) the cache simply grows to the whole prompt —
+    `Plan.capacity` alone (idx + stride) would be too small."""
+    n = cap = n_dense
+    for _, q_len, st in sched:
+        cap = max(cap, n + q_len)
+        n += q_len - int(st.evict)
+    return cap
+
+
 def resolve_plan(kv_mode, length, budget, stride, recent_ratio=0.1, temp_length=4) -> Plan:
     if kv_mode == "auto":
         if type(budget) is not int:

@@ -99,6 +99,8 @@ class OracleCache:
             if ids is not None:
                 ids = torch.sort(ids, dim=-1)[0][None].int()
         self.n[l] = lo.K.shape[1]
+        if self.n[l] + (0 if ids is None else ids.shape[-1]) > self.cap:      # what BudgetedKVCache.step raises
+            raise ValueError(f"cache capacity {self.cap} exceeded")
         return out[None], ids
 
 
@@ -177,6 +179,34 @@ def test_driver_chunked_dense_prefill_cpu(monkeypatch):
     result, printed, sess = _run(meta, model, ids, "cpu")
     assert "53.12%(136/256)" in printed
     assert len(sess.events) == 15
+
+
+@pytest.mark.parametrize("mode,budget", [("encoding", 0.5), ("ppl", 0.5), ("encoding", 1.0), ("ppl", 1.0)])
+def test_driver_full_policy_baseline_matches_reference_cpu(mode, budget, monkeypatch):
+    """kv_policy='full' with a budget below the prompt length is the full-cache baseline the reference's ppl and
+    summarisation scripts run (easykv.py:459, :850 `mode != 'full'`): nothing is ever evicted, the cache grows to the
+    whole prompt (the capacity must follow the schedule, not idx + stride), and 'encoding' prints its ratio line even
+    when the prefill is dense (:501-503).  Compared with a fresh run of the unmodified reference."""
+    from oracle import ref_harness
+    if ref_harness.reference_root() is None:
+        pytest.skip("reference not available")
+    c = dict(arch="llama", L=1, H=4, Hkv=2, d=128, seq=100, dtype="float32", mode=mode, stride=8,
+             max_new_tokens=0 if mode == "ppl" else 3, gen=dict(budget=budget, kv_policy="full"))
+    model = scaffold.build(c["arch"], seed=0, dtype=torch.float32, L=c["L"], H=c["H"], Hkv=c["Hkv"], d=c["d"], vocab=512)
+    ids = torch.randint(3, 512, (1, c["seq"]), generator=torch.Generator().manual_seed(1))
+    gen = dict(temperature=1e-9, top_p=1.0, max_new_tokens=c["max_new_tokens"], **c["gen"])
+    ref = ref_harness.run_reference(model, ids, gen, mode="encoding", stride=c["stride"], ppl=mode == "ppl", record_tensors=False)
+    monkeypatch.setattr(drv, "BudgetedKVCache", OracleCache)
+    monkeypatch.setattr(torch, "multinomial", lambda p, num_samples=1, **kw: p.argmax(dim=-1, keepdim=True))
+    meta = dict(case=c)
+    result, printed, sess = _run(meta, model, ids, "cpu")
+    if mode == "ppl":
+        assert result == pytest.approx(float(ref.result), rel=1e-5)
+    else:
+        assert result == str(ref.result)
+    for ln in [ln for ln in ref.printed.splitlines() if "atio" in ln and "%" in ln]:
+        assert ln in printed, (ln, printed)
+    assert not sess.events
 
 
 def test_driver_rejects_what_the_reference_silently_ignores():
