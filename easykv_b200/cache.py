@@ -319,35 +319,42 @@ class BudgetedKVCache:
         self.free[l] = None
 
 
-class SteadyDecode:
-    """The steady-state decode step of `encoding_decoding` / `decoding` (easykv.py:670-748, :257-363
-    once the budget is reached): every step appends one token per sequence and evicts one per
-    (sequence, layer, kv head), so shapes never change.  All C-ABI arguments are built once; the
-    per-layer victim buffer of step t is the new-slot buffer of step t+1 (no host round trip), and the
-    whole L-layer step can be captured into one CUDA graph."""
+class SteadyStep:
+    """The steady state of a budgeted loop: every forward appends `q_len` tokens per sequence and evicts `q_len` per
+    (sequence, layer, kv head), so shapes never change — the decode step of `encoding_decoding` / `decoding`
+    (q_len = 1; easykv.py:670-748, :257-363 once the budget is reached) and the strided-prefill chunk once the cache
+    has reached its size (q_len = stride; easykv.py:426-500, :587-661).  All C-ABI arguments are built once; the
+    per-layer victim buffer of step t is the new-slot buffer of step t+1 (no host round trip), and the whole L-layer
+    step can be captured into one CUDA graph."""
 
     def __init__(self, cache: BudgetedKVCache, sp: StepParams, q, k_new, v_new, out=None):
-        """q `[L, B, H, 1, d]`, k_new / v_new `[L, B, Hkv, 1, d]`: device buffers the caller refills
+        """q `[L, B, H, q_len, d]`, k_new / v_new `[L, B, Hkv, q_len, d]`: device buffers the caller refills
         before each `run()` (e.g. the projections' outputs)."""
-        assert sp.evict == 1
         c = self.cache = cache
+        ql = self.q_len = q.shape[3]
+        assert sp.evict == ql, "steady state: as many victims as appended tokens"
         self.q, self.k_new, self.v_new = q, k_new, v_new
         self.out = torch.empty_like(q) if out is None else out
-        self.victim_lidx = torch.empty(c.L, c.B, c.Hkv, 1, dtype=torch.int32, device=c.device)
-        self.slots = torch.empty(c.L, c.B, c.Hkv, 1, dtype=torch.int32, device=c.device)
+        self.victim_lidx = torch.empty(c.L, c.B, c.Hkv, ql, dtype=torch.int32, device=c.device)
+        self.slots = torch.empty(c.L, c.B, c.Hkv, ql, dtype=torch.int32, device=c.device)
         self.cstep = sp.to_c(apply=True, arith=c.arith)
         self.calls = []
         for l in range(c.L):
-            if c.free_count(l) != 1:
+            if c.free_count(l) != ql:
                 # bring the layer into the steady state: one append-mode evicting step
                 o, _ = c.step(l, sp, q[l], k_new[l], v_new[l])
                 self.out[l].copy_(o)
             self.slots[l].copy_(c.free[l])
             c.free[l] = self.slots[l]
-            shape = c._shape(l, 1)
+            shape = c._shape(l, ql)
+            need = c.lib.ekv_scratch_bytes(C.byref(shape), C.byref(self.cstep)) if (ql > 1 or self.cstep.tova_head_mean) else 0
+            if need and (c.scratch is None or c.scratch.numel() < need):
+                c.scratch = torch.empty(need, dtype=torch.uint8, device=c.device)
             io = c._io(l, q=q[l], k_new=k_new[l], v_new=v_new[l], out=self.out[l], new_slots=self.slots[l],
                        victim_slots=self.slots[l], victim_lidx=self.victim_lidx[l])
             self.calls.append((shape, io))
+        for shape, io in self.calls:                  # the scratch may have been re-allocated while the list was built
+            io.scratch = c.scratch.data_ptr() if c.scratch is not None else None
         self.graph = None
 
     def run(self, stream=None):
@@ -367,7 +374,7 @@ class SteadyDecode:
             _lib.check(rc)
 
     def capture(self):
-        """Capture one whole step (L launches) into a CUDA graph; `replay()` then costs one launch."""
+        """Capture one whole step (L forwards) into a CUDA graph; `replay()` then costs one launch."""
         self.run()                                   # warm: function attributes are set outside capture
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -377,3 +384,6 @@ class SteadyDecode:
 
     def replay(self):
         self.graph.replay()
+
+
+SteadyDecode = SteadyStep

@@ -32,7 +32,8 @@ unsigned long long* debug_timeline() { return g_timeline.load(std::memory_order_
 static std::atomic<int> g_variant{[] { const char* e = getenv("EKV_DECODE_VARIANT"); return e ? atoi(e) : 0; }()};
 static std::atomic<int> g_cluster{[] { const char* e = getenv("EKV_DECODE_CLUSTER"); return e ? atoi(e) : 0; }()};
 static std::atomic<int> g_chunk{[] { const char* e = getenv("EKV_CHUNK_VARIANT"); return e ? atoi(e) : 0; }()};
-int chunk_variant() { return g_chunk.load(std::memory_order_relaxed); }   // 0 = automatic, 1 = tcgen05 path, 2 = mma.sync two-pass path
+int chunk_variant() { return g_chunk.load(std::memory_order_relaxed) & 0xff; }
+int umma_force_cluster() { return (g_chunk.load(std::memory_order_relaxed) >> 8) & 0xff; }   // bits 8-15: forced cluster size   // 0 = automatic, 1 = tcgen05 path, 2 = mma.sync two-pass path
 int decode_variant() { return g_variant.load(std::memory_order_relaxed); }
 int decode_cluster_size() { return g_cluster.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -127,7 +128,7 @@ int64_t ekv_scratch_bytes(const ekv_shape* sh, const ekv_step* st) {
 static int launch_chunk_auto(const KernelArgs& a, const ekv_shape* sh, int32_t kernel, cudaStream_t s) {
   if (kernel == 0 && chunk_tc_shape(sh) && a.scratch) {
     // 16-bit chunks: the tcgen05 / TMEM / tensor-map-TMA cluster kernel; the two-pass mma.sync kernels serve what
-    // it declines (more than 8 x 10 key tiles per unit) and chunk_variant 2 (development / A-B comparisons)
+    // it declines (more than 8 x 12 key tiles per unit) and chunk_variant 2 (development / A-B comparisons)
     int rc = chunk_variant() == 2 ? EKV_ERR_UNSUPPORTED : launch_chunk_umma(a, s);
     if (rc != EKV_ERR_UNSUPPORTED) return rc;
     rc = launch_chunk_tc(a, s);

@@ -13,6 +13,7 @@ struct ChunkPlan {
   // tcgen05 path: 128-key tiles — nct over the cached slots, nnt over the chunk's own keys; a cluster of `splits`
   // CTAs per (unit, 64-row block), `tps` tiles each
   int nct, nnt;
+  int cparts;                                           // column-statistics partials per 64-row block (query groups)
 };
 
 ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys);            // ekv_chunk_tc.cu

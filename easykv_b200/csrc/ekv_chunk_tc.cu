@@ -70,6 +70,7 @@ ChunkPlan make_chunk_plan(int B, int Hkv, int G, int q_len, int n_phys) {
   o = (o + 255) / 256 * 256;
   p.off_opart = o; o += (long long)U * p.splits * p.Rpad * D * 4;
   o = (o + 255) / 256 * 256;
+  p.cparts = 2;
   p.off_cpart = o; o += (long long)U * (2 * p.RB) * p.NEpad * 2 * 4;      // two query halves per row block
   o = (o + 255) / 256 * 256;
   p.off_klj = o; o += (long long)U * p.NEpad * 4;                          // per entry: logical index, the two selection
@@ -446,9 +447,9 @@ template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a
     float ds = 0.f, dsq = 0.f;
     if (st.accumulate) {
       const float2* cg = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(a.scratch) + pl.off_cpart) +
-                         (size_t)unit * (2 * pl.RB) * pl.NEpad;
+                         (size_t)unit * (pl.cparts * pl.RB) * pl.NEpad;
       float s1 = 0.f, s2 = 0.f;
-      for (int r = 0; r < 2 * pl.RB; ++r) { const float2 v = cg[(size_t)r * pl.NEpad + e]; s1 += v.x; s2 += v.y; }
+      for (int r = 0; r < pl.cparts * pl.RB; ++r) { const float2 v = cg[(size_t)r * pl.NEpad + e]; s1 += v.x; s2 += v.y; }
       ds = st.raw_colsum ? s1 : Tr<T>::round_f(s1);         // p.sum(dim=1) is a model-dtype result (easykv.py:450)
       dsq = st.raw_colsum ? s2 : Tr<T>::round_f(s2);        // (p**2).sum(dim=1) likewise (:451)
     }

@@ -15,9 +15,10 @@
 //
 // Exact two-phase softmax (the reference rounds p = dtype(exp(x - max) / sum) AFTER normalising with the global
 // row statistics, so an online rescaling softmax cannot reproduce it bit for bit):
-//   K phase   the CTA's slice of the keys (<= 10 tiles): S^T by tcgen05.mma into a double-buffered TMEM accumulator,
+//   K phase   the CTA's slice of the keys (<= 12 tiles): S^T by tcgen05.mma into a double-buffered TMEM accumulator,
 //             logits rounded at the reference's rounding points (llama_patch.py:201-202), masked, packed to the model
-//             dtype and PARKED IN TENSOR MEMORY (the 320 columns the accumulators leave free hold 10 tiles), row
+//             dtype and PARKED IN TENSOR MEMORY (the 384 columns the S^T double buffer leaves free hold 12 tiles;
+//             the O^T accumulator of the V phase reuses the S^T columns), row
 //             maxima kept as packed 16-bit maxima in registers;
 //   exchange  per-row slice maxima all-to-all over distributed shared memory (st.shared::cluster + remote mbarrier
 //             arrives: only the softmax warps take part, the TMA / MMA warps run ahead into the V stream);
@@ -40,22 +41,25 @@ namespace cu {
 constexpr int D = 128;
 constexpr int TKEYS = 128;               // keys per tile = MMA M
 constexpr int NROWS = 64;                // (query, head) rows per cluster = MMA N
-constexpr int NSOFT = 256;               // 8 softmax warps
-constexpr int NT = NSOFT + 64;           // + TMA producer warp + MMA warp
+// softmax warps: 4 TMEM lane quarters x NSPLIT column groups (NSPLIT = 2: 8 warps x 32 rows per thread,
+// NSPLIT = 4: 16 warps x 16 rows per thread); + TMA producer warp + MMA warp
+__host__ __device__ constexpr int nsoft(int nsplit) { return 128 * nsplit; }
+__host__ __device__ constexpr int nthreads(int nsplit) { return nsoft(nsplit) + 64; }
 constexpr int STAGE_BYTES = 32768;       // one K or V tile: 2 boxes of [128 keys][64 dims]
-constexpr int NSTAGE = 4;
-constexpr int MAX_TILES = 10;            // logits parked in TMEM: 10 tiles x 32 columns
+constexpr int NSTAGE = 5;
+constexpr int MAX_TILES = 12;            // logits parked in TMEM: 12 tiles x 32 columns
 constexpr int MAX_CLUSTER = 8;
-constexpr uint32_t TM_S = 0, TM_O = 128, TM_LOG = 192, TM_COLS = 512;
+// tensor memory columns: S^T double buffer [0,128); O^T reuses [0,64) once the K phase is over; parked logits [128,512)
+constexpr uint32_t TM_S = 0, TM_O = 0, TM_LOG = 128, TM_COLS = 512;
 // shared memory (after 1024-byte alignment)
 constexpr int OFF_RING = 0;
 constexpr int OFF_Q = OFF_RING + NSTAGE * STAGE_BYTES;
 constexpr int OFF_P = OFF_Q + 16384;
 constexpr int OFF_BAR = OFF_P + 2 * 16384;                // 32 mbarriers
 constexpr int OFF_TMEM = OFF_BAR + 32 * 8;
-constexpr int OFF_REDMAX = OFF_TMEM + 16;                 // [8 warps][16] packed maxima
-constexpr int OFF_REDSUM = OFF_REDMAX + 8 * 16 * 4;       // [8 warps][32] sums
-constexpr int OFF_XMAX = OFF_REDSUM + 8 * 32 * 4;         // [MAX_CLUSTER][64]
+constexpr int OFF_REDMAX = OFF_TMEM + 16;                 // [4 lane quarters][64 rows] slice maxima
+constexpr int OFF_REDSUM = OFF_REDMAX + 4 * 64 * 4;       // [4 lane quarters][64 rows] slice sums
+constexpr int OFF_XMAX = OFF_REDSUM + 4 * 64 * 4;         // [MAX_CLUSTER][64]
 constexpr int OFF_XSUM = OFF_XMAX + MAX_CLUSTER * 64 * 4;
 constexpr int OFF_ROWM = OFF_XSUM + MAX_CLUSTER * 64 * 4; // [64] max | [64] sum or 1/sum | [64] rcp(sum)
 constexpr int SMEM_BYTES = OFF_ROWM + 3 * 64 * 4;
@@ -65,6 +69,8 @@ constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_SFULL = 2 * NSTAGE, B_SEMPTY = B_S
               B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_XCH = B_OFULL + 1;
 static_assert(B_XCH + 2 <= 32, "barrier block");
 }  // namespace cu
+
+int umma_force_cluster();      // ekv_api.cu (env EKV_CHUNK_CLUSTER / ekv_debug_set_chunk_variant): 0 = planner's choice
 
 template <typename T> __device__ __forceinline__ uint32_t neg_inf2();
 template <> __device__ __forceinline__ uint32_t neg_inf2<__half>() { return 0xfc00fc00u; }
@@ -79,12 +85,46 @@ template <> __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, 
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <typename T, int G, bool ARITH>
-__global__ void __launch_bounds__(cu::NT, 1)
+template <int N> struct TmemIO;
+template <> struct TmemIO<32> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[32]) { umma::tmem_ld32(a, r); }
+};
+template <> struct TmemIO<16> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[16]) { umma::tmem_ld16(a, r); }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[16]) { umma::tmem_st16(a, r); }
+};
+template <> struct TmemIO<8> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+  }
+};
+
+// a latency-tolerant waiter (the TMA / MMA threads): sleep between polls instead of burning the issue slots of the
+// scheduler partition it shares with two softmax warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <typename T, int G, bool ARITH, int NSPLIT>
+__global__ void __launch_bounds__(cu::nthreads(NSPLIT), 1)
 chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant__ CUtensorMap mapK,
                   const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapKn,
                   const __grid_constant__ CUtensorMap mapVn) {
   using namespace cu;
+  constexpr int NSOFT = nsoft(NSPLIT), NT = nthreads(NSPLIT), NSW = NSOFT / 32;
+  constexpr int CW = NROWS / NSPLIT;                             // rows (TMEM columns) per softmax thread
+  constexpr int CW2 = CW / 2;                                    // ... as packed 16-bit pairs
+  static_assert(CW % G == 0 && CW2 >= 8, "a thread's rows hold whole queries");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* ring = smem + OFF_RING;
@@ -92,7 +132,7 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
   unsigned char* Ps = smem + OFF_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-  uint32_t* redmax = reinterpret_cast<uint32_t*>(smem + OFF_REDMAX);
+  float* redmax = reinterpret_cast<float*>(smem + OFF_REDMAX);
   float* redsum = reinterpret_cast<float*>(smem + OFF_REDSUM);
   float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
   float* xsum = reinterpret_cast<float*>(smem + OFF_XSUM);
@@ -108,23 +148,60 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
   const int b = unit / a.Hkv, h = unit % a.Hkv;
   const int QL = a.q_len, n_phys = a.n_phys;
   const int nct = pl.nct, nt = pl.nct + pl.nnt;
-  const int t0 = min(nt, rank * pl.tps), t1 = min(nt, t0 + pl.tps);
+  const int t0 = (int)((long long)rank * nt / C), t1 = (int)((long long)(rank + 1) * nt / C);   // balanced: sizes differ by <= 1
   const int T_ = t1 - t0;
+  unsigned long long* tl = a.timeline ? a.timeline + (size_t)a.B * a.Hkv * 8 + (size_t)blockIdx.x * 16 : nullptr;
+  auto stamp = [&](int i) { if (tl && tid == 0) tl[i] = global_ns(); };
+  stamp(0);
 
   // ---- setup -----------------------------------------------------------------------------------------------------------
+  auto issue_tile = [&](int it, uint64_t pol) {                   // `it`-th tile of the producer's K-then-V stream
+    const int slot = it % NSTAGE;
+    const int i = it < T_ ? it : it - T_, t = t0 + i;
+    const bool is_new = t >= nct;
+    const CUtensorMap* map = it < T_ ? (is_new ? &mapKn : &mapK) : (is_new ? &mapVn : &mapV);
+    const int row = is_new ? unit * QL + (t - nct) * TKEYS : unit * a.cap + t * TKEYS;
+    unsigned char* dst = ring + (size_t)slot * STAGE_BYTES;
+    mbar_arrive_expect_tx(&bars[B_FULL + slot], STAGE_BYTES);
+    umma::tma_load_2d(dst, map, 0, row, &bars[B_FULL + slot], pol);
+    umma::tma_load_2d(dst + 16384, map, 64, row, &bars[B_FULL + slot], pol);
+  };
+  // several row blocks (clusters) of a unit read the same K / V: keep those lines in L2; a single reader streams
+  uint64_t tma_pol = 0;
   if (tid == NSOFT) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars[B_SFULL + s], 1); mbar_init(&bars[B_SEMPTY + s], NSOFT / 32);
-      mbar_init(&bars[B_PFULL + s], NSOFT / 32); mbar_init(&bars[B_PEMPTY + s], 1);
+      mbar_init(&bars[B_SFULL + s], 1); mbar_init(&bars[B_SEMPTY + s], NSW);
+      mbar_init(&bars[B_PFULL + s], NSW); mbar_init(&bars[B_PEMPTY + s], 1);
       mbar_init(&bars[B_XCH + s], 64 * C);
     }
     mbar_init(&bars[B_OFULL], 1);
     mbar_fence_init();
-    umma::tma_prefetch_desc(&mapK); umma::tma_prefetch_desc(&mapV);
-    umma::tma_prefetch_desc(&mapKn); umma::tma_prefetch_desc(&mapVn);
+    // the first ring-full of tiles needs nothing but these barriers: their HBM latency overlaps the rest of the setup
+    tma_pol = pl.RB > 1 ? umma::l2_policy_evict_last() : l2_policy_evict_first();
+    for (int it = 0; it < NSTAGE && it < 2 * T_; ++it) issue_tile(it, tma_pol);
   }
-  if (warp == NSOFT / 32 + 1) umma::tmem_alloc(tmem_slot, TM_COLS);
+  if (warp == NSW + 1) umma::tmem_alloc(tmem_slot, TM_COLS);
+  // which of this thread's keys (one per tile) are attended: cached slots that are valid (free slots inside
+  // [0, n_phys) are streamed and masked), the chunk's own keys that exist.  All loads issued before first use.
+  const int q4 = warp & 3, cgp = warp >> 2;                      // TMEM lane quarter; column group (softmax warps)
+  const int kl = q4 * 32 + lane;                                 // key inside a tile (softmax) / output dim (epilogue)
+  uint32_t vmask = 0;
+  if (warp < NSW) {
+    const int32_t* lg = a.lidx + (size_t)unit * a.cap;
+    int32_t lv[MAX_TILES];
+#pragma unroll
+    for (int i = 0; i < MAX_TILES; ++i) {
+      const int t = t0 + i, key = t * TKEYS + kl;
+      lv[i] = (i < T_ && t < nct && key < n_phys) ? lg[key] : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_TILES; ++i) {
+      const int t = t0 + i;
+      const bool valid = i < T_ && (t < nct ? lv[i] >= 0 : (t - nct) * TKEYS + kl < QL);
+      vmask |= (valid ? 1u : 0u) << i;
+    }
+  }
   {
     // Q block as the K-major B operand: row `col` of the block is (query qi, head g) with qi = (rb*64 + col) / G
     const T* qg = reinterpret_cast<const T*>(a.q) + (size_t)b * a.H * QL * D;
@@ -142,29 +219,17 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
   cluster_sync_all();                                            // every CTA's barriers exist before any remote arrive
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  stamp(1);
 
-  if (warp == NSOFT / 32) {
+  if (warp == NSW) {
     // ===== TMA producer ==================================================================================================
     if (lane == 0) {
-      // several row blocks (clusters) of a unit read the same K / V: keep those lines in L2; a single reader streams
-      const uint64_t pol = pl.RB > 1 ? umma::l2_policy_evict_last() : l2_policy_evict_first();
-      int it = 0;
-      for (int phase = 0; phase < 2; ++phase) {
-        for (int i = 0; i < T_; ++i, ++it) {
-          const int slot = it % NSTAGE, use = it / NSTAGE;
-          if (use > 0) mbar_wait(&bars[B_EMPTY + slot], (use - 1) & 1);
-          const int t = t0 + i;
-          const bool is_new = t >= nct;
-          const CUtensorMap* map = phase == 0 ? (is_new ? &mapKn : &mapK) : (is_new ? &mapVn : &mapV);
-          const int row = is_new ? unit * QL + (t - nct) * TKEYS : unit * a.cap + t * TKEYS;
-          unsigned char* dst = ring + (size_t)slot * STAGE_BYTES;
-          mbar_arrive_expect_tx(&bars[B_FULL + slot], STAGE_BYTES);
-          umma::tma_load_2d(dst, map, 0, row, &bars[B_FULL + slot], pol);
-          umma::tma_load_2d(dst + 16384, map, 64, row, &bars[B_FULL + slot], pol);
-        }
+      for (int it = NSTAGE; it < 2 * T_; ++it) {
+        mbar_wait_backoff(&bars[B_EMPTY + it % NSTAGE], (it / NSTAGE - 1) & 1, 128);
+        issue_tile(it, tma_pol);
       }
     }
-  } else if (warp == NSOFT / 32 + 1) {
+  } else if (warp == NSW + 1) {
     // ===== MMA issuer ====================================================================================================
     if (lane == 0) {
       const uint32_t id_qk = umma::instr_desc<T>(TKEYS, NROWS, false, false);
@@ -173,8 +238,8 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
       int it = 0;
       for (int i = 0; i < T_; ++i, ++it) {                       // S^T(tile) = K_tile . Q^T
         const int slot = it % NSTAGE, sb = i & 1;
-        mbar_wait(&bars[B_FULL + slot], (it / NSTAGE) & 1);
-        if (i >= 2) mbar_wait(&bars[B_SEMPTY + sb], ((i >> 1) - 1) & 1);
+        mbar_wait_backoff(&bars[B_FULL + slot], (it / NSTAGE) & 1, 32);
+        if (i >= 2) mbar_wait_backoff(&bars[B_SEMPTY + sb], ((i >> 1) - 1) & 1, 32);
         umma::fence_after_sync();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                            // k-step: dims [16j, 16j+16)
@@ -185,10 +250,12 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
         umma::commit(&bars[B_EMPTY + slot]);
         umma::commit(&bars[B_SFULL + sb]);
       }
+      // O^T reuses the columns of the S^T double buffer: the softmax warps have drained every S tile before they
+      // produce the first P tile (program order in those warps), which the first wait below covers
       for (int i = 0; i < T_; ++i, ++it) {                       // O^T += V_tile^T . P^T(tile)
         const int slot = it % NSTAGE, pb = i & 1;
-        mbar_wait(&bars[B_FULL + slot], (it / NSTAGE) & 1);
-        mbar_wait(&bars[B_PFULL + pb], (i >> 1) & 1);
+        mbar_wait_backoff(&bars[B_FULL + slot], (it / NSTAGE) & 1, 32);
+        mbar_wait_backoff(&bars[B_PFULL + pb], (i >> 1) & 1, 32);
         umma::fence_after_sync();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                            // k-step: keys [16j, 16j+16)
@@ -203,92 +270,71 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
     }
   } else {
     // ===== softmax warps: lane of TMEM = key ==================================================================================
-    const int q4 = warp & 3, hf = warp >> 2;                     // TMEM lane quarter; which 32 of the 64 rows
-    const int kl = q4 * 32 + lane;                               // key inside the tile
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
-    const int32_t* lg = a.lidx + (size_t)unit * a.cap;
-    const int qbase = rb * (NROWS / G);                          // first query of this row block
-    auto tile_key = [&](int t, bool& is_new, int& e, bool& valid, int& jn) {
-      is_new = t >= nct;
-      if (is_new) {
-        jn = (t - nct) * TKEYS + kl;                             // index among the chunk's own keys
-        e = n_phys + jn;
-        valid = jn < QL;
-      } else {
-        const int key = t * TKEYS + kl;
-        e = key;
-        jn = -1;
-        valid = key < n_phys && lg[key] >= 0;                    // free slots inside [0, n_phys) are streamed and masked
-      }
-    };
+    const int col0 = cgp * CW;                                   // first of this thread's rows inside the block
+    const int qbase = rb * (NROWS / G) + col0 / G;               // the query of that row
 
     // ---- K phase: logits -> TMEM, running row maxima ------------------------------------------------------------------
-    uint32_t rmax[16];
+    uint32_t rmax[CW2];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) rmax[j] = neg_inf2<T>();
+    for (int j = 0; j < CW2; ++j) rmax[j] = neg_inf2<T>();
     for (int i = 0; i < T_; ++i) {
-      bool is_new, valid;
-      int e, jn;
-      tile_key(t0 + i, is_new, e, valid, jn);
       const int sb = i & 1;
       mbar_wait(&bars[B_SFULL + sb], (i >> 1) & 1);
       umma::fence_after_sync();
-      uint32_t r[32];
-      umma::tmem_ld32(tmem + lane_base + TM_S + sb * NROWS + hf * 32, r);
+      uint32_t r[CW];
+      TmemIO<CW>::ld(tmem + lane_base + TM_S + sb * NROWS + col0, r);
       umma::tmem_wait_ld();
       umma::fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);
-      uint32_t w[16];
+      uint32_t w[CW2];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < CW2; ++j) {
         float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
         round2<T>(x0, x1);                                       // llama_patch.py:201: the matmul's result is a model-dtype tensor
         x0 = ARITH ? __fmul_rn(x0, a.scale_mul) : __fdiv_rn(x0, a.scale_div);    // :202
         x1 = ARITH ? __fmul_rn(x1, a.scale_mul) : __fdiv_rn(x1, a.scale_div);
         w[j] = pack2<T>(x0, x1);
       }
-      if (!valid) {
+      if (!((vmask >> i) & 1u)) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = neg_inf2<T>();
-      } else if (is_new) {                                       // causal among the chunk's own keys (:210-215)
+        for (int j = 0; j < CW2; ++j) w[j] = neg_inf2<T>();
+      } else if (t0 + i >= nct) {                                // causal among the chunk's own keys (:210-215)
+        const int jn = (t0 + i - nct) * TKEYS + kl;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int q0 = qbase + (hf * 32 + 2 * j) / G, q1 = qbase + (hf * 32 + 2 * j + 1) / G;
+        for (int j = 0; j < CW2; ++j) {
+          const int q0 = qbase + (2 * j) / G, q1 = qbase + (2 * j + 1) / G;
           if (jn > q0) w[j] = (w[j] & 0xffff0000u) | (neg_inf2<T>() & 0xffffu);
           if (jn > q1) w[j] = (w[j] & 0x0000ffffu) | (neg_inf2<T>() & 0xffff0000u);
         }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) rmax[j] = max2<T>(rmax[j], w[j]);
-      umma::tmem_st16(tmem + lane_base + TM_LOG + i * 32 + hf * 16, w);
+      for (int j = 0; j < CW2; ++j) rmax[j] = max2<T>(rmax[j], w[j]);
+      TmemIO<CW2>::st(tmem + lane_base + TM_LOG + i * 32 + cgp * CW2, w);
     }
     umma::tmem_wait_st();
+    stamp(2);
 
     // ---- row maxima: lanes -> warps -> cluster ------------------------------------------------------------------------------
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < CW2; ++j) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) rmax[j] = max2<T>(rmax[j], __shfl_xor_sync(0xffffffffu, rmax[j], o));
     }
     if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) redmax[warp * 16 + j] = rmax[j];
+      for (int j = 0; j < CW2; ++j) {
+        const float2 f = Tr<T>::to_f2(rmax[j]);
+        *reinterpret_cast<float2*>(&redmax[q4 * 64 + col0 + 2 * j]) = f;
+      }
     }
     named_bar_sync(1, NSOFT);
-    if (tid < 64) {
-      const int hfr = tid >> 5, j = tid & 31;
-      float m = -INFINITY;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const uint32_t u = redmax[(hfr * 4 + qq) * 16 + (j >> 1)];
-        const float2 f = Tr<T>::to_f2(u);
-        m = fmaxf(m, (j & 1) ? f.y : f.x);
-      }
-      for (int p = 0; p < C; ++p) {
-        st_cluster_f32(map_to_rank(&xmax[rank * 64 + tid], p), m);
-        umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 0], p));
-      }
+    for (int i = tid; i < 64 * C; i += NSOFT) {                   // (row, peer): one remote store + one remote arrive each
+      const int row = i & 63, p = i >> 6;
+      const float m = fmaxf(fmaxf(redmax[row], redmax[64 + row]), fmaxf(redmax[128 + row], redmax[192 + row]));
+      st_cluster_f32(map_to_rank(&xmax[rank * 64 + row], p), m);
+      umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 0], p));
     }
     umma::mbar_wait_cluster(&bars[B_XCH + 0], 0);
     if (tid < 64) {
@@ -297,47 +343,45 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
       rowM[tid] = m;
     }
     named_bar_sync(1, NSOFT);
-    float negM[32];
+    stamp(3);
+    float negM[CW];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(&rowM[hf * 32 + j]);
+    for (int j = 0; j < CW; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(&rowM[col0 + j]);
       negM[j] = -v.x; negM[j + 1] = -v.y; negM[j + 2] = -v.z; negM[j + 3] = -v.w;
     }
 
     // ---- L pass: sum of exp(x - max) over the parked logits ------------------------------------------------------------------
-    float L[32];
+    float L[CW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) L[j] = 0.f;
+    for (int j = 0; j < CW; ++j) L[j] = 0.f;
     for (int i = 0; i < T_; ++i) {
-      uint32_t w[16];
-      umma::tmem_ld16(tmem + lane_base + TM_LOG + i * 32 + hf * 16, w);
+      uint32_t w[CW2];
+      TmemIO<CW2>::ld(tmem + lane_base + TM_LOG + i * 32 + cgp * CW2, w);
       umma::tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < CW2; ++j) {
         const float2 x = Tr<T>::to_f2(w[j]);
         L[2 * j] += expf(x.x + negM[2 * j]);
         L[2 * j + 1] += expf(x.y + negM[2 * j + 1]);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < CW; ++j) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) L[j] += __shfl_xor_sync(0xffffffffu, L[j], o);
     }
     if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) redsum[warp * 32 + j] = L[j];
+      for (int j = 0; j < CW; ++j) redsum[q4 * 64 + col0 + j] = L[j];
     }
     named_bar_sync(1, NSOFT);
-    if (tid < 64) {
-      const int hfr = tid >> 5, j = tid & 31;
-      float s = redsum[(hfr * 4) * 32 + j];
-#pragma unroll
-      for (int qq = 1; qq < 4; ++qq) s += redsum[(hfr * 4 + qq) * 32 + j];
-      for (int p = 0; p < C; ++p) {
-        st_cluster_f32(map_to_rank(&xsum[rank * 64 + tid], p), s);
-        umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 1], p));
-      }
+    stamp(4);
+    for (int i = tid; i < 64 * C; i += NSOFT) {
+      const int row = i & 63, p = i >> 6;
+      const float s = ((redsum[row] + redsum[64 + row]) + redsum[128 + row]) + redsum[192 + row];
+      st_cluster_f32(map_to_rank(&xsum[rank * 64 + row], p), s);
+      umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 1], p));
     }
     umma::mbar_wait_cluster(&bars[B_XCH + 1], 0);
     if (tid < 64) {
@@ -348,13 +392,14 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
       rowR[tid] = __frcp_rn(s);
     }
     named_bar_sync(1, NSOFT);
-    float Rc[ARITH ? 32 : 1];
+    stamp(5);
+    float Rc[ARITH ? CW : 1];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(&rowL[hf * 32 + j]);
+    for (int j = 0; j < CW; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(&rowL[col0 + j]);
       L[j] = v.x; L[j + 1] = v.y; L[j + 2] = v.z; L[j + 3] = v.w;
       if (ARITH) {
-        const float4 u = *reinterpret_cast<const float4*>(&rowR[hf * 32 + j]);
+        const float4 u = *reinterpret_cast<const float4*>(&rowR[col0 + j]);
         Rc[j] = u.x; Rc[j + 1] = u.y; Rc[j + 2] = u.z; Rc[j + 3] = u.w;
       }
     }
@@ -364,18 +409,15 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
     const bool tova = a.st.policy == EKV_POLICY_TOVA;
     const float inv_g = 1.0f / (float)G;
     float2* cg = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_cpart) +
-                 ((size_t)unit * (2 * pl.RB) + 2 * rb + hf) * pl.NEpad;
+                 ((size_t)unit * (pl.cparts * pl.RB) + pl.cparts * rb + cgp) * pl.NEpad;
     for (int i = 0; i < T_; ++i) {
-      bool is_new, valid;
-      int e, jn;
-      tile_key(t0 + i, is_new, e, valid, jn);
-      const int pb = i & 1;
-      uint32_t w[16];
-      umma::tmem_ld16(tmem + lane_base + TM_LOG + i * 32 + hf * 16, w);
+      const int t = t0 + i, pb = i & 1;
+      uint32_t w[CW2];
+      TmemIO<CW2>::ld(tmem + lane_base + TM_LOG + i * 32 + cgp * CW2, w);
       umma::tmem_wait_ld();
-      float pr[32];                                               // the key's probabilities for this CTA's 32 rows
+      float pr[CW];                                               // the key's probabilities for this thread's rows
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < CW2; ++j) {
         const float2 x = Tr<T>::to_f2(w[j]);
         const float e0 = expf(x.x + negM[2 * j]), e1 = expf(x.y + negM[2 * j + 1]);
         float p0 = ARITH ? div_rn_by(e0, L[2 * j], Rc[ARITH ? 2 * j : 0]) : __fmul_rn(e0, L[2 * j]);              // llama_patch.py:218
@@ -384,56 +426,89 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
         pr[2 * j] = p0; pr[2 * j + 1] = p1;
         w[j] = pack2<T>(p0, p1);
       }
-      float cs = 0.f, csq = 0.f;
       if (want_stats) {
         // GQA fold in the model dtype (process_for_mqa_gqa, easykv.py:188-196), then each query's share of the
         // chunk's row sums of p and model-dtype(p^2) (:450-451); tova keeps the last query only (:454)
+        float cs = 0.f, csq = 0.f;
 #pragma unroll
-        for (int u = 0; u < 32 / G; ++u) {                        // one query: its G heads are adjacent rows
+        for (int u = 0; u < CW / G; ++u) {                        // one query: its G heads are adjacent rows
           float fsum = pr[u * G];
 #pragma unroll
           for (int g = 1; g < G; ++g) fsum += pr[u * G + g];
-          const int qi = qbase + hf * (32 / G) + u;
+          const int qi = qbase + u;
           if (qi < QL && (!tova || qi == QL - 1)) {
             const float pf = G == 1 ? fsum : Tr<T>::round_f(__fmul_rn(fsum, inv_g));
             cs += pf;
             csq += Tr<T>::round_f(__fmul_rn(pf, pf));
           }
         }
+        const int e = t < nct ? t * TKEYS + kl : n_phys + (t - nct) * TKEYS + kl;
+        if (t < nct ? e < n_phys : e < n_phys + QL) cg[e] = make_float2(cs, csq);
       }
-      if (want_stats && (is_new ? jn < QL : e < n_phys)) cg[e] = make_float2(cs, csq);
       if (i >= 2) mbar_wait(&bars[B_PEMPTY + pb], ((i >> 1) - 1) & 1);
       unsigned char* prow = Ps + pb * 16384;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(prow + umma::swz128(kl, hf * 4 + c)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      for (int c = 0; c < CW / 8; ++c)
+        *reinterpret_cast<uint4*>(prow + umma::swz128(kl, cgp * (CW / 8) + c)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
       umma::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_PFULL + pb]);
     }
+    stamp(6);
 
     // ---- epilogue: this CTA's partial O^T -> scratch ---------------------------------------------------------------------------
     float* op = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.scratch) + pl.off_opart) +
-                (((size_t)unit * pl.splits + rank) * pl.Rpad + rb * NROWS + hf * 32) * D + kl;     // kl = output dim here
+                (((size_t)unit * pl.splits + rank) * pl.Rpad + rb * NROWS + col0) * D + kl;     // kl = output dim here
     if (T_ > 0) {
       mbar_wait(&bars[B_OFULL], 0);
       umma::fence_after_sync();
-      uint32_t r[32];
-      umma::tmem_ld32(tmem + lane_base + TM_O + hf * 32, r);
+      uint32_t r[CW];
+      TmemIO<CW>::ld(tmem + lane_base + TM_O + col0, r);
       umma::tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) op[(size_t)j * D] = __uint_as_float(r[j]);
+      for (int j = 0; j < CW; ++j) op[(size_t)j * D] = __uint_as_float(r[j]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) op[(size_t)j * D] = 0.f;
+      for (int j = 0; j < CW; ++j) op[(size_t)j * D] = 0.f;
     }
+    stamp(7);
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == NSOFT / 32 + 1) umma::tmem_dealloc(tmem, TM_COLS);
+  if (warp == NSW + 1) umma::tmem_dealloc(tmem, TM_COLS);
 }
 
 // ---- plan ----------------------------------------------------------------------------------------------------------------
+// How many clusters of `c` CTAs of this kernel the device can hold at once (one CTA per SM; a cluster must fit one GPC,
+// so the answer is NOT sms / c: 8-CTA clusters pack 13-16 per B200, 6-CTA clusters ~24, pairs 74).  Asked of the driver
+// once per size; a fixed table stands in where no device is present (ekv_scratch_bytes is host-only).
+static int concurrent_clusters(int c, int sms) {
+  static int cached[cu::MAX_CLUSTER + 1] = {0};
+  if (c < 1 || c > cu::MAX_CLUSTER) return 1;
+  if (cached[c]) return cached[c];
+  static const int fallback[cu::MAX_CLUSTER + 1] = {0, 148, 74, 48, 33, 26, 24, 16, 14};
+  int n = 0, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    auto kern = chunk_umma_kernel<__half, 1, true, 4>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cu::SMEM_ALLOC) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(c * 4096), 1, 1);
+      cfg.blockDim = dim3(cu::nthreads(4), 1, 1);
+      cfg.dynamicSmemBytes = cu::SMEM_ALLOC;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+  }
+  if (n <= 0) n = fallback[c] * sms / 148;
+  if (n < 1) n = 1;
+  cached[c] = n;
+  return n;
+}
+
 bool make_umma_plan(int B, int Hkv, int G, int q_len, int n_phys, int sms, ChunkPlan& out) {
   using namespace cu;
   ChunkPlan p = make_chunk_plan(B, Hkv, G, q_len, n_phys);       // R, RB, Rpad, NE, NEpad and the scratch carve-up
@@ -443,15 +518,16 @@ bool make_umma_plan(int B, int Hkv, int G, int q_len, int n_phys, int sms, Chunk
   const int cmin = (nt + MAX_TILES - 1) / MAX_TILES;
   if (cmin > MAX_CLUSTER) return false;
   const long long groups = (long long)B * Hkv * p.RB;
+  const int force = umma_force_cluster();
   int best = 0;
   double best_cost = 0;
   for (int c = cmin; c <= MAX_CLUSTER; ++c) {
-    if (c != 1 && c != 2 && c != 4 && c != 8) continue;          // power-of-two clusters pack the GPCs best
+    if (force && c != force) continue;
     const int tps = (nt + c - 1) / c;
     if (tps > MAX_TILES) continue;
-    const long long ctas = groups * c;
-    const double waves = (double)((ctas + sms - 1) / sms);
-    const double cost = waves * (tps + 2.5);                     // per-CTA fixed work ~ 2.5 tiles (setup, exchanges, epilogue)
+    const double waves = (double)((groups + concurrent_clusters(c, sms) - 1) / concurrent_clusters(c, sms));
+    // per-CTA fixed work (setup, two exchanges, epilogue) ~ 4 tile-times; more for larger clusters (exchange skew)
+    const double cost = waves * (tps + 3.5 + 0.25 * c);
     if (!best || cost < best_cost - 1e-9) { best = c; best_cost = cost; }
   }
   if (!best) return false;
@@ -463,7 +539,8 @@ bool make_umma_plan(int B, int Hkv, int G, int q_len, int n_phys, int sms, Chunk
   p.off_stats = 0;
   p.off_opart = o; o += U * p.splits * p.Rpad * D * 4;
   o = (o + 255) / 256 * 256;
-  p.off_cpart = o; o += U * (2 * p.RB) * p.NEpad * 2 * 4;
+  p.cparts = 4;
+  p.off_cpart = o; o += U * (p.cparts * p.RB) * p.NEpad * 2 * 4;
   o = (o + 255) / 256 * 256;
   p.off_klj = o; o += U * p.NEpad * 4;
   p.off_ka = o; o += U * p.NEpad * 4;
@@ -484,8 +561,10 @@ static int device_sms() {
   return sm_count[dev];
 }
 int umma_sm_count() { return device_sms(); }
+// softmax column groups per CTA: chunk_variant 3 = 2 groups (8 warps x 32 rows per thread), otherwise 4 (16 warps x 16)
+static int umma_nsplit() { return chunk_variant() == 3 ? 2 : 4; }
 
-template <typename T, int G, bool ARITH>
+template <typename T, int G, bool ARITH, int NSPLIT>
 static int launch_umma_k(const KernelArgs& a, const ChunkPlan& pl, const CUtensorMap* maps, cudaStream_t stream) {
   using namespace cu;
   static thread_local int configured[16] = {0};
@@ -494,13 +573,13 @@ static int launch_umma_k(const KernelArgs& a, const ChunkPlan& pl, const CUtenso
   if (dev >= 16) dev = 15;
   cudaError_t err;
   if (!configured[dev]) {
-    err = cudaFuncSetAttribute(chunk_umma_kernel<T, G, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    err = cudaFuncSetAttribute(chunk_umma_kernel<T, G, ARITH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(chunk_umma)", err);
     configured[dev] = 1;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(a.B * a.Hkv * pl.RB * pl.splits), 1, 1);
-  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.blockDim = dim3(nthreads(NSPLIT), 1, 1);
   cfg.dynamicSmemBytes = SMEM_ALLOC;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -510,7 +589,7 @@ static int launch_umma_k(const KernelArgs& a, const ChunkPlan& pl, const CUtenso
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  err = cudaLaunchKernelEx(&cfg, chunk_umma_kernel<T, G, ARITH>, a, pl, maps[0], maps[1], maps[2], maps[3]);
+  err = cudaLaunchKernelEx(&cfg, chunk_umma_kernel<T, G, ARITH, NSPLIT>, a, pl, maps[0], maps[1], maps[2], maps[3]);
   if (err != cudaSuccess) return set_cuda_error("chunk_umma_kernel launch", err);
   count_launch();
   return EKV_OK;
@@ -527,7 +606,13 @@ template <typename T, int G> static int launch_umma_tg(const KernelArgs& a, cuda
   if (!rc) rc = make_tensor_map_rows128(&maps[2], a.k_new, rows_n, cu::TKEYS, a.dtype);
   if (!rc) rc = make_tensor_map_rows128(&maps[3], a.v_new, rows_n, cu::TKEYS, a.dtype);
   if (rc) return rc;
-  rc = a.st.arith ? launch_umma_k<T, G, true>(a, pl, maps, stream) : launch_umma_k<T, G, false>(a, pl, maps, stream);
+  pl.cparts = umma_nsplit();
+  if (pl.cparts == 4)
+    rc = a.st.arith ? launch_umma_k<T, G, true, 4>(a, pl, maps, stream) : launch_umma_k<T, G, false, 4>(a, pl, maps, stream);
+  else {
+    pl.cparts = 2;
+    rc = a.st.arith ? launch_umma_k<T, G, true, 2>(a, pl, maps, stream) : launch_umma_k<T, G, false, 2>(a, pl, maps, stream);
+  }
   if (rc) return rc;
   return launch_chunk_finish(a, pl, stream);
 }
@@ -543,7 +628,7 @@ template <typename T> static int launch_umma_t(const KernelArgs& a, cudaStream_t
 }
 
 // 16-bit dtypes, head_dim 128, needs scratch; EKV_ERR_UNSUPPORTED when the key range does not fit 8 CTAs x 10 tiles
-// (more than 10 240 cached slots + the chunk): the caller then takes the two-pass mma.sync path.
+// (more than 12 288 cached slots + the chunk): the caller then takes the two-pass mma.sync path.
 int launch_chunk_umma(const KernelArgs& a, cudaStream_t stream) {
   if (a.d != cu::D || !a.scratch || a.q_len < 1) return EKV_ERR_UNSUPPORTED;
   // the tensor maps address rows of 256 bytes from 16-byte aligned bases

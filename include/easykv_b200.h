@@ -225,7 +225,8 @@ EKV_API void ekv_debug_set_timeline(void* device_buffer);
 EKV_API void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size);
 
 /* Strided-chunk kernel selection (development / test hook): 0 = automatic (the tcgen05 cluster kernel, falling back to
- * the two-pass mma.sync kernels for key ranges beyond 8 x 10 tiles), 1 = same as 0, 2 = always the mma.sync kernels. */
+ * the two-pass mma.sync kernels for key ranges beyond 8 x 12 tiles), 2 = always the mma.sync kernels, 3 = the tcgen05 kernel
+ * with 8 instead of 16 softmax warps; bits 8-15: force this cluster size (0 = the planner's choice). */
 EKV_API void ekv_debug_set_chunk_variant(int32_t chunk_variant);
 
 /* Primitive-level probe of the tensor-core path the strided-prefill chunk kernel is built from (development / test

@@ -25,6 +25,7 @@ from __future__ import annotations
 import contextlib
 import io
 import sys
+import time
 
 import torch
 
@@ -170,7 +171,7 @@ def _patched(model, trace: Trace, record_tensors=True):
     def model_fwd(self, *a, **k):
         ids = k.get("input_ids", a[0] if a else None)
         pos = k.get("position_ids")
-        trace.forwards.append(dict(q_len=int(ids.shape[1]), layers=[],
+        trace.forwards.append(dict(q_len=int(ids.shape[1]), layers=[], t_begin=time.perf_counter(),
                                    input_ids=ids[0].detach().cpu().clone(),
                                    position_ids=None if pos is None else pos[0].detach().cpu().clone()))
         out = orig_model_fwd(self, *a, **k)

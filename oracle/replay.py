@@ -87,6 +87,7 @@ class Report:
     victim_mismatch: list = field(default_factory=list)   # (fwd, layer, ref ids, got ids, margin)
     tie_ambiguous: list = field(default_factory=list)     # same, but the reference's margin was 0
     max_out_err: float = 0.0
+    max_out_rel: float = 0.0                              # error relative to max(1, largest |reference output|) of the forward
     final_cache_equal: bool = True
     min_margin: tuple = (float("inf"), float("inf"))
     retained: int = 0
@@ -179,7 +180,9 @@ def replay(name, engine_factory, resync=True, shadow=None, tie_eps=0.0, golden_d
             force = ref_ids if resync else None
             out, vic = eng.forward(l, st, q, k, v, force=force, **skw)
             o_ref = o.view(ql, H, d).transpose(0, 1).float()
-            rep.max_out_err = max(rep.max_out_err, (out.float().cpu() - o_ref).abs().max().item())
+            err = (out.float().cpu() - o_ref).abs().max().item()
+            rep.max_out_err = max(rep.max_out_err, err)
+            rep.max_out_rel = max(rep.max_out_rel, err / max(1.0, o_ref.abs().max().item()))
             margin = None
             meng = sh if sh is not None else (eng if hasattr(eng, "margin") else None)
             if sh is not None:

@@ -67,7 +67,9 @@ def _check(rep, name):
     assert len(rep.victim_mismatch) + len(rep.tie_ambiguous) <= (max(2, rep.n_events // 2) if bf16 else max(1, rep.n_events // 20)), \
         (len(rep.victim_mismatch), len(rep.tie_ambiguous), rep.n_events)
     assert rep.final_cache_equal
-    assert rep.max_out_err <= (8e-3 if bf16 else 1e-3), rep.max_out_err
+    # 1e-3 (fp16) relative to the outputs' scale: these random-weight models produce |out| up to ~4, where one fp16
+    # ulp is already 2e-3 .. 4e-3
+    assert rep.max_out_rel <= (8e-3 if bf16 else 1e-3), (rep.max_out_rel, rep.max_out_err)
 
 
 @pytest.mark.parametrize("name", list(CASES))
