@@ -49,6 +49,7 @@ constexpr int STAGE_BYTES = 32768;       // one K or V tile: 2 boxes of [128 key
 constexpr int NSTAGE = 5;
 constexpr int MAX_TILES = 12;            // logits parked in TMEM: 12 tiles x 32 columns
 constexpr int MAX_CLUSTER = 8;
+constexpr float LOG2E = 1.4426950408889634f;
 // tensor memory columns: S^T double buffer [0,128); O^T reuses [0,64) once the K phase is over; parked logits [128,512)
 constexpr uint32_t TM_S = 0, TM_O = 0, TM_LOG = 128, TM_COLS = 512;
 // shared memory (after 1024-byte alignment)
@@ -59,15 +60,23 @@ constexpr int OFF_BAR = OFF_P + 2 * 16384;                // 32 mbarriers
 constexpr int OFF_TMEM = OFF_BAR + 32 * 8;
 constexpr int OFF_REDMAX = OFF_TMEM + 16;                 // [4 lane quarters][64 rows] slice maxima
 constexpr int OFF_REDSUM = OFF_REDMAX + 4 * 64 * 4;       // [4 lane quarters][64 rows] slice sums
-constexpr int OFF_XMAX = OFF_REDSUM + 4 * 64 * 4;         // [MAX_CLUSTER][64]
+constexpr int OFF_REDM0 = OFF_REDSUM + 4 * 64 * 4;        // [4 lane quarters][64 rows] reference points of the slice sums
+constexpr int OFF_XMAX = OFF_REDM0 + 4 * 64 * 4;          // [MAX_CLUSTER][64]
 constexpr int OFF_XSUM = OFF_XMAX + MAX_CLUSTER * 64 * 4;
-constexpr int OFF_ROWM = OFF_XSUM + MAX_CLUSTER * 64 * 4; // [64] max | [64] sum or 1/sum | [64] rcp(sum)
-constexpr int SMEM_BYTES = OFF_ROWM + 3 * 64 * 4;
+constexpr int OFF_XM0 = OFF_XSUM + MAX_CLUSTER * 64 * 4;
+constexpr int OFF_ROWM = OFF_XM0 + MAX_CLUSTER * 64 * 4;  // [64] max | [64] sum or 1/sum | [64] rcp(sum) | flag
+constexpr int OFF_LIDX = OFF_ROWM + 3 * 64 * 4 + 16;        // [MAX_TILES][128] the CTA's slice of the slot map (bulk copy)
+// the exact pass's sums get their own buffer (a fast peer may already be sending them while a slow CTA still reads the
+// first exchange): the slot-map slice, which is dead once the validity masks are built, before the first exchange
+constexpr int OFF_XSUM2 = OFF_LIDX;
+constexpr int SMEM_BYTES = OFF_LIDX + MAX_TILES * TKEYS * 4;
+static_assert(MAX_CLUSTER * 64 * 4 <= MAX_TILES * TKEYS * 4, "xsum2 aliases the slot-map slice");
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
+static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory per CTA");
 // barrier indices
 constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_SFULL = 2 * NSTAGE, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2,
-              B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_XCH = B_OFULL + 1;
-static_assert(B_XCH + 2 <= 32, "barrier block");
+              B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_XCH = B_OFULL + 1, B_LIDX = B_XCH + 2;
+static_assert(B_LIDX + 1 <= 32, "barrier block");
 }  // namespace cu
 
 int umma_force_cluster();      // ekv_api.cu (env EKV_CHUNK_CLUSTER / ekv_debug_set_chunk_variant): 0 = planner's choice
@@ -109,6 +118,13 @@ template <> struct TmemIO<8> {
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
+// 2^x, hardware approximation (MUFU.EX2, ~2^-22 relative): used only for the softmax DENOMINATORS, which are sums of
+// hundreds to thousands of terms whose summation order alone moves them by as much; the numerators use expf
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -136,9 +152,14 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
   float* redsum = reinterpret_cast<float*>(smem + OFF_REDSUM);
   float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
   float* xsum = reinterpret_cast<float*>(smem + OFF_XSUM);
+  float* redm0 = reinterpret_cast<float*>(smem + OFF_REDM0);
+  float* xm0 = reinterpret_cast<float*>(smem + OFF_XM0);
+  float* xsum2 = reinterpret_cast<float*>(smem + OFF_XSUM2);
   float* rowM = reinterpret_cast<float*>(smem + OFF_ROWM);
   float* rowL = rowM + 64;
   float* rowR = rowL + 64;
+  int* slow_flag = reinterpret_cast<int*>(rowR + 64);
+  int32_t* lidx_s = reinterpret_cast<int32_t*>(smem + OFF_LIDX);              // a row's one-pass denominator was unusable: exact L pass
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = pl.splits;
@@ -176,47 +197,56 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
       mbar_init(&bars[B_XCH + s], 64 * C);
     }
     mbar_init(&bars[B_OFULL], 1);
+    mbar_init(&bars[B_LIDX], 1);
+    *slow_flag = 0;
     mbar_fence_init();
+    {
+      // this CTA's slice of the slot map, one bulk copy ahead of the tiles (a per-thread load issued into the opening
+      // burst of tile requests was measured at ~4 us): ints [t0*128, +ncached) of the unit, clipped to the capacity
+      const int first = t0 * TKEYS;
+      int cnt = min(t1, nct) * TKEYS - first;
+      if (cnt > a.cap - first) cnt = a.cap - first;              // cap is a multiple of 8 ints: 16-byte granularity holds
+      if (cnt > 0) {
+        cnt = (cnt + 3) & ~3;
+        if (cnt > a.cap - first) cnt = (a.cap - first) & ~3;
+      }
+      if (cnt > 0) {
+        mbar_arrive_expect_tx(&bars[B_LIDX], (uint32_t)cnt * 4u);
+        tma_bulk_g2s(lidx_s, a.lidx + (size_t)unit * a.cap + first, (uint32_t)cnt * 4u, &bars[B_LIDX], l2_policy_evict_first());
+      } else {
+        mbar_arrive(&bars[B_LIDX]);
+      }
+    }
     // the first ring-full of tiles needs nothing but these barriers: their HBM latency overlaps the rest of the setup
     tma_pol = pl.RB > 1 ? umma::l2_policy_evict_last() : l2_policy_evict_first();
     for (int it = 0; it < NSTAGE && it < 2 * T_; ++it) issue_tile(it, tma_pol);
+    if (tl) tl[8] = global_ns();
   }
   if (warp == NSW + 1) umma::tmem_alloc(tmem_slot, TM_COLS);
-  // which of this thread's keys (one per tile) are attended: cached slots that are valid (free slots inside
-  // [0, n_phys) are streamed and masked), the chunk's own keys that exist.  All loads issued before first use.
   const int q4 = warp & 3, cgp = warp >> 2;                      // TMEM lane quarter; column group (softmax warps)
   const int kl = q4 * 32 + lane;                                 // key inside a tile (softmax) / output dim (epilogue)
-  uint32_t vmask = 0;
-  if (warp < NSW) {
-    const int32_t* lg = a.lidx + (size_t)unit * a.cap;
-    int32_t lv[MAX_TILES];
-#pragma unroll
-    for (int i = 0; i < MAX_TILES; ++i) {
-      const int t = t0 + i, key = t * TKEYS + kl;
-      lv[i] = (i < T_ && t < nct && key < n_phys) ? lg[key] : -1;
-    }
-#pragma unroll
-    for (int i = 0; i < MAX_TILES; ++i) {
-      const int t = t0 + i;
-      const bool valid = i < T_ && (t < nct ? lv[i] >= 0 : (t - nct) * TKEYS + kl < QL);
-      vmask |= (valid ? 1u : 0u) << i;
-    }
-  }
-  {
-    // Q block as the K-major B operand: row `col` of the block is (query qi, head g) with qi = (rb*64 + col) / G
+  if (warp == NSW + 1) {
+    // Q block as the K-major B operand, staged by the MMA warp itself with asynchronous 16-byte copies (nobody else
+    // reads it; the copies overlap the first K tile's HBM latency): row `col` of the block is (query qi, head g)
+    // with qi = (rb*64 + col) / G
     const T* qg = reinterpret_cast<const T*>(a.q) + (size_t)b * a.H * QL * D;
-    for (int i = tid; i < NROWS * 16; i += NT) {
+    for (int i = lane; i < NROWS * 16; i += 32) {
       const int col = i >> 4, c = i & 15;
       const int r = rb * NROWS + col, qi = r / G, g = r % G;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (qi < QL) v = reinterpret_cast<const uint4*>(qg + ((size_t)(h * G + g) * QL + qi) * D)[c];
-      *reinterpret_cast<uint4*>(Qs + (c >> 3) * 8192 + umma::swz128(col, c & 7)) = v;
+      unsigned char* dst = Qs + (c >> 3) * 8192 + umma::swz128(col, c & 7);
+      if (qi < QL) cp_async16(dst, reinterpret_cast<const uint4*>(qg + ((size_t)(h * G + g) * QL + qi) * D) + c);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
+    cp_async_commit();
   }
-  umma::fence_proxy_async_smem();
   umma::fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();                                            // every CTA's barriers exist before any remote arrive
+  stamp(9);
+  __syncthreads();                                               // barriers initialised, TMEM base published
+  stamp(10);
+  // every CTA's barriers exist before any REMOTE arrive: arrive now, wait only right before the exchange
+  // (relaxed: the barrier initialisations were published by fence.mbarrier_init.release.cluster; a releasing arrive
+  // would also drain this thread's other traffic — measured at ~3 us here)
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   stamp(1);
@@ -231,6 +261,9 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
     }
   } else if (warp == NSW + 1) {
     // ===== MMA issuer ====================================================================================================
+    cp_async_wait<0>();
+    umma::fence_proxy_async_smem();                              // this lane's Q chunks -> visible to the tensor core
+    __syncwarp();
     if (lane == 0) {
       const uint32_t id_qk = umma::instr_desc<T>(TKEYS, NROWS, false, false);
       const uint32_t id_pv = umma::instr_desc<T>(D, NROWS, true, true);
@@ -273,11 +306,31 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const int col0 = cgp * CW;                                   // first of this thread's rows inside the block
     const int qbase = rb * (NROWS / G) + col0 / G;               // the query of that row
+    // which of this thread's keys (one per tile) are attended: cached slots that are valid (free slots inside
+    // [0, n_phys) are streamed and masked), the chunk's own keys that exist
+    uint32_t vmask = 0;
+    mbar_wait(&bars[B_LIDX], 0);
+#pragma unroll
+    for (int i = 0; i < MAX_TILES; ++i) {
+      const int t = t0 + i, key = t * TKEYS + kl;
+      const bool valid = i < T_ && (t < nct ? (key < n_phys && key < a.cap && lidx_s[i * TKEYS + kl] >= 0) : (t - nct) * TKEYS + kl < QL);
+      vmask |= (valid ? 1u : 0u) << i;
+    }
 
-    // ---- K phase: logits -> TMEM, running row maxima ------------------------------------------------------------------
+    // ---- K phase: logits -> TMEM, running row maxima, one-pass denominators ---------------------------------------------
+    // The denominator sum_k exp(x_k - M) needs the global row maximum M, which is only known after the K phase.  The
+    // K phase is HBM-bound (the ALUs idle), so every warp already sums exp(x - m0) against ITS OWN reference point
+    // m0 = the maximum of the row over the warp's 32 keys of its first tile; the slices are rescaled by exp(m0 - M)
+    // when they are combined (one cluster exchange instead of two, and no second sweep over the logits).  Each term
+    // carries one more rounding than exp(x - M) would — the same order as the freedom of the summation order itself
+    // (ATen's CUDA softmax sums in yet another order).  A row whose logits run away from m0 by more than 2^100 (or whose
+    // first tile is fully masked and whose logits are tiny) is detected and the whole cluster takes the exact L pass.
     uint32_t rmax[CW2];
+    float negm0[CW], Ssum[CW];
 #pragma unroll
     for (int j = 0; j < CW2; ++j) rmax[j] = neg_inf2<T>();
+#pragma unroll
+    for (int j = 0; j < CW; ++j) { negm0[j] = 0.f; Ssum[j] = 0.f; }
     for (int i = 0; i < T_; ++i) {
       const int sb = i & 1;
       mbar_wait(&bars[B_SFULL + sb], (i >> 1) & 1);
@@ -309,38 +362,80 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
           if (jn > q1) w[j] = (w[j] & 0x0000ffffu) | (neg_inf2<T>() & 0xffff0000u);
         }
       }
-#pragma unroll
-      for (int j = 0; j < CW2; ++j) rmax[j] = max2<T>(rmax[j], w[j]);
       TmemIO<CW2>::st(tmem + lane_base + TM_LOG + i * 32 + cgp * CW2, w);
+      if (i == 0) {                                              // the warp's reference points
+#pragma unroll
+        for (int j = 0; j < CW2; ++j) {
+          uint32_t m = w[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = max2<T>(m, __shfl_xor_sync(0xffffffffu, m, o));
+          const float2 f = Tr<T>::to_f2(m);
+          negm0[2 * j] = f.x == -INFINITY ? 0.f : -f.x * LOG2E;          // kept pre-scaled: exp(x - m0) = 2^(x*log2e - m0*log2e)
+          negm0[2 * j + 1] = f.y == -INFINITY ? 0.f : -f.y * LOG2E;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CW2; ++j) {
+        rmax[j] = max2<T>(rmax[j], w[j]);
+        const float2 x = Tr<T>::to_f2(w[j]);
+        Ssum[2 * j] += ex2_approx(fmaf(x.x, LOG2E, negm0[2 * j]));
+        Ssum[2 * j + 1] += ex2_approx(fmaf(x.y, LOG2E, negm0[2 * j + 1]));
+      }
     }
     umma::tmem_wait_st();
     stamp(2);
 
-    // ---- row maxima: lanes -> warps -> cluster ------------------------------------------------------------------------------
+    // ---- row statistics: lanes -> warps -> cluster (one exchange) ------------------------------------------------------------
 #pragma unroll
     for (int j = 0; j < CW2; ++j) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) rmax[j] = max2<T>(rmax[j], __shfl_xor_sync(0xffffffffu, rmax[j], o));
+    }
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) Ssum[j] += __shfl_xor_sync(0xffffffffu, Ssum[j], o);
     }
     if (lane == 0) {
 #pragma unroll
       for (int j = 0; j < CW2; ++j) {
         const float2 f = Tr<T>::to_f2(rmax[j]);
         *reinterpret_cast<float2*>(&redmax[q4 * 64 + col0 + 2 * j]) = f;
+        // usable iff the slice's logits stayed within e^+-80 of its reference point (an all-masked slice sums to 0)
+        const float d0 = fmaf(f.x, LOG2E, negm0[2 * j]), d1 = fmaf(f.y, LOG2E, negm0[2 * j + 1]);      // in powers of two
+        const bool ok0 = f.x == -INFINITY || (d0 < 100.f && d0 > -100.f), ok1 = f.y == -INFINITY || (d1 < 100.f && d1 > -100.f);
+        redsum[q4 * 64 + col0 + 2 * j] = ok0 ? Ssum[2 * j] : __int_as_float(0x7fc00000);
+        redsum[q4 * 64 + col0 + 2 * j + 1] = ok1 ? Ssum[2 * j + 1] : __int_as_float(0x7fc00000);
+        redm0[q4 * 64 + col0 + 2 * j] = -negm0[2 * j];               // reference points travel in log2 units
+        redm0[q4 * 64 + col0 + 2 * j + 1] = -negm0[2 * j + 1];
       }
     }
     named_bar_sync(1, NSOFT);
-    for (int i = tid; i < 64 * C; i += NSOFT) {                   // (row, peer): one remote store + one remote arrive each
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // (arrived during setup: every peer's barriers exist)
+    for (int i = tid; i < 64 * C; i += NSOFT) {                   // (row, peer): three remote stores + one remote arrive each
       const int row = i & 63, p = i >> 6;
       const float m = fmaxf(fmaxf(redmax[row], redmax[64 + row]), fmaxf(redmax[128 + row], redmax[192 + row]));
+      const float z = fmaxf(fmaxf(redm0[row], redm0[64 + row]), fmaxf(redm0[128 + row], redm0[192 + row]));
+      float sacc = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) sacc += redsum[qq * 64 + row] * ex2_approx(redm0[qq * 64 + row] - z);   // factors <= 1
       st_cluster_f32(map_to_rank(&xmax[rank * 64 + row], p), m);
+      st_cluster_f32(map_to_rank(&xm0[rank * 64 + row], p), z);
+      st_cluster_f32(map_to_rank(&xsum[rank * 64 + row], p), sacc);
       umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 0], p));
     }
     umma::mbar_wait_cluster(&bars[B_XCH + 0], 0);
     if (tid < 64) {
-      float m = xmax[tid];
-      for (int p = 1; p < C; ++p) m = fmaxf(m, xmax[p * 64 + tid]);
+      float m = xmax[tid], z = xm0[tid];
+      for (int p = 1; p < C; ++p) { m = fmaxf(m, xmax[p * 64 + tid]); z = fmaxf(z, xm0[p * 64 + tid]); }
+      float sacc = 0.f;
+      for (int p = 0; p < C; ++p) sacc += xsum[p * 64 + tid] * ex2_approx(xm0[p * 64 + tid] - z);   // rank order on every CTA
+      float s = sacc * ex2_approx(z - m * LOG2E);                 // z <= m*log2e: the reference points are maxima of subsets
+      if (m == -INFINITY) s = 1.f;                                // a row with no key at all (padding): p = 0 whatever s
+      if (!(s > 0.f) || !(s < INFINITY)) atomicOr(slow_flag, 1);  // NaN / 0 / inf: this cluster sums exactly (below)
       rowM[tid] = m;
+      rowL[tid] = ARITH ? s : __fdiv_rn(1.0f, s);
+      rowR[tid] = __frcp_rn(s);
     }
     named_bar_sync(1, NSOFT);
     stamp(3);
@@ -350,9 +445,9 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
       const float4 v = *reinterpret_cast<const float4*>(&rowM[col0 + j]);
       negM[j] = -v.x; negM[j + 1] = -v.y; negM[j + 2] = -v.z; negM[j + 3] = -v.w;
     }
-
-    // ---- L pass: sum of exp(x - max) over the parked logits ------------------------------------------------------------------
     float L[CW];
+    if (*slow_flag) {
+    // ---- exact L pass (slow path): sum of exp(x - max) over the parked logits, second exchange -------------------------------
 #pragma unroll
     for (int j = 0; j < CW; ++j) L[j] = 0.f;
     for (int i = 0; i < T_; ++i) {
@@ -380,19 +475,20 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
     for (int i = tid; i < 64 * C; i += NSOFT) {
       const int row = i & 63, p = i >> 6;
       const float s = ((redsum[row] + redsum[64 + row]) + redsum[128 + row]) + redsum[192 + row];
-      st_cluster_f32(map_to_rank(&xsum[rank * 64 + row], p), s);
+      st_cluster_f32(map_to_rank(&xsum2[rank * 64 + row], p), s);
       umma::mbar_arrive_remote(map_to_rank(&bars[B_XCH + 1], p));
     }
     umma::mbar_wait_cluster(&bars[B_XCH + 1], 0);
     if (tid < 64) {
-      float s = xsum[tid];
-      for (int p = 1; p < C; ++p) s += xsum[p * 64 + tid];        // rank order on every CTA: identical denominators
+      float s = xsum2[tid];
+      for (int p = 1; p < C; ++p) s += xsum2[p * 64 + tid];       // rank order on every CTA: identical denominators
       if (s == 0.f) s = 1.f;
       rowL[tid] = ARITH ? s : __fdiv_rn(1.0f, s);
       rowR[tid] = __frcp_rn(s);
     }
     named_bar_sync(1, NSOFT);
     stamp(5);
+    }
     float Rc[ARITH ? CW : 1];
 #pragma unroll
     for (int j = 0; j < CW; j += 4) {
@@ -630,7 +726,7 @@ template <typename T> static int launch_umma_t(const KernelArgs& a, cudaStream_t
 // 16-bit dtypes, head_dim 128, needs scratch; EKV_ERR_UNSUPPORTED when the key range does not fit 8 CTAs x 10 tiles
 // (more than 12 288 cached slots + the chunk): the caller then takes the two-pass mma.sync path.
 int launch_chunk_umma(const KernelArgs& a, cudaStream_t stream) {
-  if (a.d != cu::D || !a.scratch || a.q_len < 1) return EKV_ERR_UNSUPPORTED;
+  if (a.d != cu::D || !a.scratch || a.q_len < 1 || (a.cap & 3)) return EKV_ERR_UNSUPPORTED;   // (bulk copy of the slot map: 16-byte rows)
   // the tensor maps address rows of 256 bytes from 16-byte aligned bases
   if ((reinterpret_cast<uintptr_t>(a.K) | reinterpret_cast<uintptr_t>(a.V) | reinterpret_cast<uintptr_t>(a.k_new) |
        reinterpret_cast<uintptr_t>(a.v_new)) & 15) return EKV_ERR_UNSUPPORTED;

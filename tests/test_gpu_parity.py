@@ -197,6 +197,34 @@ def test_chunk_random_vs_oracle(engines, dtype, H, Hkv, stride, policy, n0, kern
     assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
 
 
+def test_chunk_one_pass_denominator_falls_back_when_logits_run_away(engines):
+    """The tcgen05 chunk kernel sums softmax denominators in one pass against per-warp reference points (the row
+    maximum over the first 128-key tile) and must detect rows whose later logits exceed that reference by more than
+    e^80 — there every warp would overflow — and re-sum them exactly.  Keys 0..255 are tiny, a few later keys give
+    logits around +-100: outputs and victims must still match the restatement."""
+    dtype, H, Hkv, d, n0, stride = torch.float16, 4, 2, 128, 700, 16
+    g = torch.Generator().manual_seed(31)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
+    K, V = rnd(Hkv, n0, d) * 0.01, rnd(Hkv, n0, d)
+    K[:, 300:310] = 6.0                                         # q.k / sqrt(d) ~ +-100 for |q| ~ 1.5
+    K[:, 500:505] = -6.0
+    eng = engines.CudaEngine(1, H, Hkv, d, dtype, kernel=0, capacity=n0 + stride)
+    orc = replay.OracleEngine(1, H, Hkv, d, dtype)
+    for e in (eng, orc):
+        e.load_prefill(0, K, V, n0, torch.zeros(n0))
+    st = restate.Step(policy="h2o_head", accumulate=True, evict=stride, counter_add=float(stride), c_new_step=1.0,
+                      win_lo=4, win_recent=70, range_start=4)
+    for t in range(3):
+        q = torch.full((H, stride, d), 1.5 if t % 2 == 0 else -1.5).to(dtype) + rnd(H, stride, d) * 0.05
+        k, v = rnd(Hkv, stride, d) * 0.01, rnd(Hkv, stride, d)
+        o_ref, v_ref = orc.forward(0, st, q, k, v)
+        assert torch.isfinite(o_ref.float()).all()
+        o, vic = eng.forward(0, st, q, k, v, force=v_ref)
+        assert (o.float() - o_ref.float()).abs().max().item() <= 2e-3 * max(1.0, o_ref.float().abs().max().item())
+        if not torch.equal(torch.sort(vic, dim=-1)[0], torch.sort(v_ref, dim=-1)[0]):
+            assert min(orc.margin(0)) < 1e-5
+
+
 def test_keep_attention_seeding_tensorcore_vs_general(ekv_lib):
     """keep_attention seeding (h2o_head_score, easykv.py:173-186): a dense causal prefill issued as chunks with
     `raw_colsum` accumulates the attention map's column sums in fp32 and rounds once at the end — the tensor-core

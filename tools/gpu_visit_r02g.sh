@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+echo "== chunk debug"; timeout 300 python tools/chunk_debug.py 0 2>&1 | grep -v "^   cache equal: True" | awk '{print $1,$2,$3,$4,$5,$6,$7,$11,$17,$18}' | tail -28 | tee $OUT/r02g_chunk_debug.txt
+echo "== timeline C3 b8"; timeout 120 python tools/umma_timeline.py 8 32 8 8208 16 h2o_head 0 2>&1 | tee -a $OUT/r02g_timeline.txt
+echo "== timeline C2 b8"; timeout 120 python tools/umma_timeline.py 8 32 32 1088 64 roco 0 2>&1 | tee -a $OUT/r02g_timeline.txt
+echo "== tail timeline C3 b8"; timeout 120 python tools/tail_timeline.py 8 32 8 8208 16 h2o_head 2>&1 | tee -a $OUT/r02g_timeline.txt
+echo "== tail timeline C2 b8"; timeout 120 python tools/tail_timeline.py 8 32 32 1088 64 roco 2>&1 | tee -a $OUT/r02g_timeline.txt
+echo "== chunk sweep"; timeout 600 python tools/sweep.py chunk 2>&1 | tee $OUT/r02g_sweep_chunk.jsonl | cut -c1-260
+echo "== gpu suite (chunk / golden / reference parts)"; timeout 2400 python -m pytest tests -m gpu -q -x -k "chunk or golden or reference or umma or fullsize or driver" 2>&1 | tail -15 | tee $OUT/r02g_pytest.txt

@@ -32,10 +32,14 @@ torch.cuda.synchronize()
 cache.lib.ekv_debug_set_timeline(None)
 t = tl[U * 8:].view(NC, 16).cpu().double()
 t = t[t[:, 0] > 0]
+for i in (4, 5):                      # stamps 4 / 5 exist only when the exact L pass ran (slow path)
+    t[:, i] = torch.where(t[:, i] > 0, t[:, i], t[:, i - 1])
 print(f"{t.shape[0]} CTAs; kernel span {(t[:, 7].max() - t[:, 0].min()) / 1e3:.1f} us; CTA lifetime mean {(t[:, 7] - t[:, 0]).mean() / 1e3:.1f} us, max {(t[:, 7] - t[:, 0]).max() / 1e3:.1f} us")
-names = ["setup", "K phase (logits, max)", "max exchange", "L pass", "sum exchange", "V phase (p, stats, P^T)", "epilogue"]
+names = ["setup", "K phase (logits, max, sums)", "row-statistics exchange", "exact L pass (slow path)", "its exchange", "V phase (p, stats, P^T)", "epilogue"]
 for i, nm in enumerate(names):
     dlt = (t[:, i + 1] - t[:, i]) / 1e3
     print(f"  {nm:26s} mean {dlt.mean():7.2f} us   p10 {dlt.quantile(0.1):7.2f}   p90 {dlt.quantile(0.9):7.2f}")
+print(f"  inside setup: barriers+first TMA issued {((t[:, 8] - t[:, 0]) / 1e3).mean():.2f} us | thread 0 done with vmask + Q fill {((t[:, 9] - t[:, 0]) / 1e3).mean():.2f} | "
+      f"__syncthreads passed {((t[:, 10] - t[:, 0]) / 1e3).mean():.2f} | cluster sync passed {((t[:, 1] - t[:, 0]) / 1e3).mean():.2f}")
 starts = torch.sort(t[:, 0] - t[:, 0].min())[0] / 1e3
 print("  CTA start times (us), deciles:", [round(float(starts[int(i * (len(starts) - 1) / 10)]), 1) for i in range(11)])
