@@ -209,9 +209,10 @@ class BudgetedKVCache:
         out = torch.empty_like(q)
         evict = int(sp.evict)
         vs = vl = None
-        if evict and self._steady is not None and new_slots is self._steady[0][l] and evict == 1 and apply:
-            # steady decode (enable_steady): this step's victim slot overwrites the slot id it appended at, in place, so
-            # every pointer of the launch is the same from step to step and the step can be replayed from a CUDA graph
+        if evict and self._steady is not None and new_slots is self._steady[0][l] and evict == q_len and apply:
+            # steady state (enable_steady): this forward's victim slots overwrite the slot ids it appended at, in place,
+            # so every pointer of the launch is the same from forward to forward and the whole model step can be replayed
+            # from a CUDA graph (decode: q_len = 1; strided prefill: q_len = stride)
             vs, vl = new_slots, self._steady[1][l]
         elif evict:
             vv = torch.empty(2, self.B, self.Hkv, evict, dtype=torch.int32, device=self.device)
@@ -246,15 +247,16 @@ class BudgetedKVCache:
             self.free[l] = vs
         return out, vl
 
-    def enable_steady(self):
-        """Pin the per-layer free-slot / victim buffers for the steady state of decoding (append one, evict one, per
-        step — easykv.py:257-363 once the budget is reached, :670-748): needs exactly one free slot per (sequence, kv
-        head) in every layer.  From here on `step()` launches with identical pointers and shapes every step, which is
-        what lets `easykv.generate` capture the whole model step into one CUDA graph.  Returns the `[L, B, Hkv, 1]`
-        buffer that holds each step's victim ids."""
-        if any(self.free_count(l) != 1 for l in range(self.L)):
-            raise RuntimeError("enable_steady needs exactly one free slot per (sequence, kv head) in every layer")
-        slots = torch.empty(self.L, self.B, self.Hkv, 1, dtype=torch.int32, device=self.device)
+    def enable_steady(self, q_len=1):
+        """Pin the per-layer free-slot / victim buffers for a steady state (append q_len, evict q_len, per forward —
+        decoding once the budget is reached, easykv.py:257-363, :670-748; the strided prefill once the cache has its
+        size, :426-500, :587-661): needs exactly q_len free slots per (sequence, kv head) in every layer.  From here on
+        `step()` launches with identical pointers and shapes every forward, which is what lets `easykv.generate` capture
+        the whole model step into one CUDA graph.  Returns the `[L, B, Hkv, q_len]` buffer that holds each forward's
+        victim ids.  `disable_steady()` returns to per-forward buffers (mode transitions)."""
+        if any(self.free_count(l) != q_len for l in range(self.L)):
+            raise RuntimeError(f"enable_steady needs exactly {q_len} free slot(s) per (sequence, kv head) in every layer")
+        slots = torch.empty(self.L, self.B, self.Hkv, q_len, dtype=torch.int32, device=self.device)
         victims = torch.empty_like(slots)
         views = ([slots[l] for l in range(self.L)], [victims[l] for l in range(self.L)])
         for l in range(self.L):
@@ -263,6 +265,15 @@ class BudgetedKVCache:
         self._steady = views
         self.steady_victims = victims
         return victims
+
+    def disable_steady(self):
+        """Leave the steady state: the current free-slot lists move to buffers of their own (the pinned ones stay with
+        whatever CUDA graph captured them)."""
+        if self._steady is not None:
+            for l in range(self.L):
+                if self.free[l] is not None:
+                    self.free[l] = self.free[l].clone()
+            self._steady = None
 
     def evict(self, l, victims):
         """Delete logical ids `victims` `[B, Hkv, e]` (what truncate_kv_cache_* did)."""
@@ -373,12 +384,17 @@ class SteadyStep:
         if rc:
             _lib.check(rc)
 
-    def capture(self):
-        """Capture one whole step (L forwards) into a CUDA graph; `replay()` then costs one launch."""
+    def capture(self, pre=None):
+        """Capture one whole step (L forwards) into a CUDA graph; `replay()` then costs one launch.  `pre`: device-side
+        work captured ahead of the step (e.g. refreshing q / k_new / v_new from a pool, as bench.py does)."""
+        if pre is not None:
+            pre()
         self.run()                                   # warm: function attributes are set outside capture
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if pre is not None:
+                pre()
             self.run()
         return self
 

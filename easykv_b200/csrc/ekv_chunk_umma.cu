@@ -81,56 +81,6 @@ static_assert(B_LIDX + 1 <= 32, "barrier block");
 
 int umma_force_cluster();      // ekv_api.cu (env EKV_CHUNK_CLUSTER / ekv_debug_set_chunk_variant): 0 = planner's choice
 
-template <typename T> __device__ __forceinline__ uint32_t neg_inf2();
-template <> __device__ __forceinline__ uint32_t neg_inf2<__half>() { return 0xfc00fc00u; }
-template <> __device__ __forceinline__ uint32_t neg_inf2<__nv_bfloat16>() { return 0xff80ff80u; }
-template <typename T> __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b);
-template <> __device__ __forceinline__ uint32_t max2<__half>(uint32_t a, uint32_t b) {
-  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
-template <> __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
-
-template <int N> struct TmemIO;
-template <> struct TmemIO<32> {
-  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[32]) { umma::tmem_ld32(a, r); }
-};
-template <> struct TmemIO<16> {
-  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[16]) { umma::tmem_ld16(a, r); }
-  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[16]) { umma::tmem_st16(a, r); }
-};
-template <> struct TmemIO<8> {
-  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
-  }
-  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-  }
-};
-
-// a latency-tolerant waiter (the TMA / MMA threads): sleep between polls instead of burning the issue slots of the
-// scheduler partition it shares with two softmax warps
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
-}
-// 2^x, hardware approximation (MUFU.EX2, ~2^-22 relative): used only for the softmax DENOMINATORS, which are sums of
-// hundreds to thousands of terms whose summation order alone moves them by as much; the numerators use expf
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 template <typename T, int G, bool ARITH, int NSPLIT>
 __global__ void __launch_bounds__(cu::nthreads(NSPLIT), 1)
 chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant__ CUtensorMap mapK,

@@ -445,7 +445,7 @@ template <typename T, int G> static int launch_decode_tg(const KernelArgs& a, cu
   }
   const int U = a.B * a.Hkv, sms = sm_count[dev];
   const int sm_total = 227 * 1024;
-  const int variant = decode_variant();
+  const int variant = decode_variant() >= 5 ? 0 : decode_variant();     // 5 / 6 only steer the tcgen05 kernel (launch_decode)
   // automatic: more than one unit per SM -> one CTA per SM with two ping-pong consumer groups over a
   // shared ring (measured best: 0.87-0.93 of the HBM roofline vs 0.79-0.89 for two independent CTAs per
   // SM); otherwise one light CTA per unit.
@@ -512,6 +512,14 @@ int launch_decode(const KernelArgs& a, cudaStream_t stream) {
   if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean) return EKV_ERR_UNSUPPORTED;
   if (a.st.evict <= 1) {
     const int G = a.H / a.Hkv;
+    // grouped-query layouts in a 16-bit dtype: the tcgen05 kernel (decode_variant 5 forces it for any g, 6 forbids it)
+    const int dv = decode_variant();
+    // automatic: long caches (>= 2048 slots) with enough units to fill the chip; short caches stay with the cluster kernel,
+    // whose whole unit fits one light CTA
+    if (dv == 5 || (dv == 0 && decode_cluster_size() == 0 && G >= 2 && a.dtype != EKV_F32 && a.B * a.Hkv >= 32 && a.n_phys >= 2048)) {
+      const int rc = launch_decode_umma(a, stream);
+      if (rc != EKV_ERR_UNSUPPORTED || dv == 5) return rc;
+    }
     if (decode_cluster_size() > 0) return launch_decode_cluster(a, false, stream);
     // fewer units than half the SMs: split each unit over a cluster.  g >= 2: the persistent kernel's 544-thread
     // CTAs leave 96 registers per thread and spill (measured 0.40-0.45 of the roofline on the Mistral layout at any

@@ -116,6 +116,10 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     mbar_fence_init();
   }
   __syncthreads();
+  // Distributed shared memory of a peer may only be touched once that CTA has started executing (racecheck: "block
+  // that might not have entered yet"): every thread arrives on the cluster barrier here, and waits for this phase
+  // right before its first remote access — by then every peer has long arrived, so the wait costs nothing.
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
   if (warp == NWARP) {
     // ===== TMA producer ==============================================================================
@@ -132,6 +136,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
           // cluster has arrived, so the producer has to take part in those two phases before it may
           // block on such a slot (it exits before the later ones; exited threads are not waited for).
           if (!synced && i - stages >= nt) {
+            asm volatile("barrier.cluster.wait.acquire;" ::: "memory");      // the start-up phase (arrived above)
             cluster_sync_unaligned();
             cluster_sync_unaligned();
             synced = true;
@@ -392,6 +397,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       }
     }
     grp.sync();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // start-up phase: every peer CTA is running
     if (tid < G * C) {                                        // thread (g, p): this slice's max of head g -> peer p
       const int g = tid / C, p = tid % C;
       float v = red[g * NWARP];
@@ -967,7 +973,7 @@ template <typename T, int G> static int launch_cluster_plan(const KernelArgs& a,
   // tensor-core variant: by default for g = 8 (measured 1.15-1.85x over the FMA variant, which is FP32-bound there);
   // for g = 4 the FMA variant keeps up with HBM and is kept (decode_variant 4 forces the tensor cores, 3 forbids them)
   if constexpr (sizeof(T) == 2 && G >= 4) {
-    const int v = decode_variant();
+    const int v = decode_variant() >= 5 ? 0 : decode_variant();
     if (v == 4 || (v != 3 && G >= 8)) return launch_cluster_plan_v<T, G, true>(a, only_if_better, stream);
   }
   return launch_cluster_plan_v<T, G, false>(a, only_if_better, stream);

@@ -29,6 +29,7 @@ void count_launch();
 
 int launch_decode(const KernelArgs& a, cudaStream_t stream);      // ekv_decode.cu
 int launch_decode_cluster(const KernelArgs& a, bool only_if_better, cudaStream_t stream);   // ekv_decode_cluster.cu
+int launch_decode_umma(const KernelArgs& a, cudaStream_t stream);                          // ekv_decode_umma.cu (tcgen05, GQA)
 int launch_general(const KernelArgs& a, cudaStream_t stream);     // ekv_chunk.cu
 int launch_chunk_tc(const KernelArgs& a, cudaStream_t stream);    // ekv_chunk_tc.cu (16-bit dtypes, needs scratch)
 long long chunk_tc_scratch_bytes(int B, int Hkv, int G, int q_len, int n_phys);

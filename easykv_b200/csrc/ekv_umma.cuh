@@ -32,6 +32,18 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// the same without a swizzle (layout type 0).  MN-major operand of 8-element (16-byte) groups: a core matrix is 8 k-rows
+// x 16 bytes, 128 contiguous bytes; SBO = distance between successive 8-element groups along M / N, LBO = distance
+// between successive groups of 8 k.  (Used for the 16-row P^T operand of the GQA decode kernel.)
+__device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
 // ---- instruction descriptor, kind::f16, fp32 accumulate ---------------------------------------------------------------
 // [4,6) D format 1 = f32 | [7,10) A format, [10,13) B format: 0 = f16, 1 = bf16 | bit 15 / 16: A / B is MN-major |
 // [17,23) N >> 3 | [24,29) M >> 4
@@ -141,6 +153,58 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 
 }  // namespace umma
+
+// ---- helpers shared by the tcgen05 kernels (chunk: ekv_chunk_umma.cu, GQA decode: ekv_decode_umma.cu) --------------------
+template <typename T> __device__ __forceinline__ uint32_t neg_inf2();
+template <> __device__ __forceinline__ uint32_t neg_inf2<__half>() { return 0xfc00fc00u; }
+template <> __device__ __forceinline__ uint32_t neg_inf2<__nv_bfloat16>() { return 0xff80ff80u; }
+template <typename T> __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t max2<__half>(uint32_t a, uint32_t b) {
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int N> struct TmemIO;
+template <> struct TmemIO<32> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[32]) { umma::tmem_ld32(a, r); }
+};
+template <> struct TmemIO<16> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[16]) { umma::tmem_ld16(a, r); }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[16]) { umma::tmem_st16(a, r); }
+};
+template <> struct TmemIO<8> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+  }
+};
+
+// a latency-tolerant waiter (the TMA / MMA threads): sleep between polls instead of burning the issue slots of the
+// scheduler partition it shares with two softmax warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+// 2^x, hardware approximation (MUFU.EX2, ~2^-22 relative): used only for the softmax DENOMINATORS, which are sums of
+// hundreds to thousands of terms whose summation order alone moves them by as much; the numerators use expf
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 
 // Host side: a 2-D tensor map over a row-major [rows][128] 16-bit matrix (row pitch 256 bytes), box = {64 columns,
 // box_rows} with the 128-byte swizzle.  The driver entry point is resolved at run time (no link-time libcuda

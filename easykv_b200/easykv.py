@@ -60,6 +60,7 @@ class Session:
         self.model_kwargs = {}
         self.graph_error = None                  # why the decode step could not be captured into a CUDA graph, if so
         self.graphed_steps = 0
+        self.graphed_chunks = 0
         self.graph_capture_s = 0.0
         self.token_times = []                    # host time at which each generated token reached the host
         self._cur = None
@@ -95,7 +96,7 @@ class Session:
 
 
 class GraphedDecodeStep:
-    """The whole model's decode step — every projection, MLP, norm and the per-layer `ekv_rope_qk` + `ekv_attend_evict`
+    """The whole model's steady step (`q_len` = 1: a decode step; `q_len` = stride: a strided-prefill chunk) — every projection, MLP, norm and the per-layer `ekv_rope_qk` + `ekv_attend_evict`
     launches — captured once into a CUDA graph and replayed per generated token.  Valid in the steady state of decoding
     (append one, evict one, identical step parameters — `BudgetedKVCache.enable_steady`), where no shape, pointer or host
     scalar changes from step to step: the token and its position are refreshed in two static device buffers.  The
@@ -103,17 +104,19 @@ class GraphedDecodeStep:
     launch overhead (≈10 ms per token at batch 1 on a 7B model); replayed, the step is one launch."""
 
     MIN_STEPS = 128       # capture costs 0.06-0.5 s (measured, 7B shape) and saves ~4 ms per token at batch 1
+    MIN_CHUNKS = 16       # strided-prefill chunks left for a chunk capture to pay off
 
-    def __init__(self, model, sess, cache, step, bsz, device):
-        self.model, self.sess, self.cache, self.step = model, sess, cache, step
-        self.ids = torch.zeros(bsz, 1, dtype=torch.int64, device=device)
-        self.pos = torch.zeros(bsz, 1, dtype=torch.int64, device=device)
+    def __init__(self, model, sess, cache, step, bsz, device, q_len=1):
+        self.model, self.sess, self.cache, self.step, self.q_len = model, sess, cache, step, q_len
+        self.ids = torch.zeros(bsz, q_len, dtype=torch.int64, device=device)
+        self.pos = torch.zeros(bsz, q_len, dtype=torch.int64, device=device)
+        self.offs = torch.arange(q_len, dtype=torch.int64, device=device)[None]
         self.graph = self.logits = None
 
     def capture(self):
         cache, sess = self.cache, self.sess
-        self.victims = cache.enable_steady()
-        sess.begin(self.step, sess.pos0, 1)
+        self.victims = cache.enable_steady(self.q_len)
+        sess.begin(self.step, sess.pos0, self.q_len)
         sess.fwd -= 1                                   # capturing executes nothing
         sess._cur = None
         # the raw capture API: `torch.cuda.graph` would first gc.collect() and empty the caching allocator — seconds
@@ -136,16 +139,21 @@ class GraphedDecodeStep:
         self.graph, self.logits = graph, logits
         return self
 
-    def run(self, ids, pos0):
+    def run(self, ids, pos0, all_rows=False):
         sess = self.sess
         self.ids.copy_(ids)
-        self.pos.fill_(pos0)
-        sess.begin(self.step, pos0, 1)
+        if self.q_len == 1:
+            self.pos.fill_(pos0)
+        else:
+            torch.add(self.offs, pos0, out=self.pos[:1])
+            if self.pos.shape[0] > 1:
+                self.pos[1:] = self.pos[:1]
+        sess.begin(self.step, pos0, self.q_len)
         sess._cur = None
         self.graph.replay()
         if sess.events is not None:
             sess.events.append((sess.fwd, self.victims.clone()))
-        return self.logits[:, -1, :]
+        return self.logits if all_rows else self.logits[:, -1, :]
 
 
 DENSE_CHUNK = 64      # tokens per forward of the dense (no-eviction) prefill
@@ -256,11 +264,40 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
             for l in range(cache.L):
                 cache.set_counter(l, C0)
         cur = n_dense
-        for _, q_len, st in chunks:                            # easykv.py:426-500 / :587-661 / :816-892
-            logits = forward(input_ids[:, cur:cur + q_len], cur, st)
+        # steady strided prefill: once the cache has its size every chunk appends `stride` rows and evicts `stride`
+        # (identical step parameters, the victims' slots are the next chunk's new slots): the whole model forward of a
+        # chunk is captured into one CUDA graph and replayed (the reference pays ~135 host syncs per chunk here)
+        steady_chunk_from = len(chunks)
+        while steady_chunk_from > 0 and chunks[steady_chunk_from - 1][2] == chunks[-1][2] and chunks[-1][2].evict == chunks[-1][1]:
+            steady_chunk_from -= 1
+        chunk_graph_ok = (bool(cfg.get("cuda_graph", True)) and device.type == "cuda" and hasattr(cache, "enable_steady")
+                          and sess.rotary is not None and not sess.streaming and bool(chunks) and policy != "random"
+                          and not (chunks[-1][2].policy == "tova" and chunks[-1][2].tova_head_mean))
+        graphed_chunk = None
+        for ci, (_, q_len, st) in enumerate(chunks):           # easykv.py:426-500 / :587-661 / :816-892
+            if (chunk_graph_ok and graphed_chunk is None and ci > steady_chunk_from
+                    and len(chunks) - ci >= int(cfg.get("cuda_graph_min_chunks", GraphedDecodeStep.MIN_CHUNKS))
+                    and all(cache.free_count(l) == q_len for l in range(cache.L))):
+                try:
+                    t_cap = time.perf_counter()
+                    graphed_chunk = GraphedDecodeStep(self, sess, cache, st, bsz, device, q_len=q_len).capture()
+                    sess.graph_capture_s += time.perf_counter() - t_cap
+                except Exception as exc:
+                    chunk_graph_ok, graphed_chunk = False, None
+                    sess.graph_error = f"{type(exc).__name__}: {exc}\n" + "".join(traceback.format_tb(exc.__traceback__)[-6:])
+                    torch.cuda.synchronize(device)
+                    cache.disable_steady()
+            if graphed_chunk is not None:
+                logits = graphed_chunk.run(input_ids[:, cur:cur + q_len], cur, all_rows=True)
+                sess.graphed_chunks += 1
+            else:
+                logits = forward(input_ids[:, cur:cur + q_len], cur, st)
             if ppl_mode:                                       # easykv.py:826-827: this chunk's rows of the final loss
                 all_nll.append(cache.token_nll(logits[0].float(), next_ids(cur, q_len)))
             cur += q_len
+        if graphed_chunk is not None:
+            cache.disable_steady()                             # the decode phase pins its own buffers
+            logits = logits.clone()
         retained = cache.n[0]
         if plan.mode in ("encoding", "ppl") or (plan.mode == "dense" and kv_mode == "encoding"):
             # easykv.py:501-503 sits outside the budget if/else: 'encoding' prints the line for a dense prefill too

@@ -219,9 +219,11 @@ EKV_API void ekv_debug_set_timeline(void* device_buffer);
 /* Kernel-selection override (development / test hook, not part of the data path).
  * decode_variant: 0 = automatic, 1 = one consumer group per CTA, 2 = ping-pong groups (ekv_decode.cu),
  *                 3 = never / 4 = always use the tensor-core variant of the cluster kernel (g >= 4, 16-bit;
- *                 automatic: g = 8 only).
+ *                 automatic: g = 8 only), 5 = always / 6 = never use the tcgen05 GQA decode kernel (ekv_decode_umma.cu;
+ *                 automatic: 16-bit dtypes, g >= 2, at least 32 (sequence, kv head) units).
  * cluster_size:   0 = automatic, -1 = never use the cluster-split decode kernel, 1/2/4/8 = always use it with
- *                 this many CTAs per (sequence, kv head) (ekv_decode_cluster.cu). */
+ *                 this many CTAs per (sequence, kv head) (ekv_decode_cluster.cu; with decode_variant 5: the tcgen05
+ *                 kernel's cluster size, 1/2/4). */
 EKV_API void ekv_debug_set_dispatch(int32_t decode_variant, int32_t cluster_size);
 
 /* Strided-chunk kernel selection (development / test hook): 0 = automatic (the tcgen05 cluster kernel, falling back to

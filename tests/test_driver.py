@@ -350,3 +350,43 @@ def test_graph_captured_decode_step_equals_eager(ekv_lib, dtype, mode, policy, b
         assert f0 == f1 and torch.equal(e0, e1)
     for a, b in zip(k0, k1):
         assert torch.equal(a, b)                        # the retained keys, in logical order
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,mode,policy,bsz,stride", [("float16", "auto", "roco", 1, 8), ("float16", "encoding", "h2o_head", 2, 16),
+                                                          ("bfloat16", "auto", "recency", 1, 8), ("float16", "ppl", "roco", 1, 8)])
+def test_graph_captured_strided_chunks_equal_eager(ekv_lib, dtype, mode, policy, bsz, stride):
+    """Steady strided-prefill chunks replayed from one CUDA graph of the whole model forward (easykv.py:426-500,
+    :587-661 as one launch per chunk) must evict the same slots, leave the same cache and produce the same tokens /
+    perplexity as the eager chunk loop."""
+    transformers = pytest.importorskip("transformers")
+    cfg = transformers.LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=2, head_dim=128, vocab_size=512, max_position_embeddings=2048,
+                                   attn_implementation="eager")
+    torch.manual_seed(0)
+    model = transformers.LlamaForCausalLM(cfg).to(getattr(torch, dtype)).cuda().eval()
+    length = 40 + stride * 30
+    ids = torch.randint(3, 512, (bsz, length), generator=torch.Generator().manual_seed(1)).cuda()
+    ppl = mode == "ppl"
+    easykv_b200.enable_fixed_kv(model, scaffold.StubTokenizer(), mode="encoding" if ppl else mode, stride=stride)
+    budget = 64 if mode == "auto" else 0.4
+    runs = []
+    for graph in (False, True):
+        torch.manual_seed(7)
+        gen = dict(temperature=1e-9, max_new_tokens=0 if ppl else 6, budget=budget, kv_policy=policy, cuda_graph=graph,
+                   cuda_graph_min_chunks=3, cuda_graph_min_steps=1000)
+        out = (model.easykv_ppl if ppl else model.easykv_generate)(input_ids=ids, generation_config=gen)
+        sess = model.easykv_last
+        runs.append((out, [(f, e.clone()) for f, e in sess.events], sess.cache.n[0], sess.graphed_chunks, sess.graph_error,
+                     [sess.cache.export(l)[0].clone() for l in range(2)]))
+    (o0, ev0, n0, g0, _, k0), (o1, ev1, n1, g1, err1, k1) = runs
+    assert g0 == 0 and g1 >= 10, (g1, err1)
+    assert n0 == n1 and len(ev0) == len(ev1)
+    for (f0, e0), (f1, e1) in zip(ev0, ev1):
+        assert f0 == f1 and torch.equal(torch.sort(e0.long(), -1)[0], torch.sort(e1.long(), -1)[0])
+    for a_, b_ in zip(k0, k1):
+        assert torch.equal(a_, b_)
+    if ppl:
+        assert o0 == pytest.approx(o1, rel=1e-6)
+    else:
+        assert o0 == o1

@@ -78,10 +78,13 @@ def test_persistent_decode_kernel_7b_layout_vs_restate(dispatch, variant):
     assert _run(cache, orcs, rnd, _decode_step(n), B, H, Hkv, 1, steps=10) <= 2
 
 
+@pytest.mark.parametrize("variant", [5, 6], ids=["tcgen05", "round1_kernels"])
 @pytest.mark.parametrize("B,H,Hkv,n", [(2, 32, 8, 8208), (2, 64, 8, 8256), (9, 64, 8, 1088)],
                          ids=["mistral_n8208_g4", "70b_n8256_g8", "70b_n1088_g8_b9"])
-def test_cluster_decode_kernel_long_gqa_vs_restate(dispatch, B, H, Hkv, n):
-    """configs[2] / [4] decode geometries through the cluster-split kernel (automatic dispatch)."""
+def test_gqa_decode_kernels_long_caches_vs_restate(dispatch, B, H, Hkv, n, variant):
+    """configs[2] / [4] decode geometries through the tcgen05 GQA decode kernel and through the round-1 cluster-split
+    kernels."""
+    dispatch.ekv_debug_set_dispatch(variant, 0)
     cache, orcs, rnd = _setup(B, H, Hkv, n, n + 1, torch.float16, [float(n - i) for i in range(n)], seed=22)
     assert _run(cache, orcs, rnd, _decode_step(n), B, H, Hkv, 1, steps=4) <= 1
 

@@ -160,6 +160,43 @@ def test_decode_random_vs_oracle(engines, dispatch, dtype, H, Hkv, policy, clust
     assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
 
 
+@pytest.mark.parametrize("cluster", [0, 1, 2, 4], ids=lambda c: f"cluster{c}")
+@pytest.mark.parametrize("dtype,H,Hkv,policy,n0", [
+    (torch.float16, 8, 2, "roco", 203), (torch.float16, 16, 2, "roco", 517), (torch.bfloat16, 8, 1, "h2o_head", 203),
+    (torch.float16, 8, 4, "tova", 1300), (torch.float16, 8, 8, "roco", 203), (torch.float16, 4, 2, "recency", 150),
+    (torch.float16, 16, 2, "roco", 4490),
+])
+def test_decode_umma_random_vs_oracle(engines, dispatch, dtype, H, Hkv, policy, n0, cluster):
+    """The tcgen05 GQA decode kernel (decode_variant 5; csrc/ekv_decode_umma.cu) forced on small and medium shapes —
+    g = 1, 2, 4, 8, every policy, one CTA per unit and clusters of 2 / 4 — against the CPU restatement."""
+    dispatch(5, cluster)
+    d, steps = 128, 10
+    g = torch.Generator().manual_seed(17)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
+    eng = engines.CudaEngine(1, H, Hkv, d, dtype, capacity=n0 + 8)
+    orc = replay.OracleEngine(1, H, Hkv, d, dtype)
+    K, V = rnd(Hkv, n0, d), rnd(Hkv, n0, d)
+    C0 = torch.arange(n0, 0, -1).float()
+    for e in (eng, orc):
+        e.load_prefill(0, K, V, n0, C0)
+    recent = int(n0 * 0.3)
+    st = restate.Step(policy=policy, accumulate=True, evict=1, counter_add=1.0, k_feasible=n0 - recent,
+                      win_recent=recent if policy == "h2o_head" else 0, range_start=4)
+    bad = 0
+    for t in range(steps):
+        q, k, v = rnd(H, 1, d) * 0.3, rnd(Hkv, 1, d), rnd(Hkv, 1, d)
+        o_ref, v_ref = orc.forward(0, st, q, k, v)
+        o, vic = eng.forward(0, st, q, k, v, force=v_ref)
+        tol = 1e-3 if dtype == torch.float16 else 8e-3
+        assert (o.float() - o_ref.float()).abs().max().item() <= tol * max(1.0, o_ref.float().abs().max().item())
+        if not torch.equal(vic, v_ref):
+            assert min(orc.margin(0)) < 1e-5
+            bad += 1
+    assert bad <= 2
+    Kc, Vc = eng.export(0)
+    assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
+
+
 # ------------------------------------------------------------------------------------------------
 # 3b. strided-prefill chunks: tensor-core path (kernel 0, 16-bit) and general kernel vs the CPU restatement
 # ------------------------------------------------------------------------------------------------
@@ -341,13 +378,18 @@ def test_full_size_decode_properties(ekv_lib):
     assert int(srt[..., :-n].max()) == -1
 
 
-@pytest.mark.parametrize("cluster", [-1, 0, 2, 8], ids=lambda c: f"cluster{c}")
+@pytest.mark.parametrize("cluster", [-1, 0, 2, 8, 105, 205], ids=lambda c: f"cluster{c}")
 @pytest.mark.parametrize("n0", [333, 1500])
 def test_decode_select_when_low_mean_slots_are_infeasible(engines, dispatch, n0, cluster):
     """roco with the std ranking anti-correlated to the mean ranking: the slots with the lowest mean all lie
     outside the k_feasible lowest std, so walking candidates by mean fails and the kernels must fall back to
-    the real two-stage select (single CTA: shared-memory radix select; cluster: cluster-wide radix select)."""
-    dispatch(0, cluster)
+    the real two-stage select (single CTA: shared-memory radix select; cluster: cluster-wide radix select; the
+    tcgen05 kernel — cluster ids 105 / 205 = decode_variant 5 with 1 / 2 CTAs per unit — keeps walking, four
+    candidates per round)."""
+    if cluster >= 100:
+        dispatch(5, cluster // 100)
+    else:
+        dispatch(0, cluster)
     dtype, H, Hkv, d = torch.float16, 4, 2, 128
     g = torch.Generator().manual_seed(n0)
     rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)

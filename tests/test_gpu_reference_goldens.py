@@ -52,11 +52,13 @@ def test_reference_on_b200_replay_two_pass_chunk_kernels(ekv_lib, name, chunk_va
     _check(rep, name)
 
 
-@pytest.mark.parametrize("variant,cluster", [(2, -1), (1, -1), (0, 2)], ids=["pingpong", "one_group", "cluster2"])
+@pytest.mark.parametrize("variant,cluster", [(2, -1), (1, -1), (0, 2), (6, 0), (5, 0), (5, 2)],
+                         ids=["pingpong", "one_group", "cluster2", "round1_dispatch", "tcgen05", "tcgen05_pair"])
 @pytest.mark.parametrize("name", [n for n in CASES if "decoding" in n or "auto" in n])
 def test_reference_on_b200_replay_decode_kernels(ekv_lib, name, variant, cluster):
     """Decode steps of the B200-recorded runs forced through each decode kernel: the persistent ping-pong kernel
-    (decode_kernel<T,G,2>, the headline instantiation), its one-group form, and the cluster-split kernel."""
+    (decode_kernel<T,G,2>, the headline instantiation), its one-group form, the cluster-split kernel, the round-1
+    dispatch as a whole, and the tcgen05 GQA decode kernel (one CTA per unit and CTA pairs)."""
     import engines as E
     ekv_lib.ekv_debug_set_dispatch(variant, cluster)
     try:

@@ -119,6 +119,10 @@ if run("cluster"):
     decode_case("cluster decode C=2 (FMA)", 1, 8, 8, 200, 3, variant=0, cluster=2)
     decode_case("cluster decode C=4, g=4 (FMA)", 1, 8, 2, 300, 3, variant=3, cluster=4)
     decode_case("cluster decode C=2, g=8 (tensor-core variant)", 1, 16, 2, 300, 3, variant=4, cluster=2)
+if run("decode_umma"):
+    decode_case("tcgen05 GQA decode, g=4, one CTA per unit", 2, 8, 2, 300, 3, variant=5, cluster=1)
+    decode_case("tcgen05 GQA decode, g=8, CTA pairs", 1, 16, 2, 700, 3, variant=5, cluster=2)
+    decode_case("tcgen05 GQA decode, g=2, clusters of 4", 1, 4, 2, 1100, 2, variant=5, cluster=4)
 if run("chunk_umma"):
     chunk_case("tcgen05 chunk, 1 CTA per unit", 1, 4, 4, 200, 16, 2, variant=0)
     chunk_case("tcgen05 chunk, cluster of CTAs per unit, g=4", 1, 8, 2, 1500, 16, 2, variant=0)
