@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libeasykv_b200.so")
 SOURCES = ["ekv_api.cu", "ekv_decode.cu", "ekv_decode_cluster.cu", "ekv_chunk.cu", "ekv_chunk_tc.cu", "ekv_aux.cu", "ekv_sample.cu", "ekv_umma_probe.cu", "ekv_chunk_umma.cu", "ekv_decode_umma.cu"]
-HEADERS = ["ekv_common.cuh", "ekv_select.cuh", "ekv_decode_common.cuh", "ekv_mma.cuh", "ekv_umma.cuh", "ekv_chunk_plan.h", "ekv_kernels.h", os.path.join("..", "..", "include", "easykv_b200.h")]
+HEADERS = ["ekv_common.cuh", "ekv_select.cuh", "ekv_bucket.cuh", "ekv_decode_common.cuh", "ekv_mma.cuh", "ekv_umma.cuh", "ekv_chunk_plan.h", "ekv_kernels.h", os.path.join("..", "..", "include", "easykv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "--expt-extended-lambda", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-Wall"]

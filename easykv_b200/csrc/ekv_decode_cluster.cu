@@ -49,7 +49,7 @@ constexpr int TC_TILE_BYTES = 64 * TC_PITCH;      // ldmatrix conflict-free), 64
 
 template <typename T> struct ClusterSmem {
   int off_bar, off_red, off_xnew, off_q, off_qp, off_k, off_v, off_ns, off_lj, off_plog, off_ka, off_kb, off_flag;
-  int off_xmax, off_xsum, off_xout, off_xbest, off_xcnt, off_hist, off_xhist, off_ring, fixed, slp;
+  int off_xmax, off_xsum, off_xout, off_xbest, off_xcnt, off_hist, off_xhist, off_bkt, off_ring, fixed, slp;
   __host__ __device__ ClusterSmem(int G, int slice, int C, bool tc = false) {
     using Cfg = DecodeCfg<T>;
     const int NEl = slice + 1;                    // rank 0 also owns the appended token's entry
@@ -76,6 +76,7 @@ template <typename T> struct ClusterSmem {
     off_xcnt = o; o += 2 * C * 4;
     off_hist = align_up(o, 16); o = off_hist + 256 * 4 + 16;          // radix select: local histogram + 4 ints
     off_xhist = o; o += 2 * C * 256 * 4;                              // every CTA's histogram, double-buffered
+    off_bkt = align_up(o, 16); o = off_bkt + BucketScratch::bytes(8);  // bucket select (ekv_bucket.cuh)
     o = align_up(o, 128);
     off_ring = o;                                 // the ring doubles as the cross-warp P·V scratch [NWARP][G][D] fp32
     fixed = o;
@@ -194,6 +195,10 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L.off_hist);
   int* hmisc = reinterpret_cast<int*>(hist + 256);
   uint32_t* xhist = reinterpret_cast<uint32_t*>(smem + L.off_xhist);
+  BucketScratch bs;
+  bs.carve(smem + L.off_bkt, 8);
+  const int lsh = bk::lidx_shift(a.n_before + 1);
+  const bool roco_sel = a.st.evict > 0 && a.st.policy == EKV_POLICY_ROCO;
 
   auto finish_logit = [&](float dot, bool valid) -> T {
     float x = Tr<T>::round_f(dot);                                           // llama_patch.py:201
@@ -215,6 +220,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       else if (i < QCH + RCH) reinterpret_cast<uint4*>(kh)[i - QCH] = kg[i - QCH];
       else reinterpret_cast<uint4*>(vh)[i - QCH - RCH] = vg[i - QCH - RCH];
     }
+    if (roco_sel) bs.clear(tid, NCONS);                       // the select's histograms (filled by the tail's keys pass)
     const int32_t* lg = a.lidx + (size_t)unit * a.cap + lo;
     for (int e = tid; e < nloc; e += NCONS) lj[e] = lg[e];
     if (tid == 0) {
@@ -609,14 +615,16 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
 #pragma unroll
       for (int k = 0; k < FCH; ++k) {
         const int e = base + k * NCONS + tid;
-        if (e >= NEl) continue;
         uint32_t ka = 0, kb = 0;
         uint8_t f = 0;
-        bool dirty = false;
-        if (rl[k] >= 0 && rl[k] >= P)
-          entry_update(st, rl[k] - P, n_s, e >= nloc, ds[k], dsq[k], sv[k], sq[k], cc[k], ka, kb, f, dirty);
-        if (dirty) { const int ph = phys_of(e); Sg[ph] = sv[k]; SQg[ph] = sq[k]; Cg[ph] = cc[k]; }
-        keyA[e] = ka; keyB[e] = kb; flag[e] = f;
+        if (e < NEl) {
+          bool dirty = false;
+          if (rl[k] >= 0 && rl[k] >= P)
+            entry_update(st, rl[k] - P, n_s, e >= nloc, ds[k], dsq[k], sv[k], sq[k], cc[k], ka, kb, f, dirty);
+          if (dirty) { const int ph = phys_of(e); Sg[ph] = sv[k]; SQg[ph] = sq[k]; Cg[ph] = cc[k]; }
+          keyA[e] = ka; keyB[e] = kb; flag[e] = f;
+        }
+        if (roco_sel) bs.add_warp(e < NEl && (f & F_CAND), ka, (uint32_t)rl[k], lsh, lane);
       }
     }
   }
@@ -660,7 +668,11 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   };
   int attempt = 0;
   constexpr int MAX_TRY = 1;                                    // candidate walks before the radix select (2 cluster barriers each)
-  if (single) {
+  // roco: one candidate attempt (the lowest-mean slot is usually among the k_feasible lowest std), then the bucket select
+  // (ekv_bucket.cuh; barrier (3) publishes its histograms) instead of walking on
+  const bool bucket = single && roco_sel && NEl < 65535;
+  const bool walk = single;
+  if (walk) {
     const Tuple128 b = local_best(need_flag);
     if (tid < C) {
       const uint32_t dst = map_to_rank(&xbest[(0 * C + rank) * 2], tid);
@@ -690,7 +702,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       store_row8<T>(reinterpret_cast<T*>(a.V) + ((size_t)unit * a.cap + slot) * D, l16, x);
     }
   }
-  if (single) {
+  if (walk) {
     while (true) {
       const int pb = attempt & 1;
       Tuple128 best; best.hi = xbest[(pb * C) * 2]; best.lo = xbest[(pb * C) * 2 + 1];
@@ -724,6 +736,45 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       grp.sync();
       ++attempt;
       if (attempt >= MAX_TRY) {
+        bool bucket_done = false;
+        if (bucket) {
+          // the k_feasible-th smallest std from the histograms of every CTA (read over DSMEM), one pass over the entries, one
+          // exchange (per-warp argmins + the cut bucket's entries), exact ranks of the listed entries (easykv.py:322-324)
+          auto sync = [&] { grp.sync(); };
+          auto ld = [&](const uint32_t* ptr, int peer) -> uint4 {
+            if (peer == rank) return *reinterpret_cast<const uint4*>(ptr);
+            uint4 v;
+            asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(map_to_rank(ptr, peer)) : "memory");
+            return v;
+          };
+          auto get = [&](int e, uint32_t& ka, uint32_t& kb, uint32_t& l) -> bool {
+            if (!(flag[e] & F_CAND)) return false;
+            ka = keyA[e]; kb = keyB[e]; l = (uint32_t)lj[e];
+            return true;
+          };
+          auto push = [&](unsigned long long* slot, unsigned long long hi, unsigned long long lo2) {
+            for (int p = 0; p < C; ++p) {
+              const uint32_t dst = map_to_rank(slot, p);
+              st_cluster_u64(dst, hi);
+              st_cluster_u64(dst + 8, lo2);
+            }
+          };
+          Feasibility fz;
+          fz.mode = 1; fz.lsh = lsh; fz.T1 = 0u; fz.jT = 0xffffffffu;
+          fz.b = bucket_scan<8>(bs, st.k_feasible, C, rank, tid, NCONS, NEl, sync, ld, get, [&] { cluster_sync_all(); });
+          if (fz.b.status != bk::FALLBACK) {
+            bucket_pass(bs, fz, NEl, rank, tid, NCONS, get, push);
+            cluster_sync_all();                                                             // (4) argmins + boundary entries
+            Tuple128 wn;
+            if (bucket_final(bs, fz, C, tid, NCONS, sync, wn)) {
+              l_c = (uint32_t)(wn.lo >> 32); owner = (int)((wn.lo >> 24) & 0xffu); e_c = (int)(wn.lo & 0xffffffu);
+              found = true;
+            }
+            bucket_done = true;
+          }
+        }
+        if (bucket_done) break;
+        // (a cut bucket crowded with bit-identical keys falls through to here)
         // The low-mean slots keep falling outside the k_feasible lowest std: stop walking and select properly.
         // Cluster-wide MSB-first radix select (8 bits per pass) of the k-th smallest 64-bit key (std key,
         // logical index) — unique keys, so no tie handling — then one cluster argmin over the feasible set.
@@ -836,7 +887,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       }
       cluster_sync_all();                                                           // (4b)
     }
-  } else if (evicting) {                                      // RANGE with one victim: positional
+  } else if (evicting && !single) {                           // RANGE with one victim: positional
     l_c = (uint32_t)(P + st.range_start);
     found = true;
   }

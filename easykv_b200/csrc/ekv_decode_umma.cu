@@ -28,6 +28,7 @@
 //
 // Replaces the same reference lines as ekv_decode.cu / ekv_decode_cluster.cu.
 #include "ekv_decode_common.cuh"
+#include "ekv_bucket.cuh"
 #include "ekv_mma.cuh"
 #include "ekv_umma.cuh"
 
@@ -38,10 +39,11 @@ constexpr int D = 128;
 constexpr int TKEYS = 128;               // keys per tile = MMA M
 constexpr int NR = 16;                   // MMA N: the g heads padded to 16 rows
 constexpr int NSOFT = 128;               // 4 softmax warps: one thread per TMEM lane
-constexpr int NHELP = 128;               // 4 helper warps: idle until the tail (victim walk, renumbering), which is latency-
-                                         // bound shared-memory scanning — 8 warps instead of 4 halve it
-constexpr int NTAIL = NSOFT + NHELP;
-constexpr int NT = NSOFT + 64 + NHELP;   // softmax | TMA producer warp | MMA warp | helpers
+constexpr int NHS = 128;                 // helper warps, one SET of 4: the per-key policy work of the V phase (state update, IEEE
+constexpr int NHELP = 2 * NHS;           // div / sqrt for the roco keys, select histograms) is a long dependent chain per key — two sets
+                                         // take alternate tiles, so each has two tile-times for its chain; set 0 joins the tail
+constexpr int NTAIL = NSOFT + NHS;       // threads of the tail (select, renumbering): latency-bound shared-memory scanning
+constexpr int NT = NSOFT + 64 + NHELP;   // softmax | TMA producer warp | MMA warp | helper set 0 | helper set 1
 constexpr int STAGE_BYTES = 32768;
 constexpr int MAX_STAGE = 5;             // ring depth: whatever shared memory is left after the per-entry arrays (3 .. 5)
 constexpr int MAX_CLUSTER = 4;
@@ -68,12 +70,14 @@ constexpr int OFF_HIST = OFF_WIN + NCAND * 16 + NTW * NCAND * 4 + 32;    // radi
 constexpr int OFF_CAND = (OFF_HIST + 1024 + 15) / 16 * 16;               // candidates [2 parities][MAX_CLUSTER][NTW][NCAND] 128-bit tuples,
 constexpr int CAND_BYTES = 2 * MAX_CLUSTER * 256 * 4;                     // reused for the radix histograms [2][MAX_CLUSTER][256] u32
 static_assert(2 * MAX_CLUSTER * NTW * NCAND * 16 <= CAND_BYTES, "candidate exchange fits");
-constexpr int OFF_RING = (OFF_CAND + CAND_BYTES + 1023) / 1024 * 1024;
+constexpr int OFF_FS = OFF_CAND + CAND_BYTES;                             // [2][128] folded probabilities: softmax warps -> helper warps
+constexpr int OFF_BKT = OFF_FS + 2 * TKEYS * 4;                            // bucket select (ekv_bucket.cuh): histograms, boundary list, gather
+constexpr int OFF_RING = (OFF_BKT + BucketScratch::bytes(MAX_CLUSTER) + 1023) / 1024 * 1024;
 // barriers
 constexpr int B_FULL = 0, B_EMPTY = MAX_STAGE, B_SFULL = 2 * MAX_STAGE, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2,
               B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_LIDX = B_OFULL + 1, B_XST = B_LIDX + 1, B_XST2 = B_XST + 1,
-              B_XOUT = B_XST2 + 1, B_XCAND = B_XOUT + 1, B_XCNT = B_XCAND + 2, B_XHIST = B_XCNT + 2;
-static_assert(B_XHIST + 2 <= 40, "barrier block");
+              B_XOUT = B_XST2 + 1, B_XHIST = B_XOUT + 1, B_HRDY = B_XHIST + 2, B_XG = B_HRDY + 1, B_FSFULL = B_XG + 1, B_FSEMPTY = B_FSFULL + 2;
+static_assert(B_FSEMPTY + 2 <= 40, "barrier block");
 }  // namespace du
 
 // What depends on the plan: ring depth, the gathered partial outputs (rank 0, clusters only), one logical index and one
@@ -124,15 +128,15 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   float* xnew_s = rowR + 8;
   float* pnew_s = xnew_s + 8;
   int* flags = reinterpret_cast<int*>(pnew_s + 8);               // [0] slow path, [1] walk decision, [2..] scratch
-  unsigned long long* xcand = reinterpret_cast<unsigned long long*>(smem + OFF_CAND);
-  int* xcnt = reinterpret_cast<int*>(smem + OFF_CNT);
-  unsigned long long* win = reinterpret_cast<unsigned long long*>(smem + OFF_WIN);
-  int* wcnt = reinterpret_cast<int*>(smem + OFF_WIN + NCAND * 16);
-  int* hmisc = wcnt + NTW * NCAND;                               // radix select: digit, count below, count equal
+  int* hmisc = reinterpret_cast<int*>(smem + OFF_WIN);           // radix select: digit, count below, count equal
   // radix select: every CTA's 256-bin histogram, double-buffered [2][MAX_CLUSTER][256] — the candidate exchange buffer,
   // idle once the walk has given up
   uint32_t* xhist = reinterpret_cast<uint32_t*>(smem + OFF_CAND);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem + OFF_HIST);
+  BucketScratch bs;
+  bs.carve(smem + OFF_BKT, MAX_CLUSTER);
+  float* fs = reinterpret_cast<float*>(smem + OFF_FS);
+  const int lsh = bk::lidx_shift(a.n_before + 1);               // logical indices -> histogram buckets
   int32_t* lj = reinterpret_cast<int32_t*>(smem + SL.off_lj);
   unsigned long long* kk = reinterpret_cast<unsigned long long*>(smem + SL.off_kk);
 
@@ -164,9 +168,11 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars[B_SFULL + s], 1); mbar_init(&bars[B_SEMPTY + s], NSOFT / 32);
       mbar_init(&bars[B_PFULL + s], NSOFT / 32); mbar_init(&bars[B_PEMPTY + s], 1);
-      mbar_init(&bars[B_XCAND + s], NTW * NCAND * C); mbar_init(&bars[B_XCNT + s], NCAND * C);
       mbar_init(&bars[B_XHIST + s], NTAIL * C);
     }
+    mbar_init(&bars[B_HRDY], C);
+    mbar_init(&bars[B_XG], NTW * C);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_FSFULL + s], NSOFT / 32); mbar_init(&bars[B_FSEMPTY + s], NHS / 32); }
     mbar_init(&bars[B_OFULL], 1);
     mbar_init(&bars[B_LIDX], 1);
     mbar_init(&bars[B_XST], 8 * C);
@@ -202,6 +208,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     cp_async_commit();
     for (int i = lane; i < 2 * 4096 / 16; i += 32) reinterpret_cast<uint4*>(Ps)[i] = make_uint4(0, 0, 0, 0);
   }
+  if (warp >= NSOFT / 32 + 2) bs.clear(tid - NSOFT - 64, NHELP);  // the helper warps zero the select histograms
   umma::fence_before_sync();
   __syncthreads();                                               // barriers initialised, TMEM base published
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");      // waited for right before the first remote access
@@ -275,6 +282,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     const bool stateful = st.policy == EKV_POLICY_ROCO || st.policy == EKV_POLICY_H2O || st.policy == EKV_POLICY_TOVA;
     // which entries the victim walk visits: roco — every scored slot (F_CAND; the std rank decides); h2o_head / tova — the window
     const uint8_t need_flag = !evicting ? 0 : st.policy == EKV_POLICY_ROCO ? F_CAND : (st.policy == EKV_POLICY_RANGE ? 0 : F_FEAS);
+    const bool roco_sel = evicting && st.policy == EKV_POLICY_ROCO;
 
     auto finish_logit2 = [&](float x0, float x1) -> uint32_t {
       round2<T>(x0, x1);                                         // llama_patch.py:201
@@ -502,20 +510,10 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     const float inv_g = 1.0f / (float)G;
     stamp(2);
 
-    // ---- V phase: probabilities, P^T tiles, policy state + selection keys per key ---------------------------------------------
-    float s_nx = 0.f, sq_nx = 0.f, c_nx = 1.f;                   // state of the NEXT tile's entry, loaded one tile ahead
-    auto load_state = [&](int i, float& sv, float& sq, float& cc) {
-      sv = 0.f; sq = 0.f; cc = 1.f;
-      if (i < T_ && stateful) {
-        const int rl = lj[i * TKEYS + kl];
-        if (rl >= P) { const int ph = first + i * TKEYS + kl; sv = Sg[ph]; sq = SQg[ph]; cc = Cg[ph]; }
-      }
-    };
-    load_state(0, s_nx, sq_nx, c_nx);
+    // ---- V phase: probabilities, P^T tiles; the folded probability of every key goes to the helper warps, which keep the
+    // policy state and the selection keys (below) --------------------------------------------------------------------------------
     for (int i = 0; i < T_; ++i) {
-      const int pb = i & 1, e = i * TKEYS + kl;
-      float sv = s_nx, sq = sq_nx, cc = c_nx;
-      load_state(i + 1, s_nx, sq_nx, c_nx);
+      const int pb = i & 1;
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       {
         uint32_t r4[4];
@@ -536,23 +534,10 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
         fsum += p0;
         fsum += p1;
       }
-      // policy state + selection keys of this entry (accumulate, counter: easykv.py:288-304; keys: ekv_select.cuh)
-      {
-        const int rl = lj[e];
-        uint32_t ka = 0, kb = 0;
-        uint8_t f = 0;
-        bool dirty = false;
-        if (rl >= 0 && rl >= P) {
-          float ds = 0.f, dsq = 0.f;
-          if (st.accumulate) {
-            ds = G == 1 ? fsum : Tr<T>::round_f(__fmul_rn(fsum, inv_g));          // process_for_mqa_gqa, easykv.py:188-196
-            dsq = Tr<T>::round_f(__fmul_rn(ds, ds));                              // p**2 in the model dtype, :296
-          }
-          entry_update(st, rl - P, n_s, false, ds, dsq, sv, sq, cc, ka, kb, f, dirty);
-          if (dirty) { const int ph = first + e; Sg[ph] = sv; SQg[ph] = sq; Cg[ph] = cc; }
-        }
-        kk[e] = (f & need_flag) == need_flag && need_flag ? (((unsigned long long)kb << 32) | ka) : ~0ull;
-      }
+      if (i >= 2) mbar_wait(&bars[B_FSEMPTY + pb], ((i >> 1) - 1) & 1);
+      fs[pb * TKEYS + kl] = fsum;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_FSFULL + pb]);
       if (i >= 2) mbar_wait(&bars[B_PEMPTY + pb], ((i >> 1) - 1) & 1);
       {
         // the key's row group 0 (rows 0..7) of the un-swizzled MN-major operand: 16 bytes; rows >= GP stay zero
@@ -593,7 +578,9 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
         entry_update(st, rl - P, n_s, true, ds, dsq, sv, sq, cc, ka, kb, f, dirty);
         if (dirty) { Sg[new_slot] = sv; SQg[new_slot] = sq; Cg[new_slot] = cc; }
       }
-      kk[e_new] = (f & need_flag) == need_flag && need_flag ? (((unsigned long long)kb << 32) | ka) : ~0ull;
+      const bool keyed = (f & need_flag) == need_flag && need_flag;
+      kk[e_new] = keyed ? (((unsigned long long)kb << 32) | ka) : ~0ull;
+      if (roco_sel && keyed && (((unsigned long long)kb << 32) | ka) != ~0ull) bs.add(ka, (uint32_t)rl, lsh);
     }
 
     // ---- output: partial O^T -> rank 0 -> out ---------------------------------------------------------------------------------
@@ -633,8 +620,74 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     }
     stamp(4);
   }
+  if (warp >= NSOFT / 32 + 2) {
+    // ===== helper warps, V phase: policy state + selection keys per key (accumulate, counter: easykv.py:288-304; keys:
+    // ekv_select.cuh) and the select's histograms, from the folded probabilities the softmax warps hand over ===================
+    const int hset = (tid - NSOFT - 64) / NHS;                   // set 0: even tiles, set 1: odd tiles (= the hand-over buffer)
+    const int kl = (tid - NSOFT - 64) % NHS;                     // key inside a tile
+    const ekv_step& st = a.st;
+    const int P = st.score_offset;
+    const int n_s = a.n_before + 1 - P;
+    const bool evicting = st.evict > 0 && st.policy != EKV_POLICY_NONE;
+    float* Sg = a.S + (size_t)unit * a.cap;
+    float* SQg = a.SQ + (size_t)unit * a.cap;
+    float* Cg = a.C + (size_t)unit * a.cap;
+    const bool stateful = st.policy == EKV_POLICY_ROCO || st.policy == EKV_POLICY_H2O || st.policy == EKV_POLICY_TOVA;
+    const uint8_t need_flag = !evicting ? 0 : st.policy == EKV_POLICY_ROCO ? F_CAND : (st.policy == EKV_POLICY_RANGE ? 0 : F_FEAS);
+    const bool roco_sel = evicting && st.policy == EKV_POLICY_ROCO;
+    const float inv_g = 1.0f / (float)G;
+    if (stateful && hset == 0) {
+      // this slice's policy state -> L2 while the K phase streams (the helpers idle until the V phase): the per-tile loads
+      // below then cost an L2 hit instead of a DRAM round trip per tile
+      int cnt = T_ * TKEYS;
+      if (cnt > a.cap - first) cnt = a.cap - first;
+      const int lines = (cnt * 4 + 127) / 128;
+      for (int i = kl; i < 3 * lines; i += NHS) {
+        const float* base = (i < lines ? Sg : (i < 2 * lines ? SQg : Cg)) + first;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + (size_t)(i % lines) * 128));
+      }
+    }
+    float s_nx = 0.f, sq_nx = 0.f, c_nx = 1.f;                   // state of the NEXT tile's entry, loaded one tile ahead
+    auto load_state = [&](int i, float& sv, float& sq, float& cc) {
+      sv = 0.f; sq = 0.f; cc = 1.f;
+      if (i < T_ && stateful) {
+        const int rl = lj[i * TKEYS + kl];
+        if (rl >= P) { const int ph = first + i * TKEYS + kl; sv = Sg[ph]; sq = SQg[ph]; cc = Cg[ph]; }
+      }
+    };
+    for (int i = hset; i < T_; i += 2) {
+      const int pb = i & 1, e = i * TKEYS + kl;
+      mbar_wait(&bars[B_FSFULL + pb], (i >> 1) & 1);             // (first tile: the slot-map slice is final as well)
+      const float fsum = fs[pb * TKEYS + kl];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_FSEMPTY + pb]);
+      if (i == hset) load_state(i, s_nx, sq_nx, c_nx);
+      float sv = s_nx, sq = sq_nx, cc = c_nx;
+      load_state(i + 2, s_nx, sq_nx, c_nx);
+      const int rl = lj[e];
+      uint32_t ka = 0, kb = 0;
+      uint8_t f = 0;
+      bool dirty = false;
+      if (rl >= 0 && rl >= P) {
+        float ds = 0.f, dsq = 0.f;
+        if (st.accumulate) {
+          ds = G == 1 ? fsum : Tr<T>::round_f(__fmul_rn(fsum, inv_g));          // process_for_mqa_gqa, easykv.py:188-196
+          dsq = Tr<T>::round_f(__fmul_rn(ds, ds));                              // p**2 in the model dtype, :296
+        }
+        entry_update(st, rl - P, n_s, false, ds, dsq, sv, sq, cc, ka, kb, f, dirty);
+        if (dirty) { const int ph = first + e; Sg[ph] = sv; SQg[ph] = sq; Cg[ph] = cc; }
+      }
+      const bool keyed = (f & need_flag) == need_flag && need_flag;
+      kk[e] = keyed ? (((unsigned long long)kb << 32) | ka) : ~0ull;
+      if (roco_sel) {                                                           // the select's histograms, on the fly
+        __syncwarp();
+        bs.add_warp(keyed && (((unsigned long long)kb << 32) | ka) != ~0ull, ka, (uint32_t)rl, lsh, lane);
+      }
+    }
+    if (hset == 1) asm volatile("bar.arrive 2, %0;" ::"r"(NTAIL + NHS) : "memory");      // its keys are in shared memory; no part in the tail
+  }
   // ===== tail: victim walk, renumbering, append — the softmax warps and the helper warps (8 warps) ================================
-  if (warp < NSOFT / 32 || warp >= NSOFT / 32 + 2) {
+  if (warp < NSOFT / 32 || (warp >= NSOFT / 32 + 2 && warp < NSOFT / 32 + 2 + NHS / 32)) {
     const int ttid = warp < NSOFT / 32 ? tid : tid - 64;         // 0 .. NTAIL-1
     const int tw = ttid >> 5;                                    // tail warp 0 .. NTW-1
     const ekv_step& st = a.st;
@@ -644,7 +697,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     const int new_slot = a.new_slots ? a.new_slots[unit] : n_phys;
     unsigned long long* tl = a.timeline ? a.timeline + (size_t)blockIdx.x * 16 : nullptr;
     if (warp >= NSOFT / 32 + 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // helpers: peers are running
-    named_bar_sync(2, NTAIL);                                    // keys of every entry are in shared memory
+    named_bar_sync(2, NTAIL + NHS);                              // keys of every entry are in shared memory (helper set 1 arrives only)
     bool found = false;
     uint32_t l_c = 0;
     int owner = -1, e_c = -1;
@@ -652,148 +705,45 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       l_c = (uint32_t)(P + st.range_start);
       found = true;
     } else if (evicting) {
-      // Candidates are visited in (mean key, std key, logical index) order, NCAND per round: every warp proposes its
-      // NCAND smallest entries above the last one visited, the proposals are all-gathered over the cluster, every CTA
-      // derives the same NCAND smallest, and (roco) their std ranks are counted in one pass and summed over the cluster:
-      // the first candidate whose rank is below k_feasible is the slot argmin-over-the-k-smallest-std picks
-      // (easykv.py:322-324).  h2o_head / tova need the single smallest of the window (:311, :335).
+      // roco: the k_feasible-th smallest std from the histograms the V phase filled (ekv_bucket.cuh), then ONE pass over the
+      // entries — argmin of (mean, std, logical index) over the feasible ones, the cut bucket's entries listed — one exchange
+      // over the cluster, exact ranks of the listed entries (easykv.py:322-324).  h2o_head / tova: the pass and the exchange
+      // only (the window's argmin, :311, :335).
       const bool roco = st.policy == EKV_POLICY_ROCO;
-      const int ncand = roco ? NCAND : 1;
-      unsigned long long last_k = 0ull, last_lo = 0ull;         // candidates already visited: tuples <= (last_k, last_lo)
-      bool have_last = false;
-      for (int round = 0; !found; ++round) {
-        const int par = round & 1;
-        if (tl && ttid == 0) tl[8] = (unsigned long long)(round + 1);
-        unsigned long long wk = last_k, wlo = last_lo;
-        bool hl = have_last;
-        unsigned long long ck[NCAND], clo[NCAND];
-#pragma unroll
-        for (int c = 0; c < NCAND; ++c) {
-          unsigned long long bk = ~0ull, blo = ~0ull;
-          if (c < ncand) {
-#pragma unroll 4
-            for (int e = ttid; e < NEl; e += NTAIL) {            // the 8 warps partition the CTA's entries
-              const unsigned long long k = kk[e];
-              if (k < bk || (k == bk && k != ~0ull)) {
-                const unsigned long long lo = ((unsigned long long)(uint32_t)lj[e] << 32) | ((uint32_t)rank << 24) | (uint32_t)e;
-                const bool above = !hl || k > wk || (k == wk && lo > wlo);
-                if (above && k != ~0ull && (k < bk || lo < blo)) { bk = k; blo = lo; }
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o), olo = __shfl_xor_sync(0xffffffffu, blo, o);
-              if (ok < bk || (ok == bk && olo < blo)) { bk = ok; blo = olo; }
-            }
+      auto sync = [&] { named_bar_sync(2, NTAIL); };
+      Feasibility fz;
+      fz.mode = 0; fz.lsh = lsh; fz.T1 = 0u; fz.jT = 0xffffffffu;
+      fz.b.status = bk::OK; fz.b.bsel = 0; fz.b.rb = 0; fz.b.csel = 0; fz.b.kind = 0; fz.b.mtot = 0; fz.b.my_off = 0;
+      auto get = [&](int e, uint32_t& ka, uint32_t& kb, uint32_t& l) -> bool {
+        const unsigned long long k = kk[e];
+        if (k == ~0ull) return false;
+        ka = (uint32_t)k; kb = (uint32_t)(k >> 32); l = (uint32_t)lj[e];
+        return true;
+      };
+      if (roco) {
+        int hphase = 0;
+        auto hist_sync = [&] {
+          if (C > 1) {
+            // every thread's histogram adds precede a named barrier; one release-arrive per peer publishes them
+            if (ttid < C) umma::mbar_arrive_remote(map_to_rank(&bars[B_HRDY], ttid));
+            umma::mbar_wait_cluster(&bars[B_HRDY], hphase);
+            hphase ^= 1;
           }
-          ck[c] = bk; clo[c] = blo;
-          if (blo != ~0ull) { wk = bk; wlo = blo; hl = true; }
-        }
-        if (lane < C * NCAND) {                                  // lane (peer, candidate): two remote stores + one remote arrive
-          const int p = lane / NCAND, c = lane % NCAND;
-          unsigned long long tk = ck[0], tlo = clo[0];
-#pragma unroll
-          for (int q = 1; q < NCAND; ++q) if (c == q) { tk = ck[q]; tlo = clo[q]; }
-          unsigned long long* slot = &xcand[(((par * MAX_CLUSTER + rank) * NTW + tw) * NCAND + c) * 2];
-          if (C == 1) { slot[0] = tk; slot[1] = tlo; }
-          else {
-            const uint32_t dst = map_to_rank(slot, p);
-            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst), "l"(tk) : "memory");
-            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst + 8), "l"(tlo) : "memory");
-            umma::mbar_arrive_remote(map_to_rank(&bars[B_XCAND + par], p));
-          }
-        }
-        if (C > 1 && ttid == 0) umma::mbar_wait_cluster(&bars[B_XCAND + par], (round >> 1) & 1);
-        named_bar_sync(2, NTAIL);
-        // the cluster's NCAND smallest proposals, in order (every CTA computes the same list)
-        if (tw == 0) {
-          unsigned long long pk = 0ull, plo = 0ull;
-          bool hp = false;
-          const int total = C * NTW * NCAND;
-          for (int c = 0; c < NCAND; ++c) {
-            unsigned long long bk = ~0ull, blo = ~0ull;
-            for (int i = lane; i < total; i += 32) {
-              const int p = i / (NTW * NCAND), rest = i % (NTW * NCAND);
-              const unsigned long long k = xcand[((par * MAX_CLUSTER + p) * NTW * NCAND + rest) * 2];
-              const unsigned long long lo = xcand[((par * MAX_CLUSTER + p) * NTW * NCAND + rest) * 2 + 1];
-              const bool above = !hp || k > pk || (k == pk && lo > plo);
-              if (lo != ~0ull && above && (k < bk || (k == bk && lo < blo))) { bk = k; blo = lo; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o), olo = __shfl_xor_sync(0xffffffffu, blo, o);
-              if (ok < bk || (ok == bk && olo < blo)) { bk = ok; blo = olo; }
-            }
-            if (lane == 0) { win[2 * c] = bk; win[2 * c + 1] = blo; }
-            if (blo != ~0ull) { pk = bk; plo = blo; hp = true; }
-          }
-        }
-        named_bar_sync(2, NTAIL);
-        unsigned long long wnk[NCAND], wnlo[NCAND];
-#pragma unroll
-        for (int c = 0; c < NCAND; ++c) { wnk[c] = win[2 * c]; wnlo[c] = win[2 * c + 1]; }
-        if (wnlo[0] == ~0ull) break;                             // no candidate left anywhere (uniform)
-        if (!roco) {
-          l_c = (uint32_t)(wnlo[0] >> 32); owner = (int)((wnlo[0] >> 24) & 0xffu); e_c = (int)(wnlo[0] & 0xffffffu);
-          found = true;
-          break;
-        }
-        // std ranks of the candidates: this CTA's share, then the cluster's
-        int cnt[NCAND];
-#pragma unroll
-        for (int c = 0; c < NCAND; ++c) cnt[c] = 0;
-#pragma unroll 4
-        for (int e = ttid; e < NEl; e += NTAIL) {
-          const unsigned long long k = kk[e];
-          if (k != ~0ull) {
-            const uint32_t ka = (uint32_t)k, le = (uint32_t)lj[e];
-#pragma unroll
-            for (int c = 0; c < NCAND; ++c) {
-              const uint32_t ka_c = (uint32_t)wnk[c], lc = (uint32_t)(wnlo[c] >> 32);
-              cnt[c] += (ka < ka_c || (ka == ka_c && le < lc)) ? 1 : 0;
-            }
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < NCAND; ++c) cnt[c] = __reduce_add_sync(0xffffffffu, cnt[c]);
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < NCAND; ++c) wcnt[tw * NCAND + c] = cnt[c];
-        }
-        named_bar_sync(2, NTAIL);
-        if (ttid < NCAND * C) {                                  // (candidate, peer)
-          const int c = ttid % NCAND, p = ttid / NCAND;
-          int tot = 0;
-#pragma unroll
-          for (int q = 0; q < NTW; ++q) tot += wcnt[q * NCAND + c];
-          if (C == 1) xcnt[(par * MAX_CLUSTER) * NCAND + c] = tot;
-          else {
-            st_cluster_u32(map_to_rank(&xcnt[(par * MAX_CLUSTER + rank) * NCAND + c], p), (uint32_t)tot);
-            umma::mbar_arrive_remote(map_to_rank(&bars[B_XCNT + par], p));
-          }
-        }
-        if (C > 1 && ttid == 0) umma::mbar_wait_cluster(&bars[B_XCNT + par], (round >> 1) & 1);
-        named_bar_sync(2, NTAIL);
-#pragma unroll
-        for (int c = 0; c < NCAND; ++c) {
-          if (!found && wnlo[c] != ~0ull) {
-            int rk = 0;
-            for (int p = 0; p < C; ++p) rk += xcnt[(par * MAX_CLUSTER + p) * NCAND + c];
-            if (rk < st.k_feasible) {
-              l_c = (uint32_t)(wnlo[c] >> 32); owner = (int)((wnlo[c] >> 24) & 0xffu); e_c = (int)(wnlo[c] & 0xffffffu);
-              found = true;
-            }
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < NCAND; ++c)                          // next round: candidates above the last one visited
-          if (wnlo[c] != ~0ull) { last_k = wnk[c]; last_lo = wnlo[c]; have_last = true; }
-        named_bar_sync(2, NTAIL);                                // win / wcnt are rewritten by the next round
-        if (!found && round + 1 >= MAX_WALK) {
-          // The low-mean slots keep falling outside the k_feasible lowest std (e.g. slots whose probabilities barely vary:
-          // std ~ 0 or NaN): stop walking and select in bounded time.  Cluster-wide MSB-first radix select (8 bits per
-          // pass, every pass's 256-bin histogram all-gathered over DSMEM) of the k_feasible-th smallest std key, ties at
-          // the cut broken by logical index, then ONE cluster argmin of (mean, std, logical index) over the feasible set.
+        };
+        hist_sync();
+        auto ld = [&](const uint32_t* ptr, int peer) -> uint4 {
+          if (C == 1 || peer == rank) return *reinterpret_cast<const uint4*>(ptr);
+          uint4 v;
+          asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(map_to_rank(ptr, peer)) : "memory");
+          return v;
+        };
+        fz.b = bucket_scan<MAX_CLUSTER>(bs, st.k_feasible, C, rank, ttid, NTAIL, NEl, sync, ld, get, hist_sync);
+        fz.mode = 1;
+        if (tl && ttid == 0) tl[8] = (unsigned long long)(1 + fz.b.status + 4 * fz.b.kind);
+        if (fz.b.status == bk::FALLBACK) {
+          // The cut falls into a bucket crowded with non-NaN keys (e.g. thousands of slots whose std is exactly 0): select in
+          // bounded time.  Cluster-wide MSB-first radix select (8 bits per pass, every pass's 256-bin histogram all-gathered
+          // over DSMEM) of the k_feasible-th smallest std key, ties at the cut broken by logical index.
           int xpass = 0;
           auto cluster_radix32 = [&](int m, auto key, auto pred, uint32_t& Tk, int& needk, int& tcount) {
             uint32_t prefix = 0u, maskp = 0u;
@@ -875,54 +825,30 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
             cluster_radix32(need1, [&](int e) { return (uint32_t)lj[e]; },
                             [&](int e) { return kk[e] != ~0ull && (uint32_t)kk[e] == T1; }, jT, nd, tc);
           }
-          // one cluster argmin of (mean key, std key, logical index) over the feasible set
-          unsigned long long bk = ~0ull, blo = ~0ull;
-          for (int e = ttid; e < NEl; e += NTAIL) {
-            const unsigned long long k = kk[e];
-            if (k == ~0ull) continue;
-            const uint32_t ka = (uint32_t)k, le = (uint32_t)lj[e];
-            if (!(ka < T1 || (ka == T1 && le <= jT))) continue;
-            const unsigned long long lo = ((unsigned long long)le << 32) | ((uint32_t)rank << 24) | (uint32_t)e;
-            if (k < bk || (k == bk && lo < blo)) { bk = k; blo = lo; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o), olo = __shfl_xor_sync(0xffffffffu, blo, o);
-            if (ok < bk || (ok == bk && olo < blo)) { bk = ok; blo = olo; }
-          }
-          const int par2 = (round + 1) & 1;                      // the next round's exchange slot
-          named_bar_sync(2, NTAIL);                              // (the histogram exchange shares the candidate buffer)
-          if (lane < C * NCAND) {
-            const int p = lane / NCAND, c = lane % NCAND;
-            unsigned long long* slot = &xcand[(((par2 * MAX_CLUSTER + rank) * NTW + tw) * NCAND + c) * 2];
-            if (C == 1) { slot[0] = c == 0 ? bk : ~0ull; slot[1] = c == 0 ? blo : ~0ull; }
-            else {
-              const uint32_t dst = map_to_rank(slot, p);
-              asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst), "l"(c == 0 ? bk : ~0ull) : "memory");
-              asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst + 8), "l"(c == 0 ? blo : ~0ull) : "memory");
-              umma::mbar_arrive_remote(map_to_rank(&bars[B_XCAND + par2], p));
-            }
-          }
-          if (C > 1 && ttid == 0) umma::mbar_wait_cluster(&bars[B_XCAND + par2], ((round + 1) >> 1) & 1);
-          named_bar_sync(2, NTAIL);
-          unsigned long long gk = ~0ull, glo = ~0ull;
-          for (int i = lane; i < C * NTW; i += 32) {
-            const int p = i / NTW, w8 = i % NTW;
-            const unsigned long long k = xcand[(((par2 * MAX_CLUSTER + p) * NTW + w8) * NCAND) * 2];
-            const unsigned long long lo = xcand[(((par2 * MAX_CLUSTER + p) * NTW + w8) * NCAND) * 2 + 1];
-            if (lo != ~0ull && (k < gk || (k == gk && lo < glo))) { gk = k; glo = lo; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, gk, o), olo = __shfl_xor_sync(0xffffffffu, glo, o);
-            if (ok < gk || (ok == gk && olo < glo)) { gk = ok; glo = olo; }
-          }
-          if (glo != ~0ull) {
-            l_c = (uint32_t)(glo >> 32); owner = (int)((glo >> 24) & 0xffu); e_c = (int)(glo & 0xffffffu);
-            found = true;
-          }
-          break;
+          fz.mode = 2; fz.T1 = T1; fz.jT = jT;
         }
+      }
+      auto push = [&](unsigned long long* slot, unsigned long long hi, unsigned long long lo) {
+        if (C == 1) { slot[0] = hi; slot[1] = lo; }
+        else
+          for (int p2 = 0; p2 < C; ++p2) {
+            const uint32_t dst = map_to_rank(slot, p2);
+            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst), "l"(hi) : "memory");
+            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst + 8), "l"(lo) : "memory");
+          }
+      };
+      bucket_pass(bs, fz, NEl, rank, ttid, NTAIL, get, push);
+      if (C > 1) {
+        __syncwarp();                                            // the warp's remote stores precede its lanes' release-arrives
+        if (lane < C) umma::mbar_arrive_remote(map_to_rank(&bars[B_XG], lane));
+        umma::mbar_wait_cluster(&bars[B_XG], 0);
+      } else {
+        sync();
+      }
+      Tuple128 wn;
+      if (bucket_final(bs, fz, C, ttid, NTAIL, sync, wn)) {
+        l_c = (uint32_t)(wn.lo >> 32); owner = (int)((wn.lo >> 24) & 0xffu); e_c = (int)(wn.lo & 0xffffffu);
+        found = true;
       }
     }
     if (tl && ttid == 0) tl[5] = global_ns();

@@ -18,6 +18,7 @@
 // run of equal keys.
 #pragma once
 #include "ekv_common.cuh"
+#include "ekv_bucket.cuh"
 
 namespace ekv {
 
@@ -128,11 +129,6 @@ __device__ __forceinline__ void radix_select(int NE, int m, Key key, Pred pred, 
   if (need < 0) need = 0;
 }
 
-struct Tuple128 { unsigned long long hi, lo; };
-__device__ __forceinline__ bool tuple_less(const Tuple128& a, const Tuple128& b) {
-  return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
-}
-
 // One scored entry's share of a forward: policy-state update (accumulate, counter) and, when evicting,
 // its selection keys and candidate flags.  j = logical index relative to score_offset, n_s = scored
 // slots after the append.  Shared by every kernel so that the arithmetic is the same everywhere.
@@ -152,7 +148,10 @@ __device__ __forceinline__ void entry_update(const ekv_step& st, int j, int n_s,
   if (evicting) {
     if (policy == EKV_POLICY_ROCO) {
       const float mean = __fdiv_rn(s, cc);
-      float sd = __fsqrt_rn(__fsub_rn(__fdiv_rn(sq, cc), __fmul_rn(mean, mean)));
+      const float var = __fsub_rn(__fdiv_rn(sq, cc), __fmul_rn(mean, mean));
+      // sqrt of a negative variance (p**2 underflowed in the model dtype) is NaN: said directly, so that the IEEE
+      // square root's out-of-line slow path is not entered by the many such slots of a long fp16 cache
+      float sd = var < 0.f ? __int_as_float(0x7fc00000) : __fsqrt_rn(var);
       if (j >= n_s - st.protect_last || j < st.sink_protect) sd = 1e9f;
       ka = order_key(sd);
       kb = order_key(mean);

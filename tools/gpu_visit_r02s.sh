@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out
+echo "== decode parity tests"; timeout 1500 python -m pytest tests -m gpu -q -x -k "decode or golden or reference or fullsize or driver or select" 2>&1 | tail -8 | tee $OUT/r02s_pytest.txt
+echo "== decode A/B"; timeout 900 python tools/decode_ab.py c2 c2_b1 c2_b8 c4_roco c3_decode c3_decode_b4 c5 c5_b32 2>&1 | grep -v "umma_c1\|umma_c4\|umma_c2" | tee $OUT/r02s_decode_ab.jsonl
+for args in "8 64 8 8256 0"; do echo "-- $args"; timeout 120 python tools/decode_umma_timeline.py $args 2>&1 | tee -a $OUT/r02s_decode_umma_timeline.txt; done
+for args in "1 32 32 1088 0" "8 32 32 1088 0"; do echo "-- $args"; timeout 120 python tools/cluster_timeline.py $args 2>&1 | tee -a $OUT/r02s_cluster_timeline.txt; done
