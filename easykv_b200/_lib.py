@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeasykv_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 F16, BF16, F32 = 0, 1, 2
 POLICY_NONE, POLICY_ROCO, POLICY_H2O, POLICY_TOVA, POLICY_RANGE = 0, 1, 2, 3, 4
@@ -26,14 +26,15 @@ class Step(C.Structure):
                 ("c_new_step", C.c_float), ("k_feasible", C.c_int32), ("protect_last", C.c_int32),
                 ("sink_protect", C.c_int32), ("win_lo", C.c_int32), ("win_recent", C.c_int32),
                 ("range_start", C.c_int32), ("arith", C.c_int32), ("tova_head_mean", C.c_int32),
-                ("raw_colsum", C.c_int32)]
+                ("raw_colsum", C.c_int32), ("budget_gate", C.c_int32)]
 
 
 class LayerIO(C.Structure):
     _fields_ = [("q", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p), ("out", C.c_void_p),
                 ("K", C.c_void_p), ("V", C.c_void_p), ("S", C.c_void_p), ("SQ", C.c_void_p), ("C", C.c_void_p),
                 ("lidx", C.c_void_p), ("new_slots", C.c_void_p), ("victim_slots", C.c_void_p),
-                ("victim_lidx", C.c_void_p), ("scratch", C.c_void_p)]
+                ("victim_lidx", C.c_void_p), ("scratch", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+                ("k_new_raw", C.c_void_p), ("seq_n_before", C.c_void_p)]
 
 
 class Shape(C.Structure):

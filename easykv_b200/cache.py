@@ -54,6 +54,11 @@ class BudgetedKVCache:
         self.free = [None] * num_layers    # int32 [B, Hkv, f]: free physical slots inside [0, n_phys)
         self.scratch = None
         self.K_raw = None                  # streaming variant: the un-rotated keys, same physical layout as K
+        # streaming variant, decode steps: rotate the cached rows inside the attention kernel (True), always in a separate
+        # pass (False), or "auto": fused while the batch is small enough for the cluster-split kernel (latency-bound, where
+        # one launch less and one cache pass less win); the persistent kernel's K phase is instruction-bound with the
+        # rotation in it (measured 598 vs 434 us per layer-step at 64 sequences), so large batches stay two-pass
+        self.fused_streaming = "auto"
         self._shape_cache = [self._shape(l, 1) for l in range(num_layers)]
         self._io_cache = [self._io(l) for l in range(num_layers)]
         self._rope_shape = self._shape(0, 1)
@@ -160,19 +165,27 @@ class BudgetedKVCache:
             cos, sin = cos.to(self.dtype), sin.to(self.dtype)
         cos, sin = cos.contiguous(), sin.contiguous()
         n = self.n[l]
+        pos = torch.arange(n, n + ql, dtype=torch.int32, device=self.device)[None].expand(B, -1)
+        q, k_rot, v = self.rope_qkv(q_in, k_in, v_in, cos, sin, pos)
+        k_raw = k_in.view(B, ql, self.Hkv, self.d).transpose(1, 2)
+        fused = self.fused_streaming is True or (self.fused_streaming == "auto" and 2 * B * self.Hkv <= 148)
+        if fused and ql == 1 and kernel == 0 and self.dtype != torch.float32 and self.d == 128 and n:
+            # decode steps: the kernels read K_raw and rotate every cached row at its cache-relative position on the fly
+            # (ekv_layer_io.rope_cos / rope_sin / k_new_raw) — no rotated copy of the cache is written or re-read
+            try:
+                return self.step(l, sp, q, k_rot, v, apply=apply, kernel=kernel, rope=(cos, sin, k_raw.contiguous()))
+            except NotImplementedError:
+                pass                                      # a shape the fused kernels decline: the two-pass path below
         if n:                                             # K = rope(K_raw, position = logical index)
             shape = self._shape(l, 0)
             io = self._io(l)
             _lib.check(self.lib.ekv_rope_cache(C.byref(shape), C.byref(io), self.K_raw[l].data_ptr(), cos.data_ptr(),
                                                sin.data_ptr(), torch.cuda.current_stream().cuda_stream))
-        pos = torch.arange(n, n + ql, dtype=torch.int32, device=self.device)[None].expand(B, -1)
-        q, k_rot, v = self.rope_qkv(q_in, k_in, v_in, cos, sin, pos)
         if self.free_count(l) == ql:                      # the slots the fused kernel will append to
             slots = self.free[l].long()
         else:
             slots = torch.arange(self.n_phys[l], self.n_phys[l] + ql, device=self.device).expand(B, self.Hkv, ql)
         out, vl = self.step(l, sp, q, k_rot, v, apply=apply, kernel=kernel)
-        k_raw = k_in.view(B, ql, self.Hkv, self.d).transpose(1, 2)
         self.K_raw[l].scatter_(2, slots[..., None].expand(B, self.Hkv, ql, self.d), k_raw)
         return out, vl
 
@@ -195,7 +208,7 @@ class BudgetedKVCache:
             self.S[l].copy_(self.S[l].to(self.dtype).float())
             self.SQ[l].copy_(self.SQ[l].to(self.dtype).float())
 
-    def step(self, l, sp: StepParams, q, k_new, v_new, apply=True, kernel=0):
+    def step(self, l, sp: StepParams, q, k_new, v_new, apply=True, kernel=0, rope=None):
         """One forward of layer `l`: q `[B, H, q_len, d]`, k_new / v_new `[B, Hkv, q_len, d]`
         (post-RoPE).  Returns (out `[B, H, q_len, d]`, victim_lidx `[B, Hkv, evict]` int32 or None).
         With `apply=False` the victims are only reported (the caller may `evict()` others)."""
@@ -237,7 +250,13 @@ class BudgetedKVCache:
         io.victim_slots = None if vs is None else vs.data_ptr()
         io.victim_lidx = None if vl is None else vl.data_ptr()
         io.scratch = self.scratch.data_ptr() if need else None
-        _lib.check(self.lib.ekv_attend_evict(C.byref(shape), C.byref(io), C.byref(cstep), kernel, self._stream()))
+        if rope is not None:                              # fused streaming variant: K_raw is the cache, rotated while read
+            io.K, io.rope_cos, io.rope_sin, io.k_new_raw = self.K_raw[l].data_ptr(), rope[0].data_ptr(), rope[1].data_ptr(), rope[2].data_ptr()
+        try:
+            _lib.check(self.lib.ekv_attend_evict(C.byref(shape), C.byref(io), C.byref(cstep), kernel, self._stream()))
+        finally:
+            if rope is not None:
+                io.K, io.rope_cos, io.rope_sin, io.k_new_raw = self.K[l].data_ptr(), None, None, None
         self.n[l] += q_len
         if new_slots is None:
             self.n_phys[l] += q_len
@@ -403,3 +422,70 @@ class SteadyStep:
 
 
 SteadyDecode = SteadyStep
+
+
+class RaggedDecode:
+    """Decode steps over a batch whose sequences hold DIFFERENT numbers of slots (the reference is hard-wired to one
+    sequence; SURVEY §8b proposed per-sequence lengths).  ABI: `ekv_layer_io.seq_n_before` + `ekv_step.budget_gate` — a
+    sequence below the budget only accumulates and appends (at its own physical extent), one above it evicts and the
+    next token reuses the victim's slot, exactly as `if cur_kv_size - len(prefix) > budget` (easykv.py:303) decides for
+    a single sequence.  No host synchronisation: the per-sequence counts follow from the lengths and the gate."""
+
+    def __init__(self, cache: BudgetedKVCache, lengths, budget_gate: int):
+        c = self.cache = cache
+        assert len(lengths) == c.B
+        self.gate = int(budget_gate)
+        self.n = [[int(x) for x in lengths] for _ in range(c.L)]             # valid slots per layer and sequence
+        self.ext = [[int(x) for x in lengths] for _ in range(c.L)]           # physical extent per layer and sequence
+        self.victims = [None] * c.L                                          # last step's victim slots [B, Hkv, 1] (-1: none)
+        self.had = [[False] * c.B for _ in range(c.L)]                       # ... and whether sequence b evicted in it
+
+    def load_prefill(self, l, Ks, Vs, C_inits=None):
+        """Sequence b starts from Ks[b], Vs[b] `[Hkv, n_b, d]`; slots beyond n_b are free."""
+        c = self.cache
+        c.S[l].zero_(); c.SQ[l].zero_(); c.Cn[l].zero_(); c.lidx[l].fill_(-1)
+        for b, (K, V) in enumerate(zip(Ks, Vs)):
+            n = K.shape[1]
+            assert n == self.n[l][b]
+            c.K[l][b, :, :n].copy_(K); c.V[l][b, :, :n].copy_(V)
+            c.lidx[l][b, :, :n] = torch.arange(n, dtype=torch.int32, device=c.device)
+            if C_inits is not None:
+                ci = torch.as_tensor(C_inits[b], dtype=torch.float32, device=c.device)
+                c.Cn[l][b, :, n - ci.numel():n] = ci
+        c.n[l] = c.n_phys[l] = max(self.n[l])
+        c.free[l] = None
+        self.victims[l] = None
+        self.had[l] = [False] * c.B
+
+    def step(self, l, sp: StepParams, q, k_new, v_new, kernel=0):
+        """q `[B, H, 1, d]`, k_new / v_new `[B, Hkv, 1, d]`.  Returns (out, victim_lidx `[B, Hkv, 1]`, -1 where the
+        sequence did not evict)."""
+        from dataclasses import replace
+        c = self.cache
+        sp = replace(sp, budget_gate=self.gate)
+        n, ext = self.n[l], self.ext[l]
+        dev = c.device
+        seq_n = torch.tensor(n, dtype=torch.int32, device=dev)
+        own = torch.tensor(ext, dtype=torch.int32, device=dev)[:, None, None].expand(c.B, c.Hkv, 1)
+        slots = own.contiguous() if self.victims[l] is None else torch.where(self.victims[l] >= 0, self.victims[l], own).contiguous()
+        out = torch.empty_like(q)
+        vv = torch.empty(2, c.B, c.Hkv, 1, dtype=torch.int32, device=dev)
+        shape = _lib.Shape(dtype=_DTYPES[c.dtype], B=c.B, H=c.H, Hkv=c.Hkv, d=c.d, q_len=1, cap=c.cap, n_before=max(n),
+                           n_phys=max(ext))
+        io = c._io(l, q=q.contiguous(), k_new=k_new.contiguous(), v_new=v_new.contiguous(), out=out, new_slots=slots,
+                   victim_slots=vv[0], victim_lidx=vv[1], seq_n_before=seq_n)
+        cstep = sp.to_c(apply=True, arith=c.arith)
+        _lib.check(c.lib.ekv_attend_evict(C.byref(shape), C.byref(io), C.byref(cstep), kernel, c._stream()))
+        had = self.had[l]
+        for b in range(c.B):
+            if not had[b]:                                                   # appended at its own extent (no victim slot to reuse)
+                ext[b] += 1
+            if self.gate > 0 and n[b] + 1 - sp.score_offset <= self.gate:    # below the budget: grew by one, nothing evicted
+                n[b] += 1
+                had[b] = False
+            else:
+                had[b] = True
+        self.victims[l] = vv[0]
+        c.n[l], c.n_phys[l] = max(n), max(ext)
+        return out, vv[1]
+

@@ -49,6 +49,9 @@ static int build_args(const ekv_shape* sh, const ekv_layer_io* io, const ekv_ste
   a.q = io->q; a.k_new = io->k_new; a.v_new = io->v_new; a.out = io->out;
   a.K = io->K; a.V = io->V; a.S = io->S; a.SQ = io->SQ; a.C = io->C; a.lidx = io->lidx;
   a.new_slots = io->new_slots; a.victim_slots = io->victim_slots; a.victim_lidx = io->victim_lidx; a.scratch = io->scratch;
+  a.rope_cos = io->rope_cos; a.rope_sin = io->rope_sin; a.k_new_raw = io->k_new_raw; a.seq_n_before = io->seq_n_before;
+  if ((a.rope_cos != nullptr) != (a.rope_sin != nullptr) || (a.rope_cos != nullptr) != (a.k_new_raw != nullptr))
+    return set_error(EKV_ERR_INVALID, "rope_cos, rope_sin and k_new_raw go together");
   a.dtype = sh->dtype; a.B = sh->B; a.H = sh->H; a.Hkv = sh->Hkv; a.d = sh->d; a.q_len = sh->q_len; a.cap = sh->cap;
   a.n_before = sh->n_before; a.n_phys = sh->n_phys;
   a.scale_div = (float)std::sqrt((double)sh->d);
@@ -150,6 +153,7 @@ int ekv_attend_evict(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const bool defer = a.st.policy == EKV_POLICY_TOVA && a.st.tova_head_mean && a.st.accumulate;
+  if (defer && (a.rope_cos || a.seq_n_before)) return set_error(EKV_ERR_UNSUPPORTED, "tova_head_mean with fused streaming / ragged batches");
   if (defer) {
     // per-head accumulate inside the fused kernel, then the cross-head mean, then the select
     if (!io->scratch) return set_error(EKV_ERR_INVALID, "tova_head_mean needs scratch (ekv_scratch_bytes)");
@@ -172,6 +176,10 @@ int ekv_attend_evict(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step
     rc = launch_decode(a, s);
     if (rc != EKV_ERR_UNSUPPORTED) return rc;
   }
+  if (a.rope_cos)      // only the decode kernels rotate on the fly: the caller falls back to ekv_rope_cache + a second buffer
+    return set_error(EKV_ERR_UNSUPPORTED, "fused streaming (rope_cos) needs a decode step (q_len == 1) in a 16-bit dtype with d == 128");
+  if (a.seq_n_before && sh->q_len != 1)
+    return set_error(EKV_ERR_UNSUPPORTED, "ragged batches (seq_n_before) are served for decode steps (q_len == 1) only");
   return launch_chunk_auto(a, sh, kernel, s);
 }
 

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
   float* cpart = reinterpret_cast<float*>(pool + L.off_cpart);
 
   const int unit = blockIdx.x, b = unit / a.Hkv, h = unit % a.Hkv;
+  const int nb = a.seq_n_before ? a.seq_n_before[b] : a.n_before;            // ragged batches: this sequence's valid slots
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Grp grp{tid, NT, 0};
   const T* Kg = reinterpret_cast<const T*>(a.K) + (size_t)unit * a.cap * D;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
     for (int e = tid; e < n_phys; e += NT) lj[e] = lg[e];
     for (int i = tid; i < QL; i += NT) {
       ns[i] = a.new_slots ? a.new_slots[(size_t)unit * QL + i] : n_phys + i;
-      lj[n_phys + i] = a.n_before + i;
+      lj[n_phys + i] = nb + i;
     }
     for (int e = tid; e < NE; e += NT) { colS[e] = 0.f; colSQ[e] = 0.f; }
   }
@@ -293,7 +294,17 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
     ds = a.st.raw_colsum ? colS[e] : Tr<T>::round_f(colS[e]);       // p.sum(dim=1) is a model-dtype result (easykv.py:450)
     dsq = a.st.raw_colsum ? colSQ[e] : Tr<T>::round_f(colSQ[e]);    // (p**2).sum(dim=1) likewise (:451)
   };
-  state_select_apply(a.st, u, a.n_before, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
+  if (a.st.budget_gate > 0 && nb + QL - a.st.score_offset <= a.st.budget_gate) {      // ragged batches: this sequence is below the budget
+    ekv_step stu = a.st;
+    stu.evict = 0;
+    state_select_apply(stu, u, nb, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
+    for (int t = tid; t < a.st.evict; t += gen::NT) {
+      if (u.victim_lidx) u.victim_lidx[t] = -1;
+      if (u.victim_slots) u.victim_slots[t] = -1;
+    }
+  } else {
+    state_select_apply(a.st, u, nb, n_phys, QL, /*lj_preloaded=*/true, accf, sc, grp);
+  }
 }
 
 template <typename T, int G> static int launch_general_tg(const KernelArgs& a, cudaStream_t stream) {

@@ -89,6 +89,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// pull `bytes` (a multiple of 16, from a 16-byte aligned address) into L2 without waiting for them
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // Ampere-style per-thread async copies (SASS LDGSTS) for the small per-unit headers
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -257,6 +262,35 @@ __device__ __forceinline__ void axpy8(__nv_bfloat16 p, const Row8<__nv_bfloat16>
   axpy2_bf16(pb, v.u.x, o[0], o[1]); axpy2_bf16(pb, v.u.y, o[2], o[3]);
   axpy2_bf16(pb, v.u.z, o[4], o[5]); axpy2_bf16(pb, v.u.w, o[6], o[7]);
 }
+
+// ---------------------------------------------------------------------------------------
+// RoPE of one cached row while it is read (fused streaming variant, llama_patch.py:310-327): the row is spread over
+// the 16 lanes of a half-warp, 8 consecutive dims per lane (Row8), so lane l16 ^ 8 holds the partner half
+// (rotate_half, :47-55).  Packed model-dtype arithmetic = apply_rotary_pos_emb's roundings: rn(x*cos), rn(rot*sin),
+// rn(sum) (:70) — bit-identical to rope_cache_kernel, whose fp32 product / sum of two 11-bit (8-bit) operands rounds once.
+// NOT inlined on purpose: inlined into the cluster decode kernel's unrolled K loop, the g = 2 and g = 8 instantiations
+// (nvcc 12.9, sm_100a, -O3) fetched table rows through garbage addresses (compute-sanitizer: invalid 16-byte global
+// reads in this function; g = 1 / 4 and the persistent kernel were fine, and so was any build with one more live
+// value in the loop) although the SASS address arithmetic reads correctly; as a call every instantiation is
+// bit-identical to the two-pass path (tests/test_gpu_stream_ragged.py covers g = 1, 2, 4, 8 on both kernels).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mul2_rn(uint32_t a, uint32_t b, __half) { uint32_t r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t add2_rn(uint32_t a, uint32_t b, __half) { uint32_t r; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mul2_rn(uint32_t a, uint32_t b, __nv_bfloat16) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t add2_rn(uint32_t a, uint32_t b, __nv_bfloat16) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+template <typename T> __device__ __noinline__ void rope_row8(Row8<T>& x, int l16, const void* cos_t, const void* sin_t, int pos) {
+  // table row `pos` = 16 uint4 (d == 128, 16-bit dtype)
+  const uint4 c = *(reinterpret_cast<const uint4*>(cos_t) + (size_t)pos * 16 + l16);
+  const uint4 sn = *(reinterpret_cast<const uint4*>(sin_t) + (size_t)pos * 16 + l16);
+  const uint32_t sg = l16 < 8 ? 0x80008000u : 0u;              // rotate_half: -x2 under the lower half, +x1 under the upper
+  uint4 o;
+  o.x = __shfl_xor_sync(0xffffffffu, x.u.x, 8) ^ sg; o.y = __shfl_xor_sync(0xffffffffu, x.u.y, 8) ^ sg;
+  o.z = __shfl_xor_sync(0xffffffffu, x.u.z, 8) ^ sg; o.w = __shfl_xor_sync(0xffffffffu, x.u.w, 8) ^ sg;
+  const T t{};
+  x.u.x = add2_rn(mul2_rn(x.u.x, c.x, t), mul2_rn(o.x, sn.x, t), t); x.u.y = add2_rn(mul2_rn(x.u.y, c.y, t), mul2_rn(o.y, sn.y, t), t);
+  x.u.z = add2_rn(mul2_rn(x.u.z, c.z, t), mul2_rn(o.z, sn.z, t), t); x.u.w = add2_rn(mul2_rn(x.u.w, c.w, t), mul2_rn(o.w, sn.w, t), t);
+}
+template <> __device__ __forceinline__ void rope_row8<float>(Row8<float>&, int, const void*, const void*, int) {}   // (fp32 is not fused)
 
 template <typename T> __device__ __forceinline__ T neg_inf();
 template <> __device__ __forceinline__ __half neg_inf<__half>() { return __ushort_as_half(0xfc00); }

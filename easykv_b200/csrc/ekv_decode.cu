@@ -60,7 +60,9 @@ template <typename T> struct DecodeSmem {
 
 // NG consumer groups per CTA: 2 = one CTA per SM whose groups ping-pong over one shared ring;
 // 1 = a lighter CTA (one group, its own ring) of which two are resident per SM and stream independently.
-template <typename T, int G, int NG>
+// EXT: the instantiation that also serves the fused streaming variant (io.rope_cos: cached rows rotated while read) and
+// ragged batches (io.seq_n_before / step.budget_gate); the plain one carries none of that code (96 registers, no spills).
+template <typename T, int G, int NG, bool EXT>
 __global__ void __launch_bounds__(NG * DecodeCfg<T>::NCONS + 32, NG == 1 ? 2 : 1)
 decode_kernel(const KernelArgs a, const int stages) {
   constexpr int ngroups = NG;
@@ -78,6 +80,7 @@ decode_kernel(const KernelArgs a, const int stages) {
 
   const int U = a.B * a.Hkv;
   const int n_phys = a.n_phys, NE = n_phys + 1, nep = L.nep;
+  const bool stream_rope = EXT && sizeof(T) == 2 && a.rope_cos != nullptr;
   const int nt = (n_phys + TILE_ROWS - 1) / TILE_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -102,6 +105,15 @@ decode_kernel(const KernelArgs a, const int stages) {
         uint64_t* gfull = full + (k_unit % ngroups) * Cfg::MAX_STAGES;
         const T* Kg = reinterpret_cast<const T*>(a.K) + (size_t)unit * a.cap * D;
         const T* Vg = reinterpret_cast<const T*>(a.V) + (size_t)unit * a.cap * D;
+        {
+          // this unit's header (slot map, q, new K / V rows) -> L2 now: its consumer group reaches the header a tail and
+          // most of a ring later, and would otherwise wait for DRAM behind the saturated tile stream (~6 K cycles)
+          const uint32_t lb = (uint32_t)(((n_phys * 4 + 15) / 16) * 16);
+          if (((size_t)unit * a.cap * 4) % 16 == 0) bulk_prefetch_l2(a.lidx + (size_t)unit * a.cap, lb);
+          bulk_prefetch_l2(reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D, (uint32_t)(G * Cfg::ROW_BYTES));
+          bulk_prefetch_l2(reinterpret_cast<const T*>(a.k_new) + (size_t)unit * D, (uint32_t)Cfg::ROW_BYTES);
+          bulk_prefetch_l2(reinterpret_cast<const T*>(a.v_new) + (size_t)unit * D, (uint32_t)Cfg::ROW_BYTES);
+        }
         for (int i = 0; i < 2 * nt; ++i) {
           if (use > 0) {
             if (a.timeline) {
@@ -167,6 +179,9 @@ decode_kernel(const KernelArgs a, const int stages) {
   for (int unit = blockIdx.x + gid * gridDim.x; unit < U; unit += ngroups * gridDim.x, k_unit += ngroups) {
     int s = (int)(((long long)k_unit * 2 * nt) % stages);   // ring slot of this unit's first tile
     stamp(k_unit, 0);
+    // ragged batches: this sequence's own count of valid slots; it evicts only past the budget gate (easykv.py:303)
+    const int nb = EXT && a.seq_n_before ? a.seq_n_before[unit / a.Hkv] : a.n_before;
+    const bool gated_off = EXT && a.st.budget_gate > 0 && nb + 1 - a.st.score_offset <= a.st.budget_gate;
     // ---- header: q, new K/V row, slot map (this group is idle until its first tile lands) --------------
     {
       const uint4* qg = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D);
@@ -182,7 +197,7 @@ decode_kernel(const KernelArgs a, const int stages) {
       for (int e = tid; e < n_phys; e += NCONS) lj[e] = lg[e];
       if (tid == 0) {
         ns[0] = a.new_slots ? a.new_slots[unit] : n_phys;
-        lj[n_phys] = a.n_before;
+        lj[n_phys] = nb;
       }
       // the tail reads this unit's S / SQ / C once: pull the lines into L2 now
       if (a.st.policy != EKV_POLICY_NONE && a.st.policy != EKV_POLICY_RANGE) {
@@ -222,6 +237,14 @@ decode_kernel(const KernelArgs a, const int stages) {
           Row8<T> x[RPT];
 #pragma unroll
           for (int k = 0; k < RPT; ++k) x[k].load(tile + (hw * RPT + k) * D, l16);
+          if (stream_rope) {                                   // fused streaming variant: rotate at the cache-relative position
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+              const int e = (i0 + tb) * TILE_ROWS + hw * RPT + k;
+              const int pos = e < n_phys ? max(lj[e], 0) : 0;
+              rope_row8<T>(x[k], l16, a.rope_cos, a.rope_sin, pos);
+            }
+          }
 #pragma unroll
           for (int k = 0; k < RPT; ++k)
 #pragma unroll
@@ -403,32 +426,48 @@ decode_kernel(const KernelArgs a, const int stages) {
     if (hw == 0) {
       const int slot = ns[0];
       float x[8];
-      load_row8<T>(kh, l16, x);
+      if (stream_rope) load_row8<T>(reinterpret_cast<const T*>(a.k_new_raw) + (size_t)unit * D, l16, x);   // the cache keeps un-rotated keys
+      else load_row8<T>(kh, l16, x);
       store_row8<T>(reinterpret_cast<T*>(a.K) + ((size_t)unit * a.cap + slot) * D, l16, x);   // bit-exact round trip
       load_row8<T>(vh, l16, x);
       store_row8<T>(reinterpret_cast<T*>(a.V) + ((size_t)unit * a.cap + slot) * D, l16, x);
     }
-    state_select_apply(a.st, u, a.n_before, n_phys, 1, /*lj_preloaded=*/true, acc, sc, grp);
+    if (gated_off) {                                          // below the budget: accumulate and append only
+      ekv_step stu = a.st;
+      stu.evict = 0;
+      state_select_apply(stu, u, nb, n_phys, 1, /*lj_preloaded=*/true, acc, sc, grp);
+      if (tid == 0) {
+        if (u.victim_lidx) u.victim_lidx[0] = -1;
+        if (u.victim_slots) u.victim_slots[0] = -1;
+      }
+    } else {
+      state_select_apply(a.st, u, nb, n_phys, 1, /*lj_preloaded=*/true, acc, sc, grp);
+    }
     grp.sync();                                   // the header / scratch are rewritten for the next unit
     stamp(k_unit, 7);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int G, int NG>
-static int launch_decode_cfg(const KernelArgs& a, int grid, int stages, int smem_bytes, int dev, cudaStream_t stream) {
+template <typename T, int G, int NG, bool EXT>
+static int launch_decode_cfg_x(const KernelArgs& a, int grid, int stages, int smem_bytes, int dev, cudaStream_t stream) {
   static thread_local int configured[16] = {0};
   cudaError_t err;
   if (!configured[dev]) {
-    err = cudaFuncSetAttribute(decode_kernel<T, G, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    err = cudaFuncSetAttribute(decode_kernel<T, G, NG, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(decode)", err);
     configured[dev] = 1;
   }
-  decode_kernel<T, G, NG><<<grid, NG * DecodeCfg<T>::NCONS + 32, smem_bytes, stream>>>(a, stages);
+  decode_kernel<T, G, NG, EXT><<<grid, NG * DecodeCfg<T>::NCONS + 32, smem_bytes, stream>>>(a, stages);
   err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error("decode_kernel launch", err);
   count_launch();
   return EKV_OK;
+}
+template <typename T, int G, int NG>
+static int launch_decode_cfg(const KernelArgs& a, int grid, int stages, int smem_bytes, int dev, cudaStream_t stream) {
+  if (a.rope_cos || a.seq_n_before) return launch_decode_cfg_x<T, G, NG, true>(a, grid, stages, smem_bytes, dev, stream);
+  return launch_decode_cfg_x<T, G, NG, false>(a, grid, stages, smem_bytes, dev, stream);
 }
 
 int decode_variant();   // ekv_api.cu (env EKV_DECODE_VARIANT): 0 = automatic, 1 = one group per CTA (2 CTAs/SM), 2 = ping-pong groups
@@ -510,13 +549,14 @@ static int device_sm_count() {
 
 int launch_decode(const KernelArgs& a, cudaStream_t stream) {
   if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean) return EKV_ERR_UNSUPPORTED;
+  if (a.rope_cos && a.dtype == EKV_F32) return EKV_ERR_UNSUPPORTED;       // fused streaming: 16-bit dtypes
   if (a.st.evict <= 1) {
     const int G = a.H / a.Hkv;
     // grouped-query layouts in a 16-bit dtype: the tcgen05 kernel (decode_variant 5 forces it for any g, 6 forbids it)
     const int dv = decode_variant();
     // automatic: long caches (>= 2048 slots) with enough units to fill the chip; short caches stay with the cluster kernel,
     // whose whole unit fits one light CTA
-    if (dv == 5 || (dv == 0 && decode_cluster_size() == 0 && G >= 2 && a.dtype != EKV_F32 && a.B * a.Hkv >= 32 && a.n_phys >= 2048)) {
+    if (!a.rope_cos && (dv == 5 || (dv == 0 && decode_cluster_size() == 0 && G >= 2 && a.dtype != EKV_F32 && a.B * a.Hkv >= 32 && a.n_phys >= 2048))) {
       const int rc = launch_decode_umma(a, stream);
       if (rc != EKV_ERR_UNSUPPORTED || dv == 5) return rc;
     }

@@ -104,6 +104,11 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   unsigned char* ring = smem + L.off_ring;
 
   const int unit = blockIdx.x / C;
+  // ragged batches: this sequence's own count of valid slots; it evicts only past the budget gate (easykv.py:303)
+  const int nb = a.seq_n_before ? a.seq_n_before[unit / a.Hkv] : a.n_before;
+  ekv_step stu = a.st;
+  if (stu.budget_gate > 0 && nb + 1 - stu.score_offset <= stu.budget_gate) stu.evict = 0;
+  const bool stream_rope = sizeof(T) == 2 && !TC && a.rope_cos != nullptr;     // fused streaming variant (FMA path)
   const int n_phys = a.n_phys;
   const int lo = min(rank * slice, n_phys), hi = min(lo + slice, n_phys);
   const int nloc = hi - lo;                                   // physical slots of this CTA
@@ -197,12 +202,12 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   uint32_t* xhist = reinterpret_cast<uint32_t*>(smem + L.off_xhist);
   BucketScratch bs;
   bs.carve(smem + L.off_bkt, 8);
-  const int lsh = bk::lidx_shift(a.n_before + 1);
-  const bool roco_sel = a.st.evict > 0 && a.st.policy == EKV_POLICY_ROCO;
+  const int lsh = bk::lidx_shift(nb + 1);
+  const bool roco_sel = stu.evict > 0 && stu.policy == EKV_POLICY_ROCO;
 
   auto finish_logit = [&](float dot, bool valid) -> T {
     float x = Tr<T>::round_f(dot);                                           // llama_patch.py:201
-    x = a.st.arith ? __fmul_rn(x, a.scale_mul) : __fdiv_rn(x, a.scale_div);  // :202
+    x = stu.arith ? __fmul_rn(x, a.scale_mul) : __fdiv_rn(x, a.scale_div);  // :202
     return valid ? Tr<T>::from_f(x) : neg_inf<T>();
   };
 
@@ -225,9 +230,9 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     for (int e = tid; e < nloc; e += NCONS) lj[e] = lg[e];
     if (tid == 0) {
       ns[0] = a.new_slots ? a.new_slots[unit] : n_phys;
-      if (rank == 0) lj[nloc] = a.n_before;
+      if (rank == 0) lj[nloc] = nb;
     }
-    if (a.st.policy != EKV_POLICY_NONE && a.st.policy != EKV_POLICY_RANGE) {
+    if (stu.policy != EKV_POLICY_NONE && stu.policy != EKV_POLICY_RANGE) {
       const int lines = (nloc * 4 + 127) / 128;
       for (int i = tid; i < 3 * lines; i += NCONS) {
         const float* base = (i < lines ? a.S : (i < 2 * lines ? a.SQ : a.C)) + (size_t)unit * a.cap + lo;
@@ -345,6 +350,14 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
         Row8<T> x[RPT];
 #pragma unroll
         for (int k = 0; k < RPT; ++k) x[k].load(tile + (hw * RPT + k) * D, l16);
+        if (stream_rope) {                                     // fused streaming variant: rotate at the cache-relative position
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) {
+            const int e = (i0 + tb) * TILE_ROWS + hw * RPT + k;
+            const int pos = e < nloc ? max(lj[e], 0) : 0;
+            rope_row8<T>(x[k], l16, a.rope_cos, a.rope_sin, pos);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < RPT; ++k)
 #pragma unroll
@@ -444,14 +457,14 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     for (int g = 0; g < G; ++g) {
       float v = xsum[g];
       for (int p = 1; p < C; ++p) v += xsum[p * G + g];                            // rank order on every CTA
-      inv[g] = a.st.arith ? v : __fdiv_rn(1.0f, v);
+      inv[g] = stu.arith ? v : __fdiv_rn(1.0f, v);
       rcp[g] = __frcp_rn(v);
     }
     for (int e = tid; e < NEl; e += NCONS)
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const float ex = expf(Tr<T>::to_f(plog[g * slp + e]) - mx[g]);
-        plog[g * slp + e] = Tr<T>::from_f(a.st.arith ? div_rn_by(ex, inv[g], rcp[g]) : __fmul_rn(ex, inv[g]));   // llama_patch.py:218-219
+        plog[g * slp + e] = Tr<T>::from_f(stu.arith ? div_rn_by(ex, inv[g], rcp[g]) : __fmul_rn(ex, inv[g]));   // llama_patch.py:218-219
       }
   }
   grp.sync();
@@ -571,9 +584,9 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
 
   stamp(4);
   // ---- tail, pass 1: this slice's policy state and selection keys ------------------------------------------------
-  const ekv_step& st = a.st;
+  const ekv_step& st = stu;
   const int P = st.score_offset;
-  const int n_after = a.n_before + 1, n_s = n_after - P;
+  const int n_after = nb + 1, n_s = n_after - P;
   const bool evicting = st.evict > 0 && st.policy != EKV_POLICY_NONE;
   float* Sg = a.S + (size_t)unit * a.cap;
   float* SQg = a.SQ + (size_t)unit * a.cap;
@@ -592,7 +605,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
         rl[k] = -1; sv[k] = 0.f; sq[k] = 0.f; cc[k] = 1.f; ds[k] = 0.f; dsq[k] = 0.f;
         if (e < NEl) {
           if (e >= nloc) {
-            rl[k] = a.n_before;
+            rl[k] = nb;
             cc[k] = st.c_new0;
           } else {
             rl[k] = lj[e];
@@ -696,7 +709,8 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
     if (rank == 0 && hw == 0) {
       const int slot = ns[0];
       float x[8];
-      load_row8<T>(kh, l16, x);
+      if (stream_rope) load_row8<T>(reinterpret_cast<const T*>(a.k_new_raw) + (size_t)unit * D, l16, x);     // the cache keeps un-rotated keys
+      else load_row8<T>(kh, l16, x);
       store_row8<T>(reinterpret_cast<T*>(a.K) + ((size_t)unit * a.cap + slot) * D, l16, x);
       load_row8<T>(vh, l16, x);
       store_row8<T>(reinterpret_cast<T*>(a.V) + ((size_t)unit * a.cap + slot) * D, l16, x);
@@ -912,7 +926,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
       lidx_g[phys] = l;
     }
   }
-  if (evicting && !found && rank == 0 && tid == 0) {          // degenerate: no candidate (rejected by validation normally)
+  if (((evicting && !found) || (a.st.evict > 0 && stu.evict == 0)) && rank == 0 && tid == 0) {   // no candidate (degenerate), or below the budget gate
     if (a.victim_lidx) a.victim_lidx[unit] = -1;
     if (a.victim_slots) a.victim_slots[unit] = -1;
   }
@@ -1025,7 +1039,7 @@ template <typename T, int G> static int launch_cluster_plan(const KernelArgs& a,
   // for g = 4 the FMA variant keeps up with HBM and is kept (decode_variant 4 forces the tensor cores, 3 forbids them)
   if constexpr (sizeof(T) == 2 && G >= 4) {
     const int v = decode_variant() >= 5 ? 0 : decode_variant();
-    if (v == 4 || (v != 3 && G >= 8)) return launch_cluster_plan_v<T, G, true>(a, only_if_better, stream);
+    if (!a.rope_cos && (v == 4 || (v != 3 && G >= 8))) return launch_cluster_plan_v<T, G, true>(a, only_if_better, stream);   // (fused streaming: FMA path)
   }
   return launch_cluster_plan_v<T, G, false>(a, only_if_better, stream);
 }
@@ -1043,6 +1057,7 @@ template <typename T> static int launch_cluster_t(const KernelArgs& a, bool only
 // `only_if_better`: decline (EKV_ERR_UNSUPPORTED) when the plan degenerates to one CTA per unit.
 int launch_decode_cluster(const KernelArgs& a, bool only_if_better, cudaStream_t stream) {
   if (a.q_len != 1 || a.d != 128 || a.st.tova_head_mean || a.st.evict > 1) return EKV_ERR_UNSUPPORTED;
+  if (a.rope_cos && a.dtype == EKV_F32) return EKV_ERR_UNSUPPORTED;
   switch (a.dtype) {
     case EKV_F16: return launch_cluster_t<__half>(a, only_if_better, stream);
     case EKV_BF16: return launch_cluster_t<__nv_bfloat16>(a, only_if_better, stream);

@@ -136,7 +136,6 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   BucketScratch bs;
   bs.carve(smem + OFF_BKT, MAX_CLUSTER);
   float* fs = reinterpret_cast<float*>(smem + OFF_FS);
-  const int lsh = bk::lidx_shift(a.n_before + 1);               // logical indices -> histogram buckets
   int32_t* lj = reinterpret_cast<int32_t*>(smem + SL.off_lj);
   unsigned long long* kk = reinterpret_cast<unsigned long long*>(smem + SL.off_kk);
 
@@ -144,6 +143,11 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   const int C = pl.C;
   const int rank = blockIdx.x % C;
   const int unit = blockIdx.x / C;
+  // ragged batches: this sequence's own count of valid slots; it evicts only past the budget gate (easykv.py:303)
+  const int nb = a.seq_n_before ? a.seq_n_before[unit / a.Hkv] : a.n_before;
+  ekv_step stu = a.st;
+  if (stu.budget_gate > 0 && nb + 1 - stu.score_offset <= stu.budget_gate) stu.evict = 0;
+  const int lsh = bk::lidx_shift(nb + 1);                       // logical indices -> histogram buckets
   const int n_phys = a.n_phys, nct = pl.nct;
   const int t0 = (int)((long long)rank * nct / C), t1 = (int)((long long)(rank + 1) * nct / C);
   const int T_ = t1 - t0;
@@ -267,12 +271,12 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     // ===== softmax warps: TMEM lane = key =======================================================================================
     const int kl = warp * 32 + lane;                             // key inside a tile; output dim in the epilogue
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const ekv_step& st = a.st;
+    const ekv_step& st = stu;
     unsigned long long* tl = a.timeline ? a.timeline + (size_t)blockIdx.x * 16 : nullptr;     // profiling hook
     auto stamp = [&](int i) { if (tl && tid == 0) tl[i] = global_ns(); };
     stamp(0);
     const int P = st.score_offset;
-    const int n_after = a.n_before + 1, n_s = n_after - P;
+    const int n_after = nb + 1, n_s = n_after - P;
     const bool evicting = st.evict > 0 && st.policy != EKV_POLICY_NONE;
     float* Sg = a.S + (size_t)unit * a.cap;
     float* SQg = a.SQ + (size_t)unit * a.cap;
@@ -294,7 +298,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     // slots of the last tile beyond n_phys (or beyond the copied range) are not entries
     for (int e = tid; e < T_ * TKEYS; e += NSOFT)
       if (first + e >= n_phys) lj[e] = -1;
-    if (rank == 0 && tid == 0) lj[e_new] = a.n_before;
+    if (rank == 0 && tid == 0) lj[e_new] = nb;
     named_bar_sync(1, NSOFT);
 
     // ---- K phase -----------------------------------------------------------------------------------------------------------
@@ -568,7 +572,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       uint32_t ka = 0, kb = 0;
       uint8_t f = 0;
       bool dirty = false;
-      const int rl = a.n_before;
+      const int rl = nb;
       if (rl >= P) {
         float ds = 0.f, dsq = 0.f;
         if (st.accumulate) {
@@ -625,9 +629,9 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     // ekv_select.cuh) and the select's histograms, from the folded probabilities the softmax warps hand over ===================
     const int hset = (tid - NSOFT - 64) / NHS;                   // set 0: even tiles, set 1: odd tiles (= the hand-over buffer)
     const int kl = (tid - NSOFT - 64) % NHS;                     // key inside a tile
-    const ekv_step& st = a.st;
+    const ekv_step& st = stu;
     const int P = st.score_offset;
-    const int n_s = a.n_before + 1 - P;
+    const int n_s = nb + 1 - P;
     const bool evicting = st.evict > 0 && st.policy != EKV_POLICY_NONE;
     float* Sg = a.S + (size_t)unit * a.cap;
     float* SQg = a.SQ + (size_t)unit * a.cap;
@@ -690,7 +694,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   if (warp < NSOFT / 32 || (warp >= NSOFT / 32 + 2 && warp < NSOFT / 32 + 2 + NHS / 32)) {
     const int ttid = warp < NSOFT / 32 ? tid : tid - 64;         // 0 .. NTAIL-1
     const int tw = ttid >> 5;                                    // tail warp 0 .. NTW-1
-    const ekv_step& st = a.st;
+    const ekv_step& st = stu;
     const int P = st.score_offset;
     const bool evicting = st.evict > 0 && st.policy != EKV_POLICY_NONE;
     int32_t* lidx_g = a.lidx + (size_t)unit * a.cap;
@@ -872,7 +876,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
         lidx_g[phys] = l;
       }
     }
-    if (evicting && !found && rank == 0 && ttid == 0) {
+    if (((evicting && !found) || (a.st.evict > 0 && stu.evict == 0)) && rank == 0 && ttid == 0) {     // no candidate, or below the budget gate
       if (a.victim_lidx) a.victim_lidx[unit] = -1;
       if (a.victim_slots) a.victim_slots[unit] = -1;
     }
@@ -981,7 +985,7 @@ template <typename T> static int launch_du_t(const KernelArgs& a, cudaStream_t s
 // q_len == 1, 16-bit dtypes, head_dim 128, at most one victim per unit; EKV_ERR_UNSUPPORTED otherwise (the caller falls
 // back to the FMA / mma.sync decode kernels).
 int launch_decode_umma(const KernelArgs& a, cudaStream_t stream) {
-  if (a.q_len != 1 || a.d != du::D || a.st.tova_head_mean || a.st.evict > 1 || (a.cap & 3) || a.n_phys < 1) return EKV_ERR_UNSUPPORTED;
+  if (a.q_len != 1 || a.d != du::D || a.st.tova_head_mean || a.st.evict > 1 || (a.cap & 3) || a.n_phys < 1 || a.rope_cos) return EKV_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a.K) | reinterpret_cast<uintptr_t>(a.V)) & 15) return EKV_ERR_UNSUPPORTED;
   switch (a.dtype) {
     case EKV_F16: return launch_du_t<__half>(a, stream);

@@ -12,6 +12,8 @@ struct KernelArgs {
   const void* q; const void* k_new; const void* v_new; void* out;
   void* K; void* V; float* S; float* SQ; float* C; int32_t* lidx;
   const int32_t* new_slots; int32_t* victim_slots; int32_t* victim_lidx; void* scratch;
+  const void* rope_cos; const void* rope_sin; const void* k_new_raw;   // fused streaming variant (all null: K is post-RoPE)
+  const int32_t* seq_n_before;                                          // ragged batches (null: n_before for all)
   // ekv_shape
   int32_t dtype, B, H, Hkv, d, q_len, cap, n_before, n_phys;
   // derived

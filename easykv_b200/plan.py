@@ -49,6 +49,7 @@ class StepParams:
     tova_head_mean: bool = False
     range_start: int = 0
     raw_colsum: bool = False
+    budget_gate: int = 0      # ragged batches: a sequence evicts only when its scored slots after the append exceed this
 
     def to_c(self, apply=True, arith=0) -> "_lib.Step":
         pol = _POLICY_ENUM[self.policy]
@@ -60,12 +61,12 @@ class StepParams:
                          win_lo=int(self.win_lo), win_recent=int(self.win_recent),
                          range_start=int(self.range_start), arith=int(arith),
                          tova_head_mean=int(self.tova_head_mean and self.policy == "tova"),
-                         raw_colsum=int(self.raw_colsum))
+                         raw_colsum=int(self.raw_colsum), budget_gate=int(self.budget_gate))
 
     @classmethod
     def from_fields(cls, obj) -> "StepParams":
         """Build from any object with the same attribute names (e.g. the test oracle's Step)."""
-        return cls(**{k: getattr(obj, k) for k in asdict(cls()).keys()})
+        return cls(**{k: getattr(obj, k) for k in asdict(cls()).keys() if hasattr(obj, k)})
 
 
 @dataclass

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define EKV_ABI_VERSION 7
+#define EKV_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define EKV_API __attribute__((visibility("default")))
@@ -94,6 +94,10 @@ typedef struct ekv_step {
                             as causal chunks whose column sums must be added to S / SQ WITHOUT the
                             per-forward model-dtype rounding of :450-451; the caller rounds S / SQ once
                             when the prefill is complete (torch.sum over the whole map rounds once) */
+  int32_t budget_gate;   /* ragged batches (io->seq_n_before): a sequence evicts (and counts, counter_add) only when
+                            its scored slots after the append exceed this — the reference's
+                            `if cur_kv_size - len(prefix) > budget` (:303, :459, :709) evaluated per sequence.
+                            0: every sequence evicts `evict` slots                                   */
 } ekv_step;
 
 /* One layer's tensors for one forward.  Replaces the body of llama_forward / mistral_forward
@@ -116,6 +120,20 @@ typedef struct ekv_layer_io {
                                 ordered like victim_lidx                                          */
   int32_t*    victim_lidx;   /* [B, Hkv, evict] out: the reference's eviction ids, ascending       */
   void*       scratch;       /* >= ekv_scratch_bytes() bytes of device memory, or NULL (see below)  */
+  /* --- streaming variant fused into the step (llama_forward_stream, llama_patch.py:310-327): K holds the UN-rotated
+   * keys; each cached row is rotated at its cache-relative position lidx[slot] while it is read (same roundings as
+   * apply_rotary_pos_emb, :47-72), so no rotated copy of the cache is ever written.  All three NULL: K is post-RoPE.
+   * Supported by the decode kernels' FMA paths (q_len == 1, 16-bit dtypes, d == 128, group size <= 4); otherwise the
+   * call returns EKV_ERR_UNSUPPORTED and the caller runs ekv_rope_cache into a second buffer first. */
+  const void* rope_cos;      /* [rows, d] model-dtype tables, rows > every logical index                */
+  const void* rope_sin;
+  const void* k_new_raw;     /* [B, Hkv, q_len, d] un-rotated keys of the appended tokens: THESE are written to K;
+                                k_new (rotated at the tokens' own positions) only enters this forward's logits */
+  /* --- ragged batches: sequences of one call may hold different numbers of valid slots ------------------------- */
+  const int32_t* seq_n_before;  /* [B] valid slots of each sequence before the append, each <= shape.n_before;
+                                   shape.n_phys bounds every sequence's physical extent (slots beyond a sequence's own
+                                   are free: lidx == -1).  NULL: shape.n_before for all.  Decode steps (q_len == 1)
+                                   and the general kernel; EKV_ERR_UNSUPPORTED elsewhere.               */
 } ekv_layer_io;
 
 typedef struct ekv_shape {
@@ -123,7 +141,7 @@ typedef struct ekv_shape {
   int32_t B, H, Hkv, d;
   int32_t q_len;     /* 1 = decode step, >1 = strided prefill chunk (causal inside the chunk)     */
   int32_t cap;       /* physical slots per (sequence, kv head)                                    */
-  int32_t n_before;  /* valid slots before this forward's append (same for all sequences/heads)   */
+  int32_t n_before;  /* valid slots before this forward's append (the largest, with io->seq_n_before) */
   int32_t n_phys;    /* physical slots [0, n_phys) hold every valid slot and are streamed         */
 } ekv_shape;
 

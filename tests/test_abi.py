@@ -23,9 +23,9 @@ def test_every_declared_symbol_is_exported(ekv_lib):
 def test_abi_version_and_struct_layout(ekv_lib):
     from easykv_b200 import _lib
     assert ekv_lib.ekv_abi_version() == _lib.ABI_VERSION
-    assert ctypes.sizeof(_lib.Step) == 17 * 4
+    assert ctypes.sizeof(_lib.Step) == 18 * 4
     assert ctypes.sizeof(_lib.Shape) == 9 * 4
-    assert ctypes.sizeof(_lib.LayerIO) == 14 * 8
+    assert ctypes.sizeof(_lib.LayerIO) == 18 * 8
 
 
 def test_ctypes_structs_mirror_the_header_field_for_field():

@@ -104,7 +104,7 @@ def run_case(name, B, H, Hkv, n, q_len, policy, L=4, steps=10, dtype=torch.float
     torch.cuda.empty_cache()
 
 
-def run_stream_case(name, B, H, Hkv, n, L=4, steps=10, dtype=torch.float16):
+def run_stream_case(name, B, H, Hkv, n, L=4, steps=10, dtype=torch.float16, fused="auto"):
     """Decode step of the streaming variant (generation_config['streaming']): ekv_rope_cache (re-rotate the whole
     cache at cache-relative positions) + ekv_rope_qk + ekv_attend_evict + the raw-row scatter, per layer.
     Algorithmic bytes = the non-streaming step's + one extra read and one write of K."""
@@ -112,6 +112,7 @@ def run_stream_case(name, B, H, Hkv, n, L=4, steps=10, dtype=torch.float16):
     torch.manual_seed(0)
     cache = BudgetedKVCache(L, B, H, Hkv, d, n + 1, dtype=dtype, arith=1)
     cache.enable_streaming()
+    cache.fused_streaming = fused
     for l in range(L):
         cache.load_prefill(l, torch.randn(B, Hkv, n, d, device=dev, dtype=dtype), torch.randn(B, Hkv, n, d, device=dev, dtype=dtype),
                            n, [float(n - i) for i in range(n)])
@@ -161,7 +162,11 @@ def main():
         run_case("C3 generation: mistral n8208 b16, no policy", 16, 32, 8, 8208, 1, "full")
         run_case("C5 generation: 70B n8256 b8, no policy", 8, 64, 8, 8256, 1, "full")
         run_case("C2 literal: decoding, 4096 prompt + 200 generated, no eviction", 16, 32, 32, 4296, 1, "roco", literal_prompt=4096)
-        run_stream_case("7B b64 streaming variant (4 launches per layer-step)", 64, 32, 32, 1088)
+        run_stream_case("7B b64 streaming variant (two passes: ekv_rope_cache + the step; 4 launches per layer-step)", 64, 32, 32, 1088)
+        run_stream_case("7B b1 streaming variant, two passes", 1, 32, 32, 1088, L=32, fused=False)
+        run_stream_case("7B b1 streaming variant, rotation fused into the decode kernel", 1, 32, 32, 1088, L=32, fused=True)
+        run_stream_case("mistral n8208 b1 streaming variant, two passes", 1, 32, 8, 8208, L=32, fused=False)
+        run_stream_case("mistral n8208 b1 streaming variant, rotation fused into the decode kernel", 1, 32, 8, 8208, L=32, fused=True)
         run_case("7B b32 general-kernel", 32, 32, 32, 1088, 1, "roco", kernel=1, steps=3)
     if what in ("cluster",):
         for B in (1, 2, 4, 8):
