@@ -43,6 +43,27 @@ __device__ __forceinline__ Tuple128 warp_argmin(const Tuple128& t) {
   return r;
 }
 
+// explicit shared-memory accesses: the scratch pointers are carved at run-time offsets, for which the compiler falls
+// back to GENERIC loads (LD.E, twice the latency of LDS) — measured 5 us for a 17-iteration classify pass
+__device__ __forceinline__ void lds_2u64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 namespace bk {
 constexpr int NBIN = 2048, NWORD = NBIN / 2, NAN_BIN = NBIN - 1, TOP_BIN = NBIN - 2, ZERO_BIN = 0;
 constexpr uint32_t KBASE = 0xB0000000u;  // order_key(2^-31)
@@ -54,11 +75,16 @@ enum { OK = 0, NONE = 1, FALLBACK = 2 };
 
 __device__ __forceinline__ int std_bin(uint32_t ka) {
   if (ka == 0xffffffffu) return NAN_BIN;
-  if (ka == 0x80000000u) return ZERO_BIN;
-  if (ka < KBASE) return 1;                                    // (0, 2^-31) — and negative values, which a std never is
+  if (ka <= 0x80000000u) return ZERO_BIN;                      // zero (a std is never negative: sqrt, or NaN)
+  if (ka < KBASE) return 1;                                    // (0, 2^-31)
   const uint32_t b = 2u + ((ka - KBASE) >> BIN_SHIFT);
   return b > (uint32_t)TOP_BIN ? TOP_BIN : (int)b;
 }
+// first / last key of a bucket (std_bin is monotone: a bucket is a key interval)
+__device__ __forceinline__ uint32_t bin_lo(int b) {
+  return b <= 0 ? 0u : b == 1 ? 0x80000001u : b >= NAN_BIN ? 0xffffffffu : KBASE + ((uint32_t)(b - 2) << BIN_SHIFT);
+}
+__device__ __forceinline__ uint32_t bin_last(int b) { return b >= NAN_BIN ? 0xffffffffu : bin_lo(b + 1) - 1u; }
 __device__ __forceinline__ int sub_bin(uint32_t ka) { return (int)(((ka - KBASE) >> SUB_SHIFT) & (NBIN - 1)); }
 // logical indices (< n_after) -> NBIN buckets
 __host__ __device__ inline int lidx_shift(int n_after) {
@@ -224,45 +250,89 @@ struct Feasibility {
   BucketSel b;
   int lsh;
   uint32_t T1, jT;
-  __device__ __forceinline__ void judge(uint32_t ka, uint32_t l, bool& feas, bool& bound) const {
-    bound = false;
-    if (mode == 0) feas = true;
-    else if (mode == 2) feas = ka < T1 || (ka == T1 && l <= jT);
-    else {
-      const int bin = bk::std_bin(ka);
-      if (bin != b.bsel) feas = bin < b.bsel;
-      else if (b.kind == 0) { feas = false; bound = true; }
-      else { const int cb = b.kind == 1 ? (int)(l >> lsh) : bk::sub_bin(ka); feas = cb < b.csel; bound = cb == b.csel; }
+};
+// ... as key intervals, so that the pass judges an entry with a handful of compares and no divergence: feasible iff
+// ka < a_lo, or ka <= a_last and l < l_lo; listed (boundary) iff a_lo <= ka <= a_last and l_lo <= l < l_hi.
+struct FeasCut {
+  bool all;
+  uint32_t a_lo, a_last;
+  unsigned long long l_lo, l_hi;
+  __device__ __forceinline__ explicit FeasCut(const Feasibility& f) {
+    all = f.mode == 0;
+    a_lo = 0u; a_last = 0u; l_lo = 0ull; l_hi = 0ull;                         // nothing feasible, nothing listed
+    if (f.mode == 2) { a_lo = f.T1; a_last = f.T1; l_lo = (unsigned long long)f.jT + 1ull; l_hi = l_lo; }
+    else if (f.mode == 1 && f.b.bsel >= 0) {
+      a_lo = bk::bin_lo(f.b.bsel); a_last = bk::bin_last(f.b.bsel); l_hi = 1ull << 32;
+      if (f.b.kind == 1) { l_lo = (unsigned long long)f.b.csel << f.lsh; l_hi = (unsigned long long)(f.b.csel + 1) << f.lsh; }
+      else if (f.b.kind == 2) { a_lo += (uint32_t)f.b.csel << bk::SUB_SHIFT; a_last = a_lo + (1u << bk::SUB_SHIFT) - 1u; }
     }
+  }
+  __device__ __forceinline__ void judge(uint32_t ka, uint32_t l, bool& feas, bool& bound) const {
+    const bool in = ka >= a_lo && ka <= a_last;
+    feas = all || ka < a_lo || (in && l < l_lo);
+    bound = !all && in && l >= l_lo && l < l_hi;
   }
 };
 
 // One pass over this CTA's entries: argmin over the feasible ones, boundary entries listed.  get(e, ka, kb, l) -> is a
-// candidate; push(slot, hi, lo) stores 16 bytes at `slot` (an address in this CTA's shared memory) in EVERY CTA of the
-// cluster.  Every warp's lane 0 pushes the warp's best to xg[(rank * NW + warp)] (nthr == 256).
-template <class Get, class Push>
+// candidate; push_peers(slot, hi, lo) stores 16 bytes at `slot` (an address in this CTA's shared memory) in every OTHER
+// CTA of the cluster (a no-op for a single CTA).  Boundary entries are first listed in this CTA's own copy and sent to the
+// peers afterwards, one entry per thread: remote stores issued from inside the (divergent) entry loop serialise — measured
+// 5 us for 48 entries.  Every warp's lane 0 publishes the warp's best at xg[(rank * NW + warp)] (nthr == 256).
+template <class Get, class Push, class Sync>
 __device__ __forceinline__ void bucket_pass(const BucketScratch& s, const Feasibility& f, int NEl, int rank, int tid, int nthr,
-                                            Get get, Push push) {
+                                            Get get, Push push_peers, Sync sync, unsigned long long* dbg = nullptr) {
   Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
-  if (tid >= bk::NTHR) return;                                   // whole warps; a wider group idles here
   if (nthr > bk::NTHR) nthr = bk::NTHR;
-  for (int e = tid; e < NEl; e += nthr) {
-    uint32_t ka, kb, l;
-    if (!get(e, ka, kb, l)) continue;
-    bool feas, bound;
-    f.judge(ka, l, feas, bound);
-    if (!feas && !bound) continue;
-    Tuple128 t;
-    t.hi = ((unsigned long long)kb << 32) | ka;
-    t.lo = ((unsigned long long)l << 32) | ((uint32_t)rank << 24) | (uint32_t)e;
-    if (feas) { if (tuple_less(t, best)) best = t; }
-    else {
-      const int pos = f.b.my_off + atomicAdd(&s.misc[12], 1);
-      if (pos < bk::CAP) push(&s.blist[2 * pos], t.hi, t.lo);
+  const bool active = tid < nthr;                                // a wider group idles (but joins the barrier)
+  const FeasCut cut(f);
+  constexpr int U = 4;                                            // entries in flight per thread (the loads first)
+  const uint32_t cursor = smem_u32(&s.misc[12]), bl = smem_u32(s.blist);
+  for (int e0 = tid; active && e0 < NEl; e0 += U * nthr) {
+    uint32_t ka[U], kb[U], l[U];
+    bool c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * nthr;
+      ka[u] = 0; kb[u] = 0; l[u] = 0;
+      c[u] = e < NEl && get(e, ka[u], kb[u], l[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!c[u]) continue;
+      bool feas, bound;
+      cut.judge(ka[u], l[u], feas, bound);
+      if (!feas && !bound) continue;
+      Tuple128 t;
+      t.hi = ((unsigned long long)kb[u] << 32) | ka[u];
+      t.lo = ((unsigned long long)l[u] << 32) | ((uint32_t)rank << 24) | (uint32_t)(e0 + u * nthr);
+      if (feas) { if (tuple_less(t, best)) best = t; }
+      else {
+        uint32_t slot;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(cursor) : "memory");
+        const int pos = f.b.my_off + (int)slot;
+        if (pos < bk::CAP) asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(bl + 16u * (uint32_t)pos), "l"(t.hi), "l"(t.lo) : "memory");
+      }
     }
   }
-  best = warp_argmin(best);
-  if ((tid & 31) == 0) push(&s.xg[2 * (rank * bk::NW + (tid >> 5))], best.hi, best.lo);
+  if (dbg && tid == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); dbg[0] = tns; }   // profiling hook: loop done
+  if (active) {
+    best = warp_argmin(best);
+    if ((tid & 31) == 0) {
+      unsigned long long* slot = &s.xg[2 * (rank * bk::NW + (tid >> 5))];
+      slot[0] = best.hi; slot[1] = best.lo;
+      push_peers(slot, best.hi, best.lo);
+    }
+  }
+  if (f.mode == 1) {                                             // (uniform) this CTA's listed entries -> the peers, one per thread
+    sync();
+    const int mine = s.misc[12];
+    for (int i = tid; active && i < mine && f.b.my_off + i < bk::CAP; i += nthr) {
+      unsigned long long hi, lo;
+      lds_2u64(bl + 16u * (uint32_t)(f.b.my_off + i), hi, lo);
+      push_peers(&s.blist[2 * (f.b.my_off + i)], hi, lo);
+    }
+  }
 }
 
 // After the exchange: rank the boundary entries, merge with the gathered argmins.  Every CTA derives the same winner.
@@ -271,18 +341,23 @@ __device__ __forceinline__ bool bucket_final(const BucketScratch& s, const Feasi
   Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
   const int m = f.mode == 1 ? (f.b.mtot < bk::CAP ? f.b.mtot : bk::CAP) : 0;
   const int nt = nthr > bk::NTHR ? bk::NTHR : nthr;
+  const uint32_t bl = smem_u32(s.blist), xg = smem_u32(s.xg);
   for (int i = tid; i < m && tid < nt; i += nt) {
-    Tuple128 t; t.hi = s.blist[2 * i]; t.lo = s.blist[2 * i + 1];
-    const uint32_t ka = (uint32_t)t.hi, l = (uint32_t)(t.lo >> 32);
+    Tuple128 t;
+    lds_2u64(bl + 16 * i, t.hi, t.lo);
+    const unsigned long long key = (t.hi << 32) | (t.lo >> 32);          // (std key, logical index)
     int rk = 0;
+#pragma unroll 4
     for (int j = 0; j < m; ++j) {
-      const uint32_t kj = (uint32_t)s.blist[2 * j], lj2 = (uint32_t)(s.blist[2 * j + 1] >> 32);
-      rk += (kj < ka || (kj == ka && lj2 < l)) ? 1 : 0;
+      unsigned long long hj, lj2;
+      lds_2u64(bl + 16 * j, hj, lj2);
+      rk += ((hj << 32) | (lj2 >> 32)) < key ? 1 : 0;
     }
     if (rk < f.b.rb && tuple_less(t, best)) best = t;
   }
   for (int i = tid; i < C * bk::NW && tid < nt; i += nt) {
-    Tuple128 t; t.hi = s.xg[2 * i]; t.lo = s.xg[2 * i + 1];
+    Tuple128 t;
+    lds_2u64(xg + 16 * i, t.hi, t.lo);
     if (t.lo != ~0ull && tuple_less(t, best)) best = t;
   }
   best = warp_argmin(best);

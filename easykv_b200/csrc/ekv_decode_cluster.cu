@@ -761,13 +761,14 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
             asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(map_to_rank(ptr, peer)) : "memory");
             return v;
           };
+          const uint32_t ka_a = smem_u32(keyA), kb_a = smem_u32(keyB), lj_a = smem_u32(lj), fl_a = smem_u32(flag);   // (explicit ld.shared)
           auto get = [&](int e, uint32_t& ka, uint32_t& kb, uint32_t& l) -> bool {
-            if (!(flag[e] & F_CAND)) return false;
-            ka = keyA[e]; kb = keyB[e]; l = (uint32_t)lj[e];
-            return true;
+            ka = lds_u32(ka_a + 4u * (uint32_t)e); kb = lds_u32(kb_a + 4u * (uint32_t)e); l = lds_u32(lj_a + 4u * (uint32_t)e);
+            return (lds_u8(fl_a + (uint32_t)e) & F_CAND) != 0;
           };
-          auto push = [&](unsigned long long* slot, unsigned long long hi, unsigned long long lo2) {
+          auto push = [&](unsigned long long* slot, unsigned long long hi, unsigned long long lo2) {     // to every OTHER CTA
             for (int p = 0; p < C; ++p) {
+              if (p == rank) continue;
               const uint32_t dst = map_to_rank(slot, p);
               st_cluster_u64(dst, hi);
               st_cluster_u64(dst + 8, lo2);
@@ -777,7 +778,7 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
           fz.mode = 1; fz.lsh = lsh; fz.T1 = 0u; fz.jT = 0xffffffffu;
           fz.b = bucket_scan<8>(bs, st.k_feasible, C, rank, tid, NCONS, NEl, sync, ld, get, [&] { cluster_sync_all(); });
           if (fz.b.status != bk::FALLBACK) {
-            bucket_pass(bs, fz, NEl, rank, tid, NCONS, get, push);
+            bucket_pass(bs, fz, NEl, rank, tid, NCONS, get, push, sync);
             cluster_sync_all();                                                             // (4) argmins + boundary entries
             Tuple128 wn;
             if (bucket_final(bs, fz, C, tid, NCONS, sync, wn)) {

@@ -71,8 +71,7 @@ constexpr int OFF_CAND = (OFF_HIST + 1024 + 15) / 16 * 16;               // cand
 constexpr int CAND_BYTES = 2 * MAX_CLUSTER * 256 * 4;                     // reused for the radix histograms [2][MAX_CLUSTER][256] u32
 static_assert(2 * MAX_CLUSTER * NTW * NCAND * 16 <= CAND_BYTES, "candidate exchange fits");
 constexpr int OFF_FS = OFF_CAND + CAND_BYTES;                             // [2][128] folded probabilities: softmax warps -> helper warps
-constexpr int OFF_BKT = OFF_FS + 2 * TKEYS * 4;                            // bucket select (ekv_bucket.cuh): histograms, boundary list, gather
-constexpr int OFF_RING = (OFF_BKT + BucketScratch::bytes(MAX_CLUSTER) + 1023) / 1024 * 1024;
+constexpr int OFF_RING = (OFF_FS + 2 * TKEYS * 4 + 1023) / 1024 * 1024;
 // barriers
 constexpr int B_FULL = 0, B_EMPTY = MAX_STAGE, B_SFULL = 2 * MAX_STAGE, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2,
               B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_LIDX = B_OFULL + 1, B_XST = B_LIDX + 1, B_XST2 = B_XST + 1,
@@ -82,19 +81,29 @@ static_assert(B_FSEMPTY + 2 <= 40, "barrier block");
 
 // What depends on the plan: ring depth, the gathered partial outputs (rank 0, clusters only), one logical index and one
 // 64-bit selection key per entry of the CTA's slice.
+// the tail's select scratch (bucket histograms for roco; the gather / reduction buffers of every single-victim select):
+// carved only for steps that select a victim by score — no-policy steps (generation over a retained cache) keep the
+// shared memory for one more ring stage
+__host__ __device__ inline bool du_select_scratch(const ekv_step& st) {
+  return st.evict > 0 && (st.policy == EKV_POLICY_ROCO || st.policy == EKV_POLICY_H2O || st.policy == EKV_POLICY_TOVA);
+}
+
 struct DuSmem {
-  int nstage, off_obuf, off_lj, off_kk, total;
-  __host__ __device__ DuSmem(int tps, int C) {
+  int nstage, off_obuf, off_lj, off_kk, off_bkt, total;
+  // `bucket`: the step selects a roco victim — the bucket select's histograms / lists (ekv_bucket.cuh) are carved as well
+  __host__ __device__ DuSmem(int tps, int C, bool bucket) {
     using namespace du;
     const int nent = tps * TKEYS + 8;
     const int obuf = C > 1 ? C * 8 * D * 4 : 0;
-    const int arrays = obuf + (nent * 4 + 15) / 16 * 16 + nent * 8;
+    const int bkt = bucket ? (BucketScratch::bytes(MAX_CLUSTER) + 15) / 16 * 16 : 0;
+    const int arrays = obuf + (nent * 4 + 15) / 16 * 16 + nent * 8 + bkt;
     int ns = (227 * 1024 - 1024 - OFF_RING - arrays) / STAGE_BYTES;
     nstage = ns > MAX_STAGE ? MAX_STAGE : ns;
     int o = OFF_RING + (nstage > 0 ? nstage : 0) * STAGE_BYTES;
     off_obuf = o; o += obuf;
     off_lj = o; o += (nent * 4 + 15) / 16 * 16;
     off_kk = o; o += nent * 8;
+    off_bkt = o; o += bkt;
     total = o + 1024;
   }
 };
@@ -112,7 +121,8 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   constexpr int GW = GP / 2;                                     // ... as 32-bit words = parked TMEM columns per tile
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const DuSmem SL(pl.tps, pl.C);
+  const bool want_bucket = du_select_scratch(a.st);            // (uniform over the launch; a budget gate only skips it per unit)
+  const DuSmem SL(pl.tps, pl.C, want_bucket);
   const int NSTAGE = SL.nstage;
   unsigned char* ring = smem + OFF_RING;
   unsigned char* Qs = smem + OFF_Q;
@@ -134,7 +144,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   uint32_t* xhist = reinterpret_cast<uint32_t*>(smem + OFF_CAND);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem + OFF_HIST);
   BucketScratch bs;
-  bs.carve(smem + OFF_BKT, MAX_CLUSTER);
+  bs.carve(smem + SL.off_bkt, MAX_CLUSTER);                     // (only touched when want_bucket)
   float* fs = reinterpret_cast<float*>(smem + OFF_FS);
   int32_t* lj = reinterpret_cast<int32_t*>(smem + SL.off_lj);
   unsigned long long* kk = reinterpret_cast<unsigned long long*>(smem + SL.off_kk);
@@ -212,7 +222,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     cp_async_commit();
     for (int i = lane; i < 2 * 4096 / 16; i += 32) reinterpret_cast<uint4*>(Ps)[i] = make_uint4(0, 0, 0, 0);
   }
-  if (warp >= NSOFT / 32 + 2) bs.clear(tid - NSOFT - 64, NHELP);  // the helper warps zero the select histograms
+  if (want_bucket && a.st.policy == EKV_POLICY_ROCO && warp >= NSOFT / 32 + 2) bs.clear(tid - NSOFT - 64, NHELP);  // the helper warps zero the select histograms
   umma::fence_before_sync();
   __syncthreads();                                               // barriers initialised, TMEM base published
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");      // waited for right before the first remote access
@@ -718,11 +728,12 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       Feasibility fz;
       fz.mode = 0; fz.lsh = lsh; fz.T1 = 0u; fz.jT = 0xffffffffu;
       fz.b.status = bk::OK; fz.b.bsel = 0; fz.b.rb = 0; fz.b.csel = 0; fz.b.kind = 0; fz.b.mtot = 0; fz.b.my_off = 0;
+      const uint32_t kk_a = smem_u32(kk), lj_a = smem_u32(lj);      // (explicit ld.shared: see ekv_bucket.cuh)
       auto get = [&](int e, uint32_t& ka, uint32_t& kb, uint32_t& l) -> bool {
-        const unsigned long long k = kk[e];
-        if (k == ~0ull) return false;
-        ka = (uint32_t)k; kb = (uint32_t)(k >> 32); l = (uint32_t)lj[e];
-        return true;
+        const unsigned long long k = lds_u64(kk_a + 8u * (uint32_t)e);
+        l = lds_u32(lj_a + 4u * (uint32_t)e);
+        ka = (uint32_t)k; kb = (uint32_t)(k >> 32);
+        return k != ~0ull;
       };
       if (roco) {
         int hphase = 0;
@@ -735,6 +746,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
           }
         };
         hist_sync();
+        if (tl && ttid == 0) tl[9] = global_ns();
         auto ld = [&](const uint32_t* ptr, int peer) -> uint4 {
           if (C == 1 || peer == rank) return *reinterpret_cast<const uint4*>(ptr);
           uint4 v;
@@ -743,7 +755,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
         };
         fz.b = bucket_scan<MAX_CLUSTER>(bs, st.k_feasible, C, rank, ttid, NTAIL, NEl, sync, ld, get, hist_sync);
         fz.mode = 1;
-        if (tl && ttid == 0) tl[8] = (unsigned long long)(1 + fz.b.status + 4 * fz.b.kind);
+        if (tl && ttid == 0) { tl[8] = (unsigned long long)(1 + fz.b.status + 4 * fz.b.kind); tl[10] = global_ns(); tl[14] = (unsigned long long)fz.b.mtot; }
         if (fz.b.status == bk::FALLBACK) {
           // The cut falls into a bucket crowded with non-NaN keys (e.g. thousands of slots whose std is exactly 0): select in
           // bounded time.  Cluster-wide MSB-first radix select (8 bits per pass, every pass's 256-bin histogram all-gathered
@@ -832,16 +844,16 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
           fz.mode = 2; fz.T1 = T1; fz.jT = jT;
         }
       }
-      auto push = [&](unsigned long long* slot, unsigned long long hi, unsigned long long lo) {
-        if (C == 1) { slot[0] = hi; slot[1] = lo; }
-        else
-          for (int p2 = 0; p2 < C; ++p2) {
-            const uint32_t dst = map_to_rank(slot, p2);
-            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst), "l"(hi) : "memory");
-            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst + 8), "l"(lo) : "memory");
-          }
+      auto push = [&](unsigned long long* slot, unsigned long long hi, unsigned long long lo) {       // to every OTHER CTA
+        for (int p2 = 0; p2 < C; ++p2) {
+          if (p2 == rank) continue;
+          const uint32_t dst = map_to_rank(slot, p2);
+          asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst), "l"(hi) : "memory");
+          asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst + 8), "l"(lo) : "memory");
+        }
       };
-      bucket_pass(bs, fz, NEl, rank, ttid, NTAIL, get, push);
+      bucket_pass(bs, fz, NEl, rank, ttid, NTAIL, get, push, sync, tl ? tl + 13 : nullptr);
+      if (tl && ttid == 0) tl[11] = global_ns();
       if (C > 1) {
         __syncwarp();                                            // the warp's remote stores precede its lanes' release-arrives
         if (lane < C) umma::mbar_arrive_remote(map_to_rank(&bars[B_XG], lane));
@@ -849,6 +861,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       } else {
         sync();
       }
+      if (tl && ttid == 0) tl[12] = global_ns();
       Tuple128 wn;
       if (bucket_final(bs, fz, C, ttid, NTAIL, sync, wn)) {
         l_c = (uint32_t)(wn.lo >> 32); owner = (int)((wn.lo >> 24) & 0xffu); e_c = (int)(wn.lo & 0xffffffu);
@@ -915,7 +928,7 @@ static int launch_du_k(const KernelArgs& a, const DecodeUmmaPlan& pl, const CUte
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(a.B * a.Hkv * pl.C), 1, 1);
   cfg.blockDim = dim3(NT, 1, 1);
-  cfg.dynamicSmemBytes = (size_t)DuSmem(pl.tps, pl.C).total;
+  cfg.dynamicSmemBytes = (size_t)DuSmem(pl.tps, pl.C, du_select_scratch(a.st)).total;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -955,7 +968,7 @@ template <typename T, int G> static int launch_du_tg(const KernelArgs& a, cudaSt
     const int tps = (pl.nct + c - 1) / c;
     constexpr int GW = (G < 2 ? 2 : G) / 2;
     if (tps > (int)(TM_COLS - TM_LOG) / GW) continue;            // parked logits: GW tensor-memory columns per tile
-    if (DuSmem(tps, c).nstage < 3) continue;                     // the per-entry arrays must leave a 3-stage ring
+    if (DuSmem(tps, c, du_select_scratch(a.st)).nstage < 3) continue;                     // the per-entry arrays must leave a 3-stage ring
     const int cc = conc[c] * sms / 148 > 0 ? conc[c] * sms / 148 : 1;
     const double waves = (double)((U + cc - 1) / cc);
     const double cost = waves * (tps + 5.0 + 0.5 * c);           // fixed per-CTA work ~ 5 tile-times; exchanges grow with c

@@ -156,7 +156,8 @@ class GraphedDecodeStep:
         return self.logits if all_rows else self.logits[:, -1, :]
 
 
-DENSE_CHUNK = 64      # tokens per forward of the dense (no-eviction) prefill
+DENSE_CHUNK = 256     # tokens per forward of the dense (no-eviction) prefill (generation_config['dense_chunk']): each forward
+                      # streams the whole model's weights once, so fewer, larger forwards (64 -> 256: 7B 4096-token prefill 0.60 s)
 
 
 @torch.inference_mode()
@@ -226,8 +227,9 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
         forward (easykv.py:232, :396, :557).  Chunked so that every forward is one fused launch per layer."""
         logits = None
         sp = P.StepParams(policy=policy, accumulate=True, raw_colsum=True) if seed else P.StepParams()
-        for t0 in range(0, upto, DENSE_CHUNK):
-            logits = forward(input_ids[:, t0:min(t0 + DENSE_CHUNK, upto)], t0, sp)
+        dc = int(cfg.get("dense_chunk", DENSE_CHUNK))
+        for t0 in range(0, upto, dc):
+            logits = forward(input_ids[:, t0:min(t0 + dc, upto)], t0, sp)
         if seed:
             for l in range(cache.L):
                 cache.round_state(l)

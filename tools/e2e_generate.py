@@ -87,7 +87,7 @@ def main():
                           keep_attention=args.keep_attention, stride=args.stride, policy=args.policy, prefill_s=round(out["prefill_only"], 3),
                           decode_tokens_per_s=round(args.new / dec, 2), decode_ms_per_token=round(dec / args.new * 1e3, 2),
                           retained=sess.cache.n[0], eviction_events=len(sess.events), printed=out["printed"],
-                          launches=int(sess.cache.lib.ekv_launch_count()), graphed_steps=sess.graphed_steps, graph_capture_s=round(sess.graph_capture_s, 3),
+                          launches=int(sess.cache.lib.ekv_launch_count()), graphed_steps=sess.graphed_steps, graphed_chunks=sess.graphed_chunks, graph_capture_s=round(sess.graph_capture_s, 3),
                           steady_ms_per_token=round((dec - sess.graph_capture_s) / args.new * 1e3, 2),
                           graph_error=sess.graph_error)))
 

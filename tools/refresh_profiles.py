@@ -11,9 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
 rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
-COPIES = {"bench.json": "bench_b64.json", "bench_b32.json": "bench_b32.json", "bench_ref.json": "bench_reference_arm.json",
+COPIES = {"timeline_bench.txt": "timeline_persistent_bench_state.txt", "decode_umma_timeline.txt": "decode_umma_timeline_bench_state.txt", "smoke.txt": "smoke.txt",
+          "bench.json": "bench_b64.json", "bench_b32.json": "bench_b32.json", "bench_ref.json": "bench_reference_arm.json",
           "pytest.txt": "pytest_gpu.txt", "sweep_decode.jsonl": "sweep_decode.jsonl", "sweep_cluster.jsonl": "sweep_decode_cluster.jsonl",
-          "sweep_chunk.jsonl": "sweep_chunk_tensorcore.jsonl", "chunk_launches.csv": "chunk_launches.csv", "launches.csv": "launches.csv",
+          "sweep_chunk.jsonl": "sweep_chunk.jsonl", "chunk_launches.csv": "chunk_launches.csv", "launches.csv": "launches.csv",
           "e2e_llama7b.json": "e2e_generate_llama7b.json", "e2e_mistral7b.json": "e2e_generate_mistral7b_c3_literal.json"}
 for src, dst in COPIES.items():
     s = os.path.join(G, f"{tag}_{src}")
@@ -53,23 +54,25 @@ if r:
                "dram_bytes_write": [tb(x, "dram__bytes_write.sum") for x in rows[2:]],
                "gpu_time_us": [val(x, "gpu__time_duration.sum") for x in rows[2:]], "bytes_alg_per_launch": 1197531136,
                "source": "ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 40 -c 3 python bench.py "
-                         "--steps 2 --warmup 3 --no-graph --no-cpu-baseline --layers 8 (gpurun, 1x B200, tools/gpu_round.sh)"},
+                         "--steps 2 --warmup 3 --no-sweep --no-cpu-baseline --no-gpu-reference --min-seconds 0.05 --layers 8 (gpurun, 1x B200, tools/gpu_round.sh)"},
               open(os.path.join(P, f"traffic_{rnd}.json"), "w"), indent=1)
     print("decode: traffic", sum(tr) / len(tr), "us", [val(x, "gpu__time_duration.sum") for x in rows[2:]])
-r = raw(os.path.join(G, f"{tag}_chunk_tc.ncu-rep"), os.path.join(P, f"{rnd}_chunk_tc_ncu_raw.csv"))
-if r:
-    rows, idx, units = r
-    for x in rows[2:]:
-        print(x[idx["Kernel Name"]][:70], x[idx["gpu__time_duration.sum"]], "us; hmma",
-              x[idx["sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"]], "% issue",
-              x[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]], "% regs", x[idx["launch__registers_per_thread"]])
+for rep, dst in (("chunk_umma", "chunk_umma_ncu_raw.csv"), ("decode_umma", "decode_umma_ncu_raw.csv"), ("chunk_tc", "chunk_tc_ncu_raw.csv")):
+    r = raw(os.path.join(G, f"{tag}_{rep}.ncu-rep"), os.path.join(P, f"{rnd}_{dst}"))
+    if r:
+        rows, idx, units = r
+        g = lambda x, h: x[idx[h]] if h in idx else "n/a"
+        for x in rows[2:]:
+            print(x[idx["Kernel Name"]][:70], x[idx["gpu__time_duration.sum"]], "us; dram read", g(x, "dram__bytes_read.sum"), g(x, "dram__bytes_write.sum"),
+                  "; tensor pipe", g(x, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"), "% issue",
+                  g(x, "smsp__issue_active.avg.pct_of_peak_sustained_active"), "% regs", g(x, "launch__registers_per_thread"))
 for f in ("bench_b64.json", "bench_b32.json", "bench_reference_arm.json"):
     p = os.path.join(P, f"{rnd}_{f}")
     if os.path.exists(p):
         d = json.loads(open(p).read().strip().splitlines()[-1])
         print(f, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "frac", (d.get("roofline") or {}).get("frac"),
               d.get("clocks"), (d.get("cpu_baseline") or {}).get("value"))
-for f in ("sweep_decode.jsonl", "sweep_chunk_tensorcore.jsonl"):
+for f in ("sweep_decode.jsonl", "sweep_chunk.jsonl"):
     p = os.path.join(P, f"{rnd}_{f}")
     if os.path.exists(p):
         for l in open(p):
