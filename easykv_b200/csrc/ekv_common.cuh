@@ -290,7 +290,7 @@ template <typename T> __device__ __noinline__ void rope_row8(Row8<T>& x, int l16
   x.u.x = add2_rn(mul2_rn(x.u.x, c.x, t), mul2_rn(o.x, sn.x, t), t); x.u.y = add2_rn(mul2_rn(x.u.y, c.y, t), mul2_rn(o.y, sn.y, t), t);
   x.u.z = add2_rn(mul2_rn(x.u.z, c.z, t), mul2_rn(o.z, sn.z, t), t); x.u.w = add2_rn(mul2_rn(x.u.w, c.w, t), mul2_rn(o.w, sn.w, t), t);
 }
-template <> __device__ __forceinline__ void rope_row8<float>(Row8<float>&, int, const void*, const void*, int) {}   // (fp32 is not fused)
+template <> inline __device__ void rope_row8<float>(Row8<float>&, int, const void*, const void*, int) {}   // (fp32 is not fused)
 
 template <typename T> __device__ __forceinline__ T neg_inf();
 template <> __device__ __forceinline__ __half neg_inf<__half>() { return __ushort_as_half(0xfc00); }

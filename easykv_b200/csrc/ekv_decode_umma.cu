@@ -42,16 +42,13 @@ constexpr int NSOFT = 128;               // 4 softmax warps: one thread per TMEM
 constexpr int NHS = 128;                 // helper warps, one SET of 4: the per-key policy work of the V phase (state update, IEEE
 constexpr int NHELP = 2 * NHS;           // div / sqrt for the roco keys, select histograms) is a long dependent chain per key — two sets
                                          // take alternate tiles, so each has two tile-times for its chain; set 0 joins the tail
-constexpr int NTAIL = NSOFT + NHS;       // threads of the tail (select, renumbering): latency-bound shared-memory scanning
+constexpr int NTAIL = NHELP;             // the tail (select, renumbering) runs on BOTH helper sets, concurrently with the softmax warps' output gather
 constexpr int NT = NSOFT + 64 + NHELP;   // softmax | TMA producer warp | MMA warp | helper set 0 | helper set 1
 constexpr int STAGE_BYTES = 32768;
 constexpr int MAX_STAGE = 5;             // ring depth: whatever shared memory is left after the per-entry arrays (3 .. 5)
 constexpr int MAX_CLUSTER = 4;
 constexpr int NCAND = 2;                 // candidates per walk round
 constexpr int NTW = NTAIL / 32;          // warps taking part in the tail
-constexpr int MAX_WALK = 1;              // walk rounds before the bounded-time radix select takes over (in fp16 the
-                                         // reference's p**2 underflows for p < 2.4e-4: on long caches most low-mean slots
-                                         // have a NaN std and are infeasible, so the radix select is the common case there)
 static_assert(NTAIL == 256, "one radix bin per tail thread");
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint32_t TM_S = 0, TM_O = 32, TM_LOG = 48, TM_COLS = 512;      // S^T 2 x 16 | O^T 16 | parked logits
@@ -75,8 +72,8 @@ constexpr int OFF_RING = (OFF_FS + 2 * TKEYS * 4 + 1023) / 1024 * 1024;
 // barriers
 constexpr int B_FULL = 0, B_EMPTY = MAX_STAGE, B_SFULL = 2 * MAX_STAGE, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2,
               B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_LIDX = B_OFULL + 1, B_XST = B_LIDX + 1, B_XST2 = B_XST + 1,
-              B_XOUT = B_XST2 + 1, B_XHIST = B_XOUT + 1, B_HRDY = B_XHIST + 2, B_XG = B_HRDY + 1, B_FSFULL = B_XG + 1, B_FSEMPTY = B_FSFULL + 2;
-static_assert(B_FSEMPTY + 2 <= 40, "barrier block");
+              B_XOUT = B_XST2 + 1, B_XHIST = B_XOUT + 1, B_HRDY = B_XHIST + 2, B_XG = B_HRDY + 1, B_FSFULL = B_XG + 1, B_FSEMPTY = B_FSFULL + 2, B_PNEW = B_FSEMPTY + 2;
+static_assert(B_PNEW + 1 <= 40, "barrier block");
 }  // namespace du
 
 // What depends on the plan: ring depth, the gathered partial outputs (rank 0, clusters only), one logical index and one
@@ -187,6 +184,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     mbar_init(&bars[B_HRDY], C);
     mbar_init(&bars[B_XG], NTW * C);
     for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_FSFULL + s], NSOFT / 32); mbar_init(&bars[B_FSEMPTY + s], NHS / 32); }
+    mbar_init(&bars[B_PNEW], 1);
     mbar_init(&bars[B_OFULL], 1);
     mbar_init(&bars[B_LIDX], 1);
     mbar_init(&bars[B_XST], 8 * C);
@@ -281,22 +279,9 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     // ===== softmax warps: TMEM lane = key =======================================================================================
     const int kl = warp * 32 + lane;                             // key inside a tile; output dim in the epilogue
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const ekv_step& st = stu;
     unsigned long long* tl = a.timeline ? a.timeline + (size_t)blockIdx.x * 16 : nullptr;     // profiling hook
     auto stamp = [&](int i) { if (tl && tid == 0) tl[i] = global_ns(); };
     stamp(0);
-    const int P = st.score_offset;
-    const int n_after = nb + 1, n_s = n_after - P;
-    const bool evicting = st.evict > 0 && st.policy != EKV_POLICY_NONE;
-    float* Sg = a.S + (size_t)unit * a.cap;
-    float* SQg = a.SQ + (size_t)unit * a.cap;
-    float* Cg = a.C + (size_t)unit * a.cap;
-    int32_t* lidx_g = a.lidx + (size_t)unit * a.cap;
-    const int new_slot = a.new_slots ? a.new_slots[unit] : n_phys;
-    const bool stateful = st.policy == EKV_POLICY_ROCO || st.policy == EKV_POLICY_H2O || st.policy == EKV_POLICY_TOVA;
-    // which entries the victim walk visits: roco — every scored slot (F_CAND; the std rank decides); h2o_head / tova — the window
-    const uint8_t need_flag = !evicting ? 0 : st.policy == EKV_POLICY_ROCO ? F_CAND : (st.policy == EKV_POLICY_RANGE ? 0 : F_FEAS);
-    const bool roco_sel = evicting && st.policy == EKV_POLICY_ROCO;
 
     auto finish_logit2 = [&](float x0, float x1) -> uint32_t {
       round2<T>(x0, x1);                                         // llama_patch.py:201
@@ -310,6 +295,26 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       if (first + e >= n_phys) lj[e] = -1;
     if (rank == 0 && tid == 0) lj[e_new] = nb;
     named_bar_sync(1, NSOFT);
+
+    // the appended token's own key (the reference attends it, llama_patch.py:193-196): rank 0, warp 0, CUDA cores —
+    // ahead of the K phase, while the first tiles are still in flight
+    if (rank == 0 && warp == 0) {
+      const T* qg = reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D;
+      const T* kn = reinterpret_cast<const T*>(a.k_new) + (size_t)unit * D;
+      float kx[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) kx[c] = Tr<T>::to_f(kn[lane * 4 + c]);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc = fmaf(Tr<T>::to_f(qg[g * D + lane * 4 + c]), kx[c], acc);
+        acc = warp_sum(acc);
+        float x = Tr<T>::round_f(acc);
+        x = Tr<T>::round_f(ARITH ? __fmul_rn(x, a.scale_mul) : __fdiv_rn(x, a.scale_div));
+        if (lane == 0) xnew_s[g] = x;
+      }
+    }
 
     // ---- K phase -----------------------------------------------------------------------------------------------------------
     uint32_t rmax[GW];
@@ -362,25 +367,6 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     }
     umma::tmem_wait_st();
     stamp(1);
-    // the appended token's own key (the reference attends it, llama_patch.py:193-196): rank 0, warp 0, CUDA cores
-    if (rank == 0 && warp == 0) {
-      const T* qg = reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D;
-      const T* kn = reinterpret_cast<const T*>(a.k_new) + (size_t)unit * D;
-      float kx[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) kx[c] = Tr<T>::to_f(kn[lane * 4 + c]);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc = fmaf(Tr<T>::to_f(qg[g * D + lane * 4 + c]), kx[c], acc);
-        acc = warp_sum(acc);
-        float x = Tr<T>::round_f(acc);
-        x = Tr<T>::round_f(ARITH ? __fmul_rn(x, a.scale_mul) : __fdiv_rn(x, a.scale_div));
-        if (lane == 0) xnew_s[g] = x;
-      }
-    }
-
     // ---- row statistics: lanes -> warps -> cluster -------------------------------------------------------------------------
 #pragma unroll
     for (int j = 0; j < GW; ++j) {
@@ -521,9 +507,22 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       const float ex = expf(x + negM[j]);
       return Tr<T>::round_f(ARITH ? div_rn_by(ex, L[j], Rc[j]) : __fmul_rn(ex, L[j]));
     };
-    const float inv_g = 1.0f / (float)G;
     stamp(2);
 
+    // the appended token's probabilities (rank 0), ahead of the V phase: the helper warps take its policy entry from here
+    if (rank == 0 && warp == 0) {
+      if (tid < 8) {
+        const int g = tid;
+        float pn = 0.f;
+        if (g < G) {
+          const float ex = expf(xnew_s[g] - rowM[g]);
+          pn = Tr<T>::round_f(ARITH ? div_rn_by(ex, rowL[g], rowR[g]) : __fmul_rn(ex, rowL[g]));
+        }
+        pnew_s[g] = pn;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_PNEW]);
+    }
     // ---- V phase: probabilities, P^T tiles; the folded probability of every key goes to the helper warps, which keep the
     // policy state and the selection keys (below) --------------------------------------------------------------------------------
     for (int i = 0; i < T_; ++i) {
@@ -563,39 +562,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       if (lane == 0) mbar_arrive(&bars[B_PFULL + pb]);
     }
     stamp(3);
-    // the appended token's probabilities and entry (rank 0)
-    if (rank == 0 && tid < 8) {
-      const int g = tid;
-      float pn = 0.f;
-      if (g < G) {
-        const float ex = expf(xnew_s[g] - rowM[g]);
-        pn = Tr<T>::round_f(ARITH ? div_rn_by(ex, rowL[g], rowR[g]) : __fmul_rn(ex, rowL[g]));
-      }
-      pnew_s[g] = pn;
-    }
-    named_bar_sync(1, NSOFT);
-    if (rank == 0 && tid == 0) {
-      float fsum = 0.f;
-#pragma unroll
-      for (int g = 0; g < G; ++g) fsum += pnew_s[g];
-      float sv = 0.f, sq = 0.f, cc = st.c_new0;
-      uint32_t ka = 0, kb = 0;
-      uint8_t f = 0;
-      bool dirty = false;
-      const int rl = nb;
-      if (rl >= P) {
-        float ds = 0.f, dsq = 0.f;
-        if (st.accumulate) {
-          ds = G == 1 ? fsum : Tr<T>::round_f(__fmul_rn(fsum, inv_g));
-          dsq = Tr<T>::round_f(__fmul_rn(ds, ds));
-        }
-        entry_update(st, rl - P, n_s, true, ds, dsq, sv, sq, cc, ka, kb, f, dirty);
-        if (dirty) { Sg[new_slot] = sv; SQg[new_slot] = sq; Cg[new_slot] = cc; }
-      }
-      const bool keyed = (f & need_flag) == need_flag && need_flag;
-      kk[e_new] = keyed ? (((unsigned long long)kb << 32) | ka) : ~0ull;
-      if (roco_sel && keyed && (((unsigned long long)kb << 32) | ka) != ~0ull) bs.add(ka, (uint32_t)rl, lsh);
-    }
+    named_bar_sync(1, NSOFT);                                    // (pnew_s, written by warp 0 ahead of the V phase, is read below)
 
     // ---- output: partial O^T -> rank 0 -> out ---------------------------------------------------------------------------------
     {
@@ -637,6 +604,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   if (warp >= NSOFT / 32 + 2) {
     // ===== helper warps, V phase: policy state + selection keys per key (accumulate, counter: easykv.py:288-304; keys:
     // ekv_select.cuh) and the select's histograms, from the folded probabilities the softmax warps hand over ===================
+    const int new_slot = a.new_slots ? a.new_slots[unit] : n_phys;
     const int hset = (tid - NSOFT - 64) / NHS;                   // set 0: even tiles, set 1: odd tiles (= the hand-over buffer)
     const int kl = (tid - NSOFT - 64) % NHS;                     // key inside a tile
     const ekv_step& st = stu;
@@ -698,11 +666,33 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
         bs.add_warp(keyed && (((unsigned long long)kb << 32) | ka) != ~0ull, ka, (uint32_t)rl, lsh, lane);
       }
     }
-    if (hset == 1) asm volatile("bar.arrive 2, %0;" ::"r"(NTAIL + NHS) : "memory");      // its keys are in shared memory; no part in the tail
+    if (rank == 0 && hset == 0 && kl == 0) {                     // the appended token's own entry
+      mbar_wait(&bars[B_PNEW], 0);
+      float fsum = 0.f;
+#pragma unroll
+      for (int g = 0; g < G; ++g) fsum += pnew_s[g];
+      float sv = 0.f, sq = 0.f, cc = st.c_new0;
+      uint32_t ka = 0, kb = 0;
+      uint8_t f = 0;
+      bool dirty = false;
+      const int rl = nb;
+      if (rl >= P) {
+        float ds = 0.f, dsq = 0.f;
+        if (st.accumulate) {
+          ds = G == 1 ? fsum : Tr<T>::round_f(__fmul_rn(fsum, inv_g));
+          dsq = Tr<T>::round_f(__fmul_rn(ds, ds));
+        }
+        entry_update(st, rl - P, n_s, true, ds, dsq, sv, sq, cc, ka, kb, f, dirty);
+        if (dirty) { Sg[new_slot] = sv; SQg[new_slot] = sq; Cg[new_slot] = cc; }
+      }
+      const bool keyed = (f & need_flag) == need_flag && need_flag;
+      kk[e_new] = keyed ? (((unsigned long long)kb << 32) | ka) : ~0ull;
+      if (roco_sel && keyed && (((unsigned long long)kb << 32) | ka) != ~0ull) bs.add(ka, (uint32_t)rl, lsh);
+    }
   }
   // ===== tail: victim walk, renumbering, append — the softmax warps and the helper warps (8 warps) ================================
-  if (warp < NSOFT / 32 || (warp >= NSOFT / 32 + 2 && warp < NSOFT / 32 + 2 + NHS / 32)) {
-    const int ttid = warp < NSOFT / 32 ? tid : tid - 64;         // 0 .. NTAIL-1
+  if (warp >= NSOFT / 32 + 2) {
+    const int ttid = tid - NSOFT - 64;                           // 0 .. NTAIL-1
     const int tw = ttid >> 5;                                    // tail warp 0 .. NTW-1
     const ekv_step& st = stu;
     const int P = st.score_offset;
@@ -710,8 +700,9 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     int32_t* lidx_g = a.lidx + (size_t)unit * a.cap;
     const int new_slot = a.new_slots ? a.new_slots[unit] : n_phys;
     unsigned long long* tl = a.timeline ? a.timeline + (size_t)blockIdx.x * 16 : nullptr;
-    if (warp >= NSOFT / 32 + 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // helpers: peers are running
-    named_bar_sync(2, NTAIL + NHS);                              // keys of every entry are in shared memory (helper set 1 arrives only)
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // (arrived during setup: every peer's barriers exist)
+    named_bar_sync(2, NTAIL);                                    // keys of every entry are in shared memory
+    if (tl && ttid == 0) tl[7] = global_ns();
     bool found = false;
     uint32_t l_c = 0;
     int owner = -1, e_c = -1;
@@ -894,8 +885,11 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
       if (a.victim_slots) a.victim_slots[unit] = -1;
     }
     if (tl && ttid == 0) tl[6] = global_ns();
-    // rank 0 appends the new row: every CTA of the cluster is past its streams (the output gather completed)
+    // rank 0 appends the new row once every CTA of the cluster is past its streams: the output gather has completed
+    // (the tail runs beside it on the helper warps, so it waits for the gather's barrier itself)
     if (rank == 0 && tw == 0) {
+      if (C > 1) umma::mbar_wait_cluster(&bars[B_XOUT], 0);
+      else if (T_ > 0) mbar_wait(&bars[B_OFULL], 0);
       const uint4* kn = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.k_new) + (size_t)unit * D);
       const uint4* vn = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.v_new) + (size_t)unit * D);
       uint4* Kw = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.K) + ((size_t)unit * a.cap + new_slot) * D);

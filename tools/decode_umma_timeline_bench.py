@@ -28,10 +28,12 @@ for i, nm in enumerate(names):
     dlt = (t[:, i + 1] - t[:, i]) / 1e3
     print(f"  {nm:32s} mean {dlt.mean():8.2f} us   p10 {dlt.quantile(0.1):8.2f}   p90 {dlt.quantile(0.9):8.2f}")
 if (t[:, 9] > 0).all():          # the select's pieces (roco): tail barrier + histogram exchange | scan | pass | exchange | final ranks + argmin
-    parts = [("tail barrier + histogram exchange", 4, 9), ("scan", 9, 10), ("classify pass", 10, 11), ("exchange", 11, 12), ("ranks + argmin", 12, 5)]
+    parts = [("tail barrier + histogram exchange", 7, 9), ("scan", 9, 10), ("classify pass", 10, 11), ("exchange", 11, 12), ("ranks + argmin", 12, 5)]
     for nm, i0, i1 in parts:
         dlt = (t[:, i1] - t[:, i0]) / 1e3
         print(f"    select: {nm:34s} mean {dlt.mean():6.2f} us")
     print(f"    classify pass: its entry loop alone {((t[:, 13] - t[:, 10]) / 1e3).mean():.2f} us (thread 0)")
     print(f"    boundary entries ranked by brute force: mean {t[:, 14].mean():.0f} max {t[:, 14].max():.0f}")
+if (t[:, 7] > 0).all():          # the tail runs on the helper warps beside the softmax warps' output gather
+    print(f"    tail start (helper warps) relative to the end of the V phase {((t[:, 7] - t[:, 3]) / 1e3).mean():+.2f} us; tail end after the output gather's end {((t[:, 6] - t[:, 4]) / 1e3).mean():+.2f} us; CTA busy {((t[:, 6] - t[:, 0]) / 1e3).mean():.1f} us")
 
