@@ -48,14 +48,25 @@ if r:
     val = lambda row, h: float(row[idx[h]].replace(",", ""))
     tb = lambda row, h: val(row, h) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[idx[h]]]
     tr = [tb(x, "dram__bytes_read.sum") + tb(x, "dram__bytes_write.sum") for x in rows[2:]]
-    json.dump({"round": int(rnd[1:]), "kernel": "ekv::decode_kernel<__half,1,2>", "seqs_per_gpu": 64,
-               "dram_bytes_per_launch": sum(tr) / len(tr),
-               "dram_bytes_read": [tb(x, "dram__bytes_read.sum") for x in rows[2:]],
-               "dram_bytes_write": [tb(x, "dram__bytes_write.sum") for x in rows[2:]],
-               "gpu_time_us": [val(x, "gpu__time_duration.sum") for x in rows[2:]], "bytes_alg_per_launch": 1197531136,
-               "source": "ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 40 -c 3 python bench.py "
-                         "--steps 2 --warmup 3 --no-sweep --no-cpu-baseline --no-gpu-reference --min-seconds 0.05 --layers 8 (gpurun, 1x B200, tools/gpu_round.sh)"},
-              open(os.path.join(P, f"traffic_{rnd}.json"), "w"), indent=1)
+    traffic = {"c2": {"round": int(rnd[1:]), "kernel": "ekv::decode_kernel<__half,1,2,false>", "seqs_per_gpu": 64,
+                      "dram_bytes_per_launch": sum(tr) / len(tr),
+                      "dram_bytes_read": [tb(x, "dram__bytes_read.sum") for x in rows[2:]],
+                      "dram_bytes_write": [tb(x, "dram__bytes_write.sum") for x in rows[2:]],
+                      "gpu_time_us": [val(x, "gpu__time_duration.sum") for x in rows[2:]], "bytes_alg_per_launch": 1197531136,
+                      "source": "ncu --set full --clock-control none -k regex:decode_kernel -s 60 -c 1 python bench.py --steps 2 --warmup 3 "
+                                "--no-sweep --no-cpu-baseline --no-gpu-reference --min-seconds 0.05 --layers 4 (gpurun, 1x B200, tools/gpu_ncu.sh)"}}
+    for wl, rep, seqs, src in (("c5", "decode_umma", 8, "ncu --set full -k regex:decode_umma_kernel -c 1 python bench.py --workload c5 ... (tools/gpu_ncu.sh)"),
+                               ("c3_chunk", "chunk_umma", 8, "ncu --set full -k regex:chunk_umma_kernel -c 1 python tools/chunk_profile.py 8 32 8 8208 16 h2o_head (tools/gpu_ncu.sh); "
+                                                              "the tcgen05 kernel only (chunk_out / chunk_tail add their own passes over the state)")):
+        rr = raw(os.path.join(G, f"{tag}_{rep}.ncu-rep"), os.path.join(P, f"{rnd}_{rep}_ncu_raw.csv"))
+        if rr:
+            rows2, idx2, units2 = rr
+            tb2 = lambda row, h: float(row[idx2[h]].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units2[idx2[h]]]
+            x = rows2[2]
+            traffic[wl] = {"round": int(rnd[1:]), "kernel": x[idx2["Kernel Name"]][:60], "seqs_per_gpu": seqs,
+                           "dram_bytes_per_launch": tb2(x, "dram__bytes_read.sum") + tb2(x, "dram__bytes_write.sum"),
+                           "gpu_time_us": [float(x[idx2["gpu__time_duration.sum"]].replace(",", ""))], "source": src}
+    json.dump(traffic, open(os.path.join(P, f"traffic_{rnd}.json"), "w"), indent=1)
     print("decode: traffic", sum(tr) / len(tr), "us", [val(x, "gpu__time_duration.sum") for x in rows[2:]])
 for rep, dst in (("chunk_umma", "chunk_umma_ncu_raw.csv"), ("decode_umma", "decode_umma_ncu_raw.csv"), ("chunk_tc", "chunk_tc_ncu_raw.csv")):
     r = raw(os.path.join(G, f"{tag}_{rep}.ncu-rep"), os.path.join(P, f"{rnd}_{dst}"))
