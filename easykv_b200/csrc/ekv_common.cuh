@@ -89,6 +89,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization): the next kernel of
+// the stream may be scheduled while this one still runs (pdl_trigger), and a kernel launched that way must not touch
+// global memory before the previous kernel has completed and flushed (pdl_wait).  Every decode kernel waits before its
+// first global access, so the stream's semantics are exactly the serial ones; what overlaps is launch latency, CTA
+// placement and the shared-memory / tensor-memory set-up — several microseconds per layer of a back-to-back decode step.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // pull `bytes` (a multiple of 16, from a 16-byte aligned address) into L2 without waiting for them
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");

@@ -69,6 +69,8 @@ decode_kernel(const KernelArgs a, const int stages) {
   using Cfg = DecodeCfg<T>;
   constexpr int D = Cfg::D, NWARP = Cfg::NWARP, NCONS = Cfg::NCONS, RPT = Cfg::RPT;
   constexpr int TILE_ROWS = Cfg::TILE_ROWS;
+  pdl_trigger();            // programmatic dependent launch: the next kernel may be placed now; this one touches global memory
+  pdl_wait();               // only once the previous kernel of the stream has completed (ekv_common.cuh)
   extern __shared__ __align__(128) unsigned char smem[];
   const DecodeSmem<T> L(G, a.n_phys, a.st.evict, NG);
   // full[g][s]: tile in ring slot s has landed, signalled to the consumer group g that owns the tile —
@@ -458,8 +460,17 @@ static int launch_decode_cfg_x(const KernelArgs& a, int grid, int stages, int sm
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(decode)", err);
     configured[dev] = 1;
   }
-  decode_kernel<T, G, NG, EXT><<<grid, NG * DecodeCfg<T>::NCONS + 32, smem_bytes, stream>>>(a, stages);
-  err = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(NG * DecodeCfg<T>::NCONS + 32, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // the kernel waits (pdl_wait) before its first global access
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  err = cudaLaunchKernelEx(&cfg, decode_kernel<T, G, NG, EXT>, a, stages);
   if (err != cudaSuccess) return set_cuda_error("decode_kernel launch", err);
   count_launch();
   return EKV_OK;

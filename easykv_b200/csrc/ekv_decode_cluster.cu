@@ -96,6 +96,8 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   constexpr int D = Cfg::D, NWARP = Cfg::NWARP, NCONS = Cfg::NCONS, RPT = Cfg::RPT, TILE_ROWS = Cfg::TILE_ROWS;
   constexpr int TILEB = TC ? TC_TILE_BYTES : Cfg::TILE_BYTES;
   static_assert(!TC || (sizeof(T) == 2 && TILE_ROWS == 64), "tensor-core variant: 16-bit dtypes");
+  pdl_trigger();            // programmatic dependent launch: the next kernel may be placed now; this one touches global memory
+  pdl_wait();               // only once the previous kernel of the stream has completed (ekv_common.cuh)
   extern __shared__ __align__(128) unsigned char smem[];
   const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
   const ClusterSmem<T> L(G, slice, C, TC);
@@ -954,13 +956,15 @@ static int launch_cluster_tg(const KernelArgs& a, int C, int slice, int stages, 
   cfg.blockDim = dim3(DecodeCfg<T>::NCONS + 32, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // the kernel waits (pdl_wait) before its first global access
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   err = cudaLaunchKernelEx(&cfg, decode_cluster_kernel<T, G, TC>, a, stages, slice);
   if (err != cudaSuccess) return set_cuda_error("decode_cluster_kernel launch", err);
   count_launch();

@@ -150,11 +150,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   const int C = pl.C;
   const int rank = blockIdx.x % C;
   const int unit = blockIdx.x / C;
-  // ragged batches: this sequence's own count of valid slots; it evicts only past the budget gate (easykv.py:303)
-  const int nb = a.seq_n_before ? a.seq_n_before[unit / a.Hkv] : a.n_before;
-  ekv_step stu = a.st;
-  if (stu.budget_gate > 0 && nb + 1 - stu.score_offset <= stu.budget_gate) stu.evict = 0;
-  const int lsh = bk::lidx_shift(nb + 1);                       // logical indices -> histogram buckets
+  pdl_trigger();                                                 // the next launch may be placed while this one runs (it waits itself)
   const int n_phys = a.n_phys, nct = pl.nct;
   const int t0 = (int)((long long)rank * nct / C), t1 = (int)((long long)(rank + 1) * nct / C);
   const int T_ = t1 - t0;
@@ -192,6 +188,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     mbar_init(&bars[B_XOUT], NSOFT * (C - 1) + 1);               // rank 0: every peer thread + one local arrive
     flags[0] = 0; flags[1] = 0;
     mbar_fence_init();
+    pdl_wait();                                                  // the previous kernel of the stream has completed: global memory may be touched
     {
       // the slice of the slot map ahead of the tiles (one bulk copy): ints [first, first + cnt) of the unit
       int cnt = T_ * TKEYS;
@@ -208,6 +205,7 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
   }
   if (warp == NSOFT / 32 + 1) {
     umma::tmem_alloc(tmem_slot, TM_COLS);
+    pdl_wait();
     // Q as the K-major B operand: rows g < G are the group's query heads, rows >= G zero; P^T buffers zeroed once
     // (the softmax warps only ever write the rows < GP of a key)
     const T* qg = reinterpret_cast<const T*>(a.q) + (size_t)unit * G * D;
@@ -221,11 +219,17 @@ decode_umma_kernel(const KernelArgs a, const DecodeUmmaPlan pl, const __grid_con
     for (int i = lane; i < 2 * 4096 / 16; i += 32) reinterpret_cast<uint4*>(Ps)[i] = make_uint4(0, 0, 0, 0);
   }
   if (want_bucket && a.st.policy == EKV_POLICY_ROCO && warp >= NSOFT / 32 + 2) bs.clear(tid - NSOFT - 64, NHELP);  // the helper warps zero the select histograms
+  pdl_wait();                                                    // (every thread, before its first global access; the set-up above is on-chip)
   umma::fence_before_sync();
   __syncthreads();                                               // barriers initialised, TMEM base published
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");      // waited for right before the first remote access
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  // ragged batches: this sequence's own count of valid slots; it evicts only past the budget gate (easykv.py:303)
+  const int nb = a.seq_n_before ? a.seq_n_before[unit / a.Hkv] : a.n_before;
+  ekv_step stu = a.st;
+  if (stu.budget_gate > 0 && nb + 1 - stu.score_offset <= stu.budget_gate) stu.evict = 0;
+  const int lsh = bk::lidx_shift(nb + 1);                       // logical indices -> histogram buckets
 
   if (warp == NSOFT / 32) {
     // ===== TMA producer ==================================================================================================
@@ -924,13 +928,15 @@ static int launch_du_k(const KernelArgs& a, const DecodeUmmaPlan& pl, const CUte
   cfg.blockDim = dim3(NT, 1, 1);
   cfg.dynamicSmemBytes = (size_t)DuSmem(pl.tps, pl.C, du_select_scratch(a.st)).total;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)pl.C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // the kernel waits (pdl_wait) before its first global access
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   err = cudaLaunchKernelEx(&cfg, decode_umma_kernel<T, G, ARITH>, a, pl, maps[0], maps[1]);
   if (err != cudaSuccess) return set_cuda_error("decode_umma_kernel launch", err);
   count_launch();
