@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(tc::NT, PASS == 1 ? 3 : 2) chunk_tc_kernel(con
 // ---- 3. out = sum over splits of the partial outputs (llama_patch.py:222) ------------------------------------------------------
 template <typename T, int G> __global__ void chunk_out_kernel(const KernelArgs a, const ChunkPlan pl, const int out_blocks) {
   using namespace tc;
+  pdl_trigger();            // programmatic dependent launch (ekv_common.cuh)
+  pdl_wait();
   if ((int)blockIdx.x >= out_blocks) {
     // the second part of the grid, one thread per (unit, entry): column statistics summed over the row blocks
     // (in row-block order), folded into the policy state (accumulate, counter), selection keys for the tail
@@ -499,6 +501,8 @@ struct TailSmem {
 
 template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kernel(const KernelArgs a, const ChunkPlan pl) {
   using namespace tc;
+  pdl_trigger();            // programmatic dependent launch (ekv_common.cuh)
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_phys = a.n_phys, QL = a.q_len, NE = pl.NE;
   const bool evicting = a.st.evict > 0 && a.st.policy != EKV_POLICY_NONE;
@@ -587,10 +591,22 @@ template <typename T, int G> static int launch_finish_tg(const KernelArgs& a, co
   const int U = a.B * a.Hkv;
   const int out_blocks = (U * pl.R * (D / 4) + 255) / 256;
   const int col_blocks = (U * pl.NEpad + 255) / 256;               // state update: always (new slots need their state)
-  chunk_out_kernel<T, G><<<out_blocks + col_blocks, 256, 0, stream>>>(a, pl, out_blocks);
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // both kernels wait (pdl_wait) before their first global access
+  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(out_blocks + col_blocks), 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = stream;
+  cfg.attrs = pdl;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, chunk_out_kernel<T, G>, a, pl, out_blocks);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_out_kernel launch", err);
   count_launch();
-  chunk_tail_kernel<T><<<U, TAIL_NT, TL.total, stream>>>(a, pl);
+  cfg.gridDim = dim3((unsigned)U, 1, 1);
+  cfg.blockDim = dim3(TAIL_NT, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)TL.total;
+  cudaLaunchKernelEx(&cfg, chunk_tail_kernel<T>, a, pl);
   if ((err = cudaGetLastError()) != cudaSuccess) return set_cuda_error("chunk_tail_kernel launch", err);
   count_launch();
   return EKV_OK;

@@ -91,6 +91,8 @@ chunk_umma_kernel(const KernelArgs a, const ChunkPlan pl, const __grid_constant_
   constexpr int CW = NROWS / NSPLIT;                             // rows (TMEM columns) per softmax thread
   constexpr int CW2 = CW / 2;                                    // ... as packed 16-bit pairs
   static_assert(CW % G == 0 && CW2 >= 8, "a thread's rows hold whole queries");
+  pdl_trigger();            // programmatic dependent launch (ekv_common.cuh): the next kernel may be placed now;
+  pdl_wait();               // this one touches global memory only once the previous kernel of the stream has completed
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* ring = smem + OFF_RING;
@@ -628,13 +630,15 @@ static int launch_umma_k(const KernelArgs& a, const ChunkPlan& pl, const CUtenso
   cfg.blockDim = dim3(nthreads(NSPLIT), 1, 1);
   cfg.dynamicSmemBytes = SMEM_ALLOC;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)pl.splits;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // the kernel waits (pdl_wait) before its first global access
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   err = cudaLaunchKernelEx(&cfg, chunk_umma_kernel<T, G, ARITH, NSPLIT>, a, pl, maps[0], maps[1], maps[2], maps[3]);
   if (err != cudaSuccess) return set_cuda_error("chunk_umma_kernel launch", err);
   count_launch();
