@@ -17,21 +17,22 @@
 namespace ekv {
 
 namespace gen {
-constexpr int D = 128;
 constexpr int NT = 256;          // threads
 constexpr int NW = NT / 32;      // warps
 constexpr int RB = 64;           // (query, head) rows per block = NW * 8
 constexpr int TK = 32;           // keys per tile (one per lane)
-constexpr int KS = D + 4;        // padded fp32 row stride of the K tile (conflict-free 128-bit reads)
 constexpr int PS = TK + 1;
 }  // namespace gen
+// head_dim D is a template parameter of this kernel (64, 96, 128: the reference is generic in it, llama_patch.py:169-172);
+// the tensor-core and decode kernels are built for 128 and decline anything else, which then lands here.
 
 struct GenSmem {
   int off_ns, off_lj, off_colS, off_colSQ, off_pool, total;
   // inside the pool (attention phase)
   int off_q, off_k, off_v, off_p, off_cpart;
-  __host__ __device__ GenSmem(int n_phys, int q_len, int evict) {
+  __host__ __device__ GenSmem(int n_phys, int q_len, int evict, int D) {
     using namespace gen;
+    const int KS = D + 4;   // padded fp32 row stride of the K tile (conflict-free 128-bit reads: KS % 32 == 4 for D = 64, 96, 128)
     const int NE = n_phys + q_len;
     int o = 0;
     off_ns = o; o += (q_len * 4 + 15) / 16 * 16;
@@ -69,12 +70,13 @@ template <> __device__ __forceinline__ void load4<float>(const float* p, float (
   x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
 }
 
-template <typename T, int G>
+template <typename T, int G, int D>
 __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
   using namespace gen;
+  constexpr int KS = D + 4;
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_phys = a.n_phys, QL = a.q_len, NE = n_phys + QL, R = QL * G;
-  const GenSmem L(n_phys, QL, a.st.evict);
+  const GenSmem L(n_phys, QL, a.st.evict, D);
   int32_t* ns = reinterpret_cast<int32_t*>(smem + L.off_ns);
   int32_t* lj = reinterpret_cast<int32_t*>(smem + L.off_lj);
   float* colS = reinterpret_cast<float*>(smem + L.off_colS);
@@ -244,7 +246,8 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
           colS[e] = s1; colSQ[e] = s2;
         }
       }
-      // P·V: lane owns output dims [4*lane, 4*lane+4) of the warp's 8 rows
+      // P·V: lane owns output dims [4*lane, 4*lane+4) of the warp's 8 rows (lanes past D / 4 idle for D < 128)
+      if (lane * 4 < D) {
 #pragma unroll 4
       for (int kk = 0; kk < TK; ++kk) {
         const float4 vv = *reinterpret_cast<const float4*>(vtile + kk * D + lane * 4);
@@ -255,11 +258,12 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
           acc[r][2] = fmaf(pr, vv.z, acc[r][2]); acc[r][3] = fmaf(pr, vv.w, acc[r][3]);
         }
       }
+      }
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int row = row0 + r;
-      if (row < R) {
+      if (row < R && lane * 4 < D) {
         const int i = row / G, g = row % G;
         T* o = og + ((size_t)(h * G + g) * QL + i) * D + lane * 4;
 #pragma unroll
@@ -307,23 +311,32 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
   }
 }
 
-template <typename T, int G> static int launch_general_tg(const KernelArgs& a, cudaStream_t stream) {
-  const GenSmem L(a.n_phys, a.q_len, a.st.evict);
+template <typename T, int G, int D> static int launch_general_tgd(const KernelArgs& a, cudaStream_t stream) {
+  const GenSmem L(a.n_phys, a.q_len, a.st.evict, D);
   if (L.total > 227 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "general kernel: %d bytes of shared memory needed", L.total);
   static thread_local int configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   cudaError_t err;
   if (dev < 16 && !configured[dev]) {
-    err = cudaFuncSetAttribute(general_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    err = cudaFuncSetAttribute(general_kernel<T, G, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(general)", err);
     configured[dev] = 1;
   }
-  general_kernel<T, G><<<a.B * a.Hkv, gen::NT, L.total, stream>>>(a);
+  general_kernel<T, G, D><<<a.B * a.Hkv, gen::NT, L.total, stream>>>(a);
   err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error("general_kernel launch", err);
   count_launch();
   return EKV_OK;
+}
+
+template <typename T, int G> static int launch_general_tg(const KernelArgs& a, cudaStream_t stream) {
+  switch (a.d) {
+    case 64: return launch_general_tgd<T, G, 64>(a, stream);
+    case 96: return launch_general_tgd<T, G, 96>(a, stream);
+    case 128: return launch_general_tgd<T, G, 128>(a, stream);
+    default: return set_error(EKV_ERR_UNSUPPORTED, "head_dim %d (built: 64, 96, 128)", a.d);
+  }
 }
 
 template <typename T> static int launch_general_t(const KernelArgs& a, cudaStream_t stream) {
@@ -337,7 +350,6 @@ template <typename T> static int launch_general_t(const KernelArgs& a, cudaStrea
 }
 
 int launch_general(const KernelArgs& a, cudaStream_t stream) {
-  if (a.d != gen::D) return set_error(EKV_ERR_UNSUPPORTED, "head_dim %d (only 128 is built)", a.d);
   switch (a.dtype) {
     case EKV_F16: return launch_general_t<__half>(a, stream);
     case EKV_BF16: return launch_general_t<__nv_bfloat16>(a, stream);

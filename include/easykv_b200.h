@@ -17,8 +17,10 @@
  *   - dtype: the element type of q/k/v/K/V/out (EKV_F16, EKV_BF16, EKV_F32).  Policy state is
  *     always fp32, slot maps int32.
  *
- * Supported shapes (this build): head dim d = 128; GQA group size H / Hkv in {1, 2, 4, 8} (every Llama-2 / Code Llama /
- * Mistral layout); all sequences of a call share n_before / n_phys.  Anything else returns EKV_ERR_UNSUPPORTED.
+ * Supported shapes (this build): head dim d = 128 on every kernel, d = 64 and 96 on the exact CUDA-core kernel (the
+ * tensor-core and decode kernels decline them and the call lands there: same results, lower throughput); GQA group size
+ * H / Hkv in {1, 2, 4, 8} (every Llama-2 / Code Llama / Mistral layout); sequences of a call share n_before / n_phys
+ * unless io.seq_n_before is given (decode steps).  Anything else returns EKV_ERR_UNSUPPORTED.
  *
  * HBM layout (per layer; B sequences, Hkv KV heads, `cap` physical slots, head dim d)
  *   K, V        [B, Hkv, cap, d]   dtype      physical slot order — rows NEVER move

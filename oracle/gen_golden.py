@@ -106,6 +106,16 @@ CASES = {
     "llama_enc_roco_fp16": dict(arch="llama", L=1, H=4, Hkv=4, d=128, seq=128, dtype="float16",
                                 mode="encoding", stride=8, max_new_tokens=2,
                                 gen=dict(budget=0.5, kv_policy="roco")),
+    # head_dim 64 / 96 (the reference is generic in it, llama_patch.py:169-172)
+    "llama_auto_roco_d64_fp32": dict(arch="llama", L=2, H=4, Hkv=4, d=64, seq=96, dtype="float32",
+                                     mode="auto", stride=8, max_new_tokens=16,
+                                     gen=dict(budget=40, kv_policy="roco")),
+    "gqa_mistral_enc_h2o_d96_fp16": dict(arch="mistral", L=1, H=8, Hkv=2, d=96, seq=132, dtype="float16",
+                                         mode="encoding", stride=4, max_new_tokens=3,
+                                         gen=dict(budget=0.5, kv_policy="h2o_head")),
+    "gqa_llama_decoding_roco_stream_d64_fp16": dict(arch="llama", L=1, H=8, Hkv=2, d=64, seq=32, dtype="float16",
+                                                    mode="decoding", stride=1, max_new_tokens=48,
+                                                    gen=dict(budget=36, kv_policy="roco", streaming=True)),
 }
 
 

@@ -234,6 +234,49 @@ def test_chunk_random_vs_oracle(engines, dtype, H, Hkv, stride, policy, n0, kern
     assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
 
 
+@pytest.mark.parametrize("d", [64, 96])
+@pytest.mark.parametrize("dtype,H,Hkv,stride,policy,n0", [
+    (torch.float16, 8, 8, 1, "roco", 203), (torch.float16, 8, 2, 1, "roco", 517), (torch.float32, 4, 4, 1, "roco", 203),
+    (torch.bfloat16, 8, 1, 1, "h2o_head", 260), (torch.float16, 8, 4, 1, "tova", 300),
+    (torch.float16, 8, 2, 16, "roco", 517), (torch.float32, 4, 2, 24, "h2o_head", 260), (torch.bfloat16, 4, 4, 64, "roco", 700),
+])
+def test_head_dim_64_96_vs_oracle(engines, d, dtype, H, Hkv, stride, policy, n0):
+    """head_dim 64 and 96 (the reference is generic in it, llama_patch.py:169-172): decode steps and strided chunks at
+    the automatic dispatch — the kernels built for 128 decline and the exact kernel, a template over head_dim, serves
+    them — against the CPU restatement: same victims, outputs within the dtype's tolerance, same final cache."""
+    steps = 8 if stride == 1 else 4
+    g = torch.Generator().manual_seed(23 + d)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
+    eng = engines.CudaEngine(1, H, Hkv, d, dtype, capacity=n0 + stride + 7)
+    orc = replay.OracleEngine(1, H, Hkv, d, dtype)
+    K, V = rnd(Hkv, n0, d), rnd(Hkv, n0, d)
+    C0 = torch.arange(n0, 0, -1).float() if stride == 1 else torch.zeros(n0)
+    for e in (eng, orc):
+        e.load_prefill(0, K, V, n0, C0)
+    if stride == 1:
+        recent = int(n0 * 0.3)
+        st = restate.Step(policy=policy, accumulate=True, evict=1, counter_add=1.0, k_feasible=n0 - recent,
+                          win_recent=recent if policy == "h2o_head" else 0, range_start=4)
+    else:
+        recent, sink = int(n0 * 0.1), 4
+        st = restate.Step(policy=policy, accumulate=True, evict=stride, counter_add=float(stride), c_new_step=1.0,
+                          k_feasible=max(n0 - recent - sink, stride), sink_protect=sink, win_lo=sink, win_recent=recent,
+                          range_start=sink)
+    bad = 0
+    for t in range(steps):
+        q, k, v = rnd(H, stride, d) * 0.3, rnd(Hkv, stride, d), rnd(Hkv, stride, d)
+        o_ref, v_ref = orc.forward(0, st, q, k, v)
+        o, vic = eng.forward(0, st, q, k, v, force=v_ref)
+        tol = 2e-6 if dtype == torch.float32 else (1e-3 if dtype == torch.float16 else 8e-3)
+        assert (o.float() - o_ref.float()).abs().max().item() <= tol * max(1.0, o_ref.float().abs().max().item())
+        if not torch.equal(torch.sort(vic, dim=-1)[0], torch.sort(v_ref, dim=-1)[0]):
+            assert dtype != torch.float32 and min(orc.margin(0)) < 1e-5
+            bad += 1
+    assert bad <= 1
+    Kc, Vc = eng.export(0)
+    assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
+
+
 def test_chunk_one_pass_denominator_falls_back_when_logits_run_away(engines):
     """The tcgen05 chunk kernel sums softmax denominators in one pass against per-warp reference points (the row
     maximum over the first 128-key tile) and must detect rows whose later logits exceed that reference by more than
