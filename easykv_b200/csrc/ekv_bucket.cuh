@@ -254,23 +254,26 @@ struct Feasibility {
 // ... as key intervals, so that the pass judges an entry with a handful of compares and no divergence: feasible iff
 // ka < a_lo, or ka <= a_last and l < l_lo; listed (boundary) iff a_lo <= ka <= a_last and l_lo <= l < l_hi.
 struct FeasCut {
-  bool all;
-  uint32_t a_lo, a_last;
-  unsigned long long l_lo, l_hi;
+  // 32-bit forms (logical indices stay far below 2^32 - 1, so the 64-bit bounds saturate): in = ka - a_lo <= a_span;
+  // feasible = ka < a_lo || (in && l < l_lo); listed = in && l - l_lo < l_span (the unsigned wrap rejects l < l_lo)
+  uint32_t a_lo, a_span, l_lo, l_span;
   __device__ __forceinline__ explicit FeasCut(const Feasibility& f) {
-    all = f.mode == 0;
-    a_lo = 0u; a_last = 0u; l_lo = 0ull; l_hi = 0ull;                         // nothing feasible, nothing listed
-    if (f.mode == 2) { a_lo = f.T1; a_last = f.T1; l_lo = (unsigned long long)f.jT + 1ull; l_hi = l_lo; }
+    uint32_t alo = 0u, alast = 0u;
+    unsigned long long llo = 0ull, lhi = 0ull;                                 // nothing feasible, nothing listed
+    if (f.mode == 0) { alast = 0xffffffffu; llo = 1ull << 32; lhi = llo; }      // every keyed entry is feasible
+    else if (f.mode == 2) { alo = f.T1; alast = f.T1; llo = (unsigned long long)f.jT + 1ull; lhi = llo; }
     else if (f.mode == 1 && f.b.bsel >= 0) {
-      a_lo = bk::bin_lo(f.b.bsel); a_last = bk::bin_last(f.b.bsel); l_hi = 1ull << 32;
-      if (f.b.kind == 1) { l_lo = (unsigned long long)f.b.csel << f.lsh; l_hi = (unsigned long long)(f.b.csel + 1) << f.lsh; }
-      else if (f.b.kind == 2) { a_lo += (uint32_t)f.b.csel << bk::SUB_SHIFT; a_last = a_lo + (1u << bk::SUB_SHIFT) - 1u; }
+      alo = bk::bin_lo(f.b.bsel); alast = bk::bin_last(f.b.bsel); lhi = 1ull << 32;
+      if (f.b.kind == 1) { llo = (unsigned long long)f.b.csel << f.lsh; lhi = (unsigned long long)(f.b.csel + 1) << f.lsh; }
+      else if (f.b.kind == 2) { alo += (uint32_t)f.b.csel << bk::SUB_SHIFT; alast = alo + (1u << bk::SUB_SHIFT) - 1u; }
     }
+    const uint32_t lo32 = llo > 0xffffffffull ? 0xffffffffu : (uint32_t)llo, hi32 = lhi > 0xffffffffull ? 0xffffffffu : (uint32_t)lhi;
+    a_lo = alo; a_span = alast - alo; l_lo = lo32; l_span = hi32 - lo32;
   }
   __device__ __forceinline__ void judge(uint32_t ka, uint32_t l, bool& feas, bool& bound) const {
-    const bool in = ka >= a_lo && ka <= a_last;
-    feas = all || ka < a_lo || (in && l < l_lo);
-    bound = !all && in && l >= l_lo && l < l_hi;
+    const bool in = ka - a_lo <= a_span;
+    feas = (ka < a_lo) | (in & (l < l_lo));
+    bound = in & (l - l_lo < l_span);
   }
 };
 
@@ -282,12 +285,15 @@ struct FeasCut {
 template <class Get, class Push, class Sync>
 __device__ __forceinline__ void bucket_pass(const BucketScratch& s, const Feasibility& f, int NEl, int rank, int tid, int nthr,
                                             Get get, Push push_peers, Sync sync, unsigned long long* dbg = nullptr) {
-  Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
   if (nthr > bk::NTHR) nthr = bk::NTHR;
   const bool active = tid < nthr;                                // a wider group idles (but joins the barrier)
   const FeasCut cut(f);
-  constexpr int U = 4;                                            // entries in flight per thread (the loads first)
+  // two entries in flight per thread.  The pass runs once per launch from a cold instruction cache (a third of the tail's
+  // stall samples were instruction fetches), so a compact body beats a deeper unroll: the loads are shared-memory hits
+  constexpr int U = 2;
+  Tuple128 best; best.hi = ~0ull; best.lo = ~0ull;
   const uint32_t cursor = smem_u32(&s.misc[12]), bl = smem_u32(s.blist);
+#pragma unroll 1
   for (int e0 = tid; active && e0 < NEl; e0 += U * nthr) {
     uint32_t ka[U], kb[U], l[U];
     bool c[U];
@@ -299,19 +305,20 @@ __device__ __forceinline__ void bucket_pass(const BucketScratch& s, const Feasib
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (!c[u]) continue;
+      // branch-free except for the (rare) listed entries: the pass is a chain of dependent compares on two warps per
+      // scheduler, so instructions per entry are what it costs
       bool feas, bound;
       cut.judge(ka[u], l[u], feas, bound);
-      if (!feas && !bound) continue;
-      Tuple128 t;
-      t.hi = ((unsigned long long)kb[u] << 32) | ka[u];
-      t.lo = ((unsigned long long)l[u] << 32) | ((uint32_t)rank << 24) | (uint32_t)(e0 + u * nthr);
-      if (feas) { if (tuple_less(t, best)) best = t; }
-      else {
+      const unsigned long long hi = ((unsigned long long)kb[u] << 32) | ka[u];
+      const unsigned long long lo = ((unsigned long long)l[u] << 32) | ((uint32_t)rank << 24) | (uint32_t)(e0 + u * nthr);
+      const bool less = c[u] & feas & ((hi < best.hi) | ((hi == best.hi) & (lo < best.lo)));
+      best.hi = less ? hi : best.hi;
+      best.lo = less ? lo : best.lo;
+      if (c[u] & bound) {
         uint32_t slot;
         asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(cursor) : "memory");
         const int pos = f.b.my_off + (int)slot;
-        if (pos < bk::CAP) asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(bl + 16u * (uint32_t)pos), "l"(t.hi), "l"(t.lo) : "memory");
+        if (pos < bk::CAP) asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(bl + 16u * (uint32_t)pos), "l"(hi), "l"(lo) : "memory");
       }
     }
   }
@@ -342,18 +349,29 @@ __device__ __forceinline__ bool bucket_final(const BucketScratch& s, const Feasi
   const int m = f.mode == 1 ? (f.b.mtot < bk::CAP ? f.b.mtot : bk::CAP) : 0;
   const int nt = nthr > bk::NTHR ? bk::NTHR : nthr;
   const uint32_t bl = smem_u32(s.blist), xg = smem_u32(s.xg);
-  for (int i = tid; i < m && tid < nt; i += nt) {
-    Tuple128 t;
-    lds_2u64(bl + 16 * i, t.hi, t.lo);
-    const unsigned long long key = (t.hi << 32) | (t.lo >> 32);          // (std key, logical index)
-    int rk = 0;
+  // ranks by brute force, eight lanes per listed entry (each counts every eighth competitor)
+  if (tid < nt) {                                                  // (whole warps: nt is a multiple of 32)
+    const int sub = tid & 7;
+    for (int i0 = 0; i0 < m; i0 += nt / 8) {
+      const int i = i0 + (tid >> 3);
+      const bool valid = i < m;
+      Tuple128 t; t.hi = ~0ull; t.lo = ~0ull;
+      if (valid) lds_2u64(bl + 16 * i, t.hi, t.lo);
+      const unsigned long long key = (t.hi << 32) | (t.lo >> 32);          // (std key, logical index)
+      int rk = 0;
+      if (valid) {
 #pragma unroll 4
-    for (int j = 0; j < m; ++j) {
-      unsigned long long hj, lj2;
-      lds_2u64(bl + 16 * j, hj, lj2);
-      rk += ((hj << 32) | (lj2 >> 32)) < key ? 1 : 0;
+        for (int j = sub; j < m; j += 8) {
+          unsigned long long hj, lj2;
+          lds_2u64(bl + 16 * j, hj, lj2);
+          rk += ((hj << 32) | (lj2 >> 32)) < key ? 1 : 0;
+        }
+      }
+      rk += __shfl_xor_sync(0xffffffffu, rk, 1);
+      rk += __shfl_xor_sync(0xffffffffu, rk, 2);
+      rk += __shfl_xor_sync(0xffffffffu, rk, 4);
+      if (valid && sub == 0 && rk < f.b.rb && tuple_less(t, best)) best = t;
     }
-    if (rk < f.b.rb && tuple_less(t, best)) best = t;
   }
   for (int i = tid; i < C * bk::NW && tid < nt; i += nt) {
     Tuple128 t;
