@@ -258,8 +258,13 @@ def build_workload(w, B, dev, L=None, seed=0):
     H, Hkv, n, pol = w["H"], w["Hkv"], w["n"], w["policy"]
     ql = w.get("stride", 1)
     per_layer = 2 * B * Hkv * n * D * 2
-    if L is None:                                # enough distinct layers that a step streams several times the 126 MB L2
-        L = min(w["L"], max(4, math.ceil(768e6 / per_layer)))
+    if L is None:
+        # enough distinct layers that a step streams several times the 126 MB L2, and at least 16 (never more than the
+        # model has): the per-step costs — the input refresh below, the graph launch — are amortised over 32-80 layers
+        # in the real model, and over 4-6 they inflated the per-layer time of the small workloads by 10-20 %
+        L = min(w["L"], max(16, math.ceil(768e6 / per_layer)))
+        while L > 4 and L * per_layer > 48e9:
+            L -= 1
     torch.manual_seed(1234 + seed)
     grow = pol == "full"
     cache = BudgetedKVCache(L, B, H, Hkv, D, n + ql * (1 if not grow else 64), dtype=torch.float16, device=dev, arith=1)
@@ -309,7 +314,7 @@ def build_workload(w, B, dev, L=None, seed=0):
     def refresh():
         cursor.add_(1).remainder_(POOL)
         for dst, src in zip((q, kn, vn), pool):
-            dst.copy_(src.index_select(0, cursor)[0])
+            torch.index_select(src, 0, cursor, out=dst.unsqueeze(0))       # one gather kernel per tensor, straight into place
     steady.capture(pre=None if os.environ.get("EKV_BENCH_FIXED_INPUTS") else refresh)   # (development: one fixed input set)
     return cache, steady, L, q, kn, vn
 

@@ -37,6 +37,9 @@ int umma_force_cluster() { return (g_chunk.load(std::memory_order_relaxed) >> 8)
 int decode_variant() { return g_variant.load(std::memory_order_relaxed); }
 int decode_cluster_size() { return g_cluster.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// programmatic dependent launch on every attention kernel (EKV_NO_PDL=1 in the environment at load turns it off: A/B hook)
+static const int g_pdl = [] { const char* e = getenv("EKV_NO_PDL"); return (e && atoi(e)) ? 0 : 1; }();
+int pdl_allowed() { return g_pdl; }
 
 static int build_args(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, KernelArgs& a) {
   if (!sh || !io) return set_error(EKV_ERR_INVALID, "null shape/io");

@@ -593,7 +593,7 @@ template <typename T, int G> static int launch_finish_tg(const KernelArgs& a, co
   const int col_blocks = (U * pl.NEpad + 255) / 256;               // state update: always (new slots need their state)
   cudaLaunchAttribute pdl[1];
   pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // both kernels wait (pdl_wait) before their first global access
-  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  pdl[0].val.programmaticStreamSerializationAllowed = pdl_allowed();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(out_blocks + col_blocks), 1, 1);
   cfg.blockDim = dim3(256, 1, 1);

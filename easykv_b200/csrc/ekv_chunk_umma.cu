@@ -636,7 +636,7 @@ static int launch_umma_k(const KernelArgs& a, const ChunkPlan& pl, const CUtenso
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // the kernel waits (pdl_wait) before its first global access
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_allowed();
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   err = cudaLaunchKernelEx(&cfg, chunk_umma_kernel<T, G, ARITH, NSPLIT>, a, pl, maps[0], maps[1], maps[2], maps[3]);

@@ -962,7 +962,7 @@ static int launch_cluster_tg(const KernelArgs& a, int C, int slice, int stages, 
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // the kernel waits (pdl_wait) before its first global access
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_allowed();
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   err = cudaLaunchKernelEx(&cfg, decode_cluster_kernel<T, G, TC>, a, stages, slice);

@@ -28,6 +28,7 @@ unsigned long long* debug_timeline();
 int set_cuda_error(const char* what, cudaError_t err);
 int set_error(int code, const char* fmt, ...);
 void count_launch();
+int pdl_allowed();    // 1 unless EKV_NO_PDL was set at load (ekv_api.cu)
 
 int launch_decode(const KernelArgs& a, cudaStream_t stream);      // ekv_decode.cu
 int launch_decode_cluster(const KernelArgs& a, bool only_if_better, cudaStream_t stream);   // ekv_decode_cluster.cu
