@@ -39,8 +39,7 @@ def oracle_step(orcs, st, q, k, v):
     return torch.stack(outs), (None if vics[0] is None else torch.stack(vics))
 
 
-def decode_case(label, B, H, Hkv, n, steps, variant, cluster, dtype=torch.float16, steady=False):
-    d = 128
+def decode_case(label, B, H, Hkv, n, steps, variant, cluster, dtype=torch.float16, steady=False, d=128, kernel=0):
     g = torch.Generator().manual_seed(3)
     rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
     lib.ekv_debug_set_dispatch(variant, cluster)
@@ -72,7 +71,7 @@ def decode_case(label, B, H, Hkv, n, steps, variant, cluster, dtype=torch.float1
                 sd.run()                                       # victim_slots aliases new_slots from here on
                 out, vl = sd.out[0].clone(), sd.victim_lidx[0].clone()
         else:
-            out, vl = cache.step(0, sp, q.cuda(), k.cuda(), v.cuda())
+            out, vl = cache.step(0, sp, q.cuda(), k.cuda(), v.cuda(), kernel=kernel)
         torch.cuda.synchronize()
         assert (out.cpu().float() - o_ref.float()).abs().max().item() <= 1e-3, label
         if check_victims:
@@ -81,8 +80,7 @@ def decode_case(label, B, H, Hkv, n, steps, variant, cluster, dtype=torch.float1
     print(f"ok {label}", flush=True)
 
 
-def chunk_case(label, B, H, Hkv, n, stride, steps, variant, dtype=torch.float16, policy="roco"):
-    d = 128
+def chunk_case(label, B, H, Hkv, n, stride, steps, variant, dtype=torch.float16, policy="roco", d=128, kernel=0):
     g = torch.Generator().manual_seed(4)
     rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
     lib.ekv_debug_set_chunk_variant(variant)
@@ -100,7 +98,7 @@ def chunk_case(label, B, H, Hkv, n, stride, steps, variant, dtype=torch.float16,
     for t in range(steps):
         q, k, v = rnd(B, H, stride, d) * 0.3, rnd(B, Hkv, stride, d), rnd(B, Hkv, stride, d)
         o_ref, v_ref = oracle_step(orcs, st, q, k, v)
-        out, vl = cache.step(0, StepParams.from_fields(st), q.cuda(), k.cuda(), v.cuda())
+        out, vl = cache.step(0, StepParams.from_fields(st), q.cuda(), k.cuda(), v.cuda(), kernel=kernel)
         torch.cuda.synchronize()
         assert (out.cpu().float() - o_ref.float()).abs().max().item() <= 1e-3, label
         assert torch.equal(vl.cpu().long(), v_ref), (label, t)
@@ -129,5 +127,12 @@ if run("chunk_umma"):
     chunk_case("tcgen05 chunk, two row blocks, g=2", 1, 4, 2, 300, 64, 2, variant=0)
 if run("chunk_tc"):
     chunk_case("mma.sync chunk", 1, 8, 2, 300, 16, 2, variant=2)
+if run("general"):
+    # the exact kernel, a template over head_dim: 64 and 96 arrive here at the automatic dispatch, 128 with kernel = 1
+    decode_case("general kernel decode, head_dim 64, g=4", 2, 8, 2, 203, 3, variant=0, cluster=0, d=64)
+    decode_case("general kernel decode, head_dim 96", 1, 4, 4, 150, 2, variant=0, cluster=0, d=96)
+    chunk_case("general kernel chunk, head_dim 64, g=2", 1, 4, 2, 260, 16, 2, variant=0, d=64)
+    chunk_case("general kernel chunk, head_dim 96, stride 24", 1, 4, 4, 200, 24, 2, variant=0, d=96, policy="h2o_head")
+    decode_case("general kernel decode, head_dim 128 (kernel = 1)", 1, 8, 2, 203, 2, variant=0, cluster=0, kernel=1)
 print(f"library launches in this run: {lib.ekv_launch_count() - n0}")
 assert lib.ekv_launch_count() - n0 > 0
