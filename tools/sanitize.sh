@@ -19,7 +19,7 @@ leg() {   # leg <tool> <family...>
   echo "rc=$rc" | tee -a $LOG
   if [ $rc -ne 0 ] || ! grep -q "library launches in this run: [1-9]" $OUT/.san.tmp; then fail=1; echo "LEG FAILED" | tee -a $LOG; fi
 }
-leg memcheck persistent steady cluster decode_umma chunk_umma chunk_tc
+leg memcheck persistent steady cluster decode_umma chunk_umma chunk_tc general
 leg racecheck persistent steady
 leg racecheck cluster
 leg racecheck decode_umma
