@@ -97,9 +97,36 @@ decode_cluster_kernel(const KernelArgs a, const int stages, const int slice) {
   constexpr int TILEB = TC ? TC_TILE_BYTES : Cfg::TILE_BYTES;
   static_assert(!TC || (sizeof(T) == 2 && TILE_ROWS == 64), "tensor-core variant: 16-bit dtypes");
   pdl_trigger();            // programmatic dependent launch: the next kernel may be placed now; this one touches global memory
-  pdl_wait();               // only once the previous kernel of the stream has completed (ekv_common.cuh)
-  extern __shared__ __align__(128) unsigned char smem[];
   const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+  {
+    // ... only once the previous kernel of the stream has completed (pdl_wait below).  Until then — small batches: this
+    // CTA is resident beside the previous layer's CTAs for most of their run — it pulls its slice of the cache and of
+    // the policy state into L2.  Prefetches are hints and L2 is the point of coherence, so this is safe whatever the
+    // previous kernel still writes; nothing is READ before the wait.  Bounded so that a launch never asks for more
+    // than ~48 MB (the slices of a small batch fit L2 whole; a larger launch takes the first rows only).
+    const int lo_p = min(rank * slice, a.n_phys), n_p = min(lo_p + slice, a.n_phys) - lo_p;
+    const long long per_row = 2ll * Cfg::ROW_BYTES * (long long)gridDim.x;
+    const int rows_p = (int)min((long long)n_p, (48ll << 20) / per_row);
+    const size_t e0 = (size_t)(blockIdx.x / C) * a.cap + lo_p;
+    const char* kp = reinterpret_cast<const char*>(a.K) + e0 * Cfg::ROW_BYTES;
+    const char* vp = reinterpret_cast<const char*>(a.V) + e0 * Cfg::ROW_BYTES;
+    constexpr int CH = 2048;                                     // bytes per bulk prefetch (rows are 16-byte multiples)
+    const int kv_bytes = rows_p * Cfg::ROW_BYTES;
+    for (int off = (int)threadIdx.x * CH; off < kv_bytes; off += (int)blockDim.x * CH) {
+      const uint32_t nbytes = (uint32_t)min(CH, kv_bytes - off);
+      bulk_prefetch_l2(kp + off, nbytes);
+      bulk_prefetch_l2(vp + off, nbytes);
+    }
+    const int st_lines = (rows_p * 4 + 127) / 128;               // slot map + S, SQ, C: one 128-byte line per prefetch
+    for (int i = (int)threadIdx.x; i < 4 * st_lines; i += (int)blockDim.x) {
+      const int which = i / st_lines;
+      const char* base = which == 0 ? reinterpret_cast<const char*>(a.lidx) : which == 1 ? reinterpret_cast<const char*>(a.S)
+                         : which == 2 ? reinterpret_cast<const char*>(a.SQ) : reinterpret_cast<const char*>(a.C);
+      if (base) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + e0 * 4 + (size_t)(i % st_lines) * 128));
+    }
+  }
+  pdl_wait();
+  extern __shared__ __align__(128) unsigned char smem[];
   const ClusterSmem<T> L(G, slice, C, TC);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* empty = full + Cfg::MAX_STAGES;
