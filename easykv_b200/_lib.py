@@ -17,7 +17,7 @@ POLICY_NONE, POLICY_ROCO, POLICY_H2O, POLICY_TOVA, POLICY_RANGE = 0, 1, 2, 3, 4
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 
 EXPORTS = ("ekv_abi_version", "ekv_last_error", "ekv_scratch_bytes", "ekv_attend_evict", "ekv_select",
-           "ekv_evict_explicit", "ekv_export_logical", "ekv_launch_count", "ekv_debug_set_timeline", "ekv_debug_set_dispatch", "ekv_rope_qk", "ekv_rope_cache", "ekv_sample_top_p", "ekv_token_nll", "ekv_debug_umma_probe", "ekv_debug_set_chunk_variant")
+           "ekv_evict_explicit", "ekv_export_logical", "ekv_launch_count", "ekv_debug_set_timeline", "ekv_debug_set_dispatch", "ekv_rope_qk", "ekv_rope_cache", "ekv_sample_top_p", "ekv_token_nll", "ekv_debug_umma_probe", "ekv_debug_set_chunk_variant", "ekv_chunk_entry_limit")
 
 
 class Step(C.Structure):
@@ -59,6 +59,8 @@ def load():
     lib.ekv_launch_count.restype = C.c_int64
     lib.ekv_scratch_bytes.restype = C.c_int64
     lib.ekv_scratch_bytes.argtypes = [C.POINTER(Shape), C.POINTER(Step)]
+    lib.ekv_chunk_entry_limit.restype = C.c_int32
+    lib.ekv_chunk_entry_limit.argtypes = [C.POINTER(Shape), C.c_int32, C.c_int32]
     lib.ekv_attend_evict.restype = C.c_int
     lib.ekv_attend_evict.argtypes = [C.POINTER(Shape), C.POINTER(LayerIO), C.POINTER(Step), C.c_int32, C.c_void_p]
     lib.ekv_select.restype = C.c_int

@@ -68,6 +68,29 @@ class BudgetedKVCache:
         return _lib.Shape(dtype=_DTYPES[self.dtype], B=self.B, H=self.H, Hkv=self.Hkv, d=self.d, q_len=q_len,
                           cap=self.cap, n_before=self.n[l], n_phys=self.n_phys[l])
 
+    def entry_limit(self, q_len, evict, kernel=0):
+        """Entries per (sequence, kv head) an evicting forward of `q_len` rows can hold (`ekv_chunk_entry_limit`): the
+        strided chunk's per-unit tail and the exact kernel select in one CTA's shared memory."""
+        return int(self.lib.ekv_chunk_entry_limit(C.byref(self._shape(0, q_len)), int(evict), int(kernel)))
+
+    def check_schedule(self, n_dense, sched, kernel=0):
+        """Fail BEFORE the first forward when some evicting forward of the schedule (`plan.schedule` items) would hold
+        more entries than the kernels can select among — instead of `EKV_ERR_UNSUPPORTED` in the middle of a prompt."""
+        n, limits = n_dense, {}
+        for _, q_len, st in sched:
+            ev = int(st.evict)
+            if ev > 0 and getattr(st, "policy", "roco") not in ("none", "full"):
+                key = (q_len, ev)
+                if key not in limits:
+                    limits[key] = self.entry_limit(q_len, ev, kernel)
+                if n + q_len > limits[key]:
+                    raise NotImplementedError(
+                        f"a forward of {q_len} tokens that evicts {ev} per head over {n + q_len} cache entries exceeds what the "
+                        f"kernels select among ({limits[key]} entries for this dtype / head layout; include/easykv_b200.h, "
+                        f"ekv_chunk_entry_limit): use a smaller budget or stride, or kv_policy='full'")
+            n += q_len - ev
+        return True
+
     def _io(self, l, **kw):
         io = _lib.LayerIO(K=_ptr(self.K[l]), V=_ptr(self.V[l]), S=_ptr(self.S[l]), SQ=_ptr(self.SQ[l]),
                           C=_ptr(self.Cn[l]), lidx=_ptr(self.lidx[l]))

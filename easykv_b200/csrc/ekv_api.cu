@@ -186,6 +186,17 @@ int ekv_attend_evict(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step
   return launch_chunk_auto(a, sh, kernel, s);
 }
 
+int32_t ekv_chunk_entry_limit(const ekv_shape* sh, int32_t evict, int32_t kernel) {
+  if (!sh || sh->q_len < 1 || sh->Hkv < 1) return 0;
+  if (evict <= 0) return INT32_MAX;                                       // nothing is selected: no per-entry scratch
+  const int G = sh->H / sh->Hkv;
+  const bool g_ok = G == 1 || G == 2 || G == 4 || G == 8;
+  if (sh->q_len == 1 && kernel == 0 && sh->d == 128 && g_ok && evict == 1)        // the decode kernels split a unit over a cluster of <= 8 CTAs
+    return decode_cluster_entry_limit(sh->dtype, G) + 1;
+  if (kernel == 0 && chunk_tc_shape(sh)) return chunk_tc_entry_limit(sh->q_len, evict);
+  return general_entry_limit(sh->q_len, evict, sh->d);
+}
+
 int ekv_select(const ekv_shape* sh, const ekv_layer_io* io, const ekv_step* st, void* stream) {
   KernelArgs a;
   int rc = build_args(sh, io, st, a);

@@ -311,6 +311,16 @@ __global__ void __launch_bounds__(gen::NT) general_kernel(const KernelArgs a) {
   }
 }
 
+// largest n_phys + q_len the general kernel can hold when it selects `evict` victims (ekv_chunk_entry_limit)
+int general_entry_limit(int q_len, int evict, int d) {
+  int lo = 0, hi = 1 << 22;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if (GenSmem(mid, q_len, evict, d).total <= 227 * 1024) lo = mid; else hi = mid - 1;
+  }
+  return lo + q_len;
+}
+
 template <typename T, int G, int D> static int launch_general_tgd(const KernelArgs& a, cudaStream_t stream) {
   const GenSmem L(a.n_phys, a.q_len, a.st.evict, D);
   if (L.total > 227 * 1024) return set_error(EKV_ERR_UNSUPPORTED, "general kernel: %d bytes of shared memory needed", L.total);

@@ -499,6 +499,16 @@ struct TailSmem {
   }
 };
 
+// largest NE whose evicting tail fits one CTA's shared memory (ekv_chunk_entry_limit)
+int chunk_tc_entry_limit(int q_len, int evict) {
+  int lo = 0, hi = 1 << 22;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if (TailSmem(mid, q_len, evict, true).total <= 227 * 1024) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 template <typename T> __global__ void __launch_bounds__(TAIL_NT) chunk_tail_kernel(const KernelArgs a, const ChunkPlan pl) {
   using namespace tc;
   pdl_trigger();            // programmatic dependent launch (ekv_common.cuh)

@@ -1046,6 +1046,29 @@ static int plan_cluster(const KernelArgs& a, int sms, int force_c, int& C, int& 
   return best ? EKV_OK : EKV_ERR_UNSUPPORTED;
 }
 
+// largest n_phys a decode step can hold on this kernel (clusters of 8, FMA variant): ekv_chunk_entry_limit
+template <typename T> static int cluster_limit_t(int G) {
+  using Cfg = DecodeCfg<T>;
+  int lo = 0, hi = 1 << 22;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    int sl = align_up((mid + 7) / 8, 8);
+    if (sl < 8) sl = 8;
+    const ClusterSmem<T> L(G, sl, 8, false);
+    const int min_ring = ClusterSmem<T>::min_ring(G) > 3 * Cfg::TILE_BYTES ? ClusterSmem<T>::min_ring(G) : 3 * Cfg::TILE_BYTES;
+    if (227 * 1024 - L.fixed >= min_ring) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+int decode_cluster_entry_limit(int dtype, int G) {
+  switch (dtype) {
+    case EKV_F16: return cluster_limit_t<__half>(G);
+    case EKV_BF16: return cluster_limit_t<__nv_bfloat16>(G);
+    case EKV_F32: return cluster_limit_t<float>(G);
+    default: return 0;
+  }
+}
+
 int decode_cluster_size();   // ekv_api.cu (env EKV_DECODE_CLUSTER): 0 = automatic, else forced cluster size
 int decode_variant();        // ekv_api.cu: 3 = never / 4 = always use the tensor-core variant (g >= 4, 16-bit)
 

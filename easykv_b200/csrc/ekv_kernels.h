@@ -36,6 +36,9 @@ int launch_decode_umma(const KernelArgs& a, cudaStream_t stream);               
 int launch_general(const KernelArgs& a, cudaStream_t stream);     // ekv_chunk.cu
 int launch_chunk_tc(const KernelArgs& a, cudaStream_t stream);    // ekv_chunk_tc.cu (16-bit dtypes, needs scratch)
 long long chunk_tc_scratch_bytes(int B, int Hkv, int G, int q_len, int n_phys);
+int chunk_tc_entry_limit(int q_len, int evict);                  // ekv_chunk_tc.cu: entries the evicting chunk tail can hold
+int decode_cluster_entry_limit(int dtype, int G);                // ekv_decode_cluster.cu: cached slots a decode step can hold
+int general_entry_limit(int q_len, int evict, int d);            // ekv_chunk.cu: ... the general kernel
 int launch_select(const KernelArgs& a, cudaStream_t stream);      // ekv_aux.cu
 int launch_tova_head_mean(const KernelArgs& a, cudaStream_t stream);
 int launch_evict_explicit(const KernelArgs& a, const int32_t* victims, int evict, cudaStream_t stream);

@@ -198,6 +198,10 @@ def generate(self, input_ids, generation_config, kv_mode="encoding", stride=1, r
     # ekv_step.arith): the CUDA kernels' (default — what the reference does on a GPU) or the CPU kernels'
     arith = {"cuda": 1, "cpu": 0}[cfg.get("aten_arith", "cuda")]
     cache = BudgetedKVCache(len(mods), bsz, H, Hkv, d, capacity, dtype=dtype, device=device, arith=arith)
+    # an evicting forward selects among all of a head's entries inside one CTA (strided chunks) or one cluster (decode
+    # steps): a schedule that would exceed that fails here, before the first forward, not in the middle of the prompt
+    if hasattr(cache, "check_schedule"):
+        cache.check_schedule(n_dense, sched)
     sess = Session(self, cache, record=cfg.get("record_evictions", True))
     if sess.rotary is not None:
         # transformers >= 4.48 builds a causal mask per forward — element-wise launches plus a host sync (its packed-

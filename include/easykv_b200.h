@@ -156,6 +156,17 @@ EKV_API const char* ekv_last_error(void);
  * (b) step->tova_head_mean (required).  Contents need not survive the call. */
 EKV_API int64_t ekv_scratch_bytes(const ekv_shape* shape, const ekv_step* step);
 
+/* Largest number of entries per (sequence, kv head) — cached slots + the q_len appended rows — that an EVICTING forward
+ * of this shape (dtype, d, H / Hkv, q_len; n_before / n_phys are ignored) can hold when `evict` victims are selected:
+ * the per-unit tail of a strided chunk (q_len > 1) and the exact general kernel keep one logical index and two
+ * selection keys per entry in one CTA's shared memory (about 17.6 K entries in a 16-bit dtype on the tensor-core
+ * path, about 11 K on the general kernel, which also serves kernel == 1, fp32 and d != 128).  Decode steps on the
+ * decode kernels (q_len == 1, evict == 1, kernel == 0, d == 128) split a unit over a cluster of up to 8 CTAs: tens of
+ * thousands of slots, depending on dtype and group size.  Non-evicting forwards have no ceiling: INT32_MAX.
+ * A caller checks its schedule against this BEFORE the first forward instead of meeting EKV_ERR_UNSUPPORTED in
+ * the middle of a prompt (the reference has no such limit: easykv.py:459-499).  No GPU needed.  (Additive in ABI v8.) */
+EKV_API int32_t ekv_chunk_entry_limit(const ekv_shape* shape, int32_t evict, int32_t kernel);
+
 /* Fused forward for one layer: append -> QK^T/sqrt(d) -> softmax -> PV -> GQA fold ->
  * policy accumulate -> budgeted victim select -> in-place eviction.
  * Replaces: llama_patch.py:193-230 (cache append, repeat_kv, matmul, mask, softmax, matmul),

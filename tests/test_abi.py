@@ -1,5 +1,7 @@
 """The C-ABI library builds, loads, and exports exactly what include/easykv_b200.h declares (no GPU needed)."""
 import ctypes
+
+import pytest
 import os
 import re
 
@@ -83,6 +85,41 @@ def test_scratch_bytes_is_host_only_and_consistent(ekv_lib):
     tova = _lib.Step(policy=_lib.POLICY_TOVA, accumulate=1, evict=16, tova_head_mean=1)
     assert need(_lib.F16, 16, 8208, tova) == b + 2 * 8 * (8208 + 16) * 4
     assert need(_lib.F32, 16, 8208, tova) == 2 * 8 * (8208 + 16) * 4
+
+
+def test_entry_limit_is_host_only_and_plausible(ekv_lib):
+    """ekv_chunk_entry_limit needs no GPU: ~17.6 K entries for an evicting 16-bit chunk on the tensor-core path, ~11 K on
+    the exact kernel (fp32, kernel = 1, head_dim 64), tens of thousands for decode steps, no ceiling without eviction."""
+    from easykv_b200 import _lib
+    def lim(dtype, H, Hkv, d, q_len, evict, kernel=0):
+        sh = _lib.Shape(dtype=dtype, B=1, H=H, Hkv=Hkv, d=d, q_len=q_len, cap=0, n_before=0, n_phys=0)
+        return ekv_lib.ekv_chunk_entry_limit(ctypes.byref(sh), evict, kernel)
+    assert 17000 < lim(_lib.F16, 32, 8, 128, 16, 16) < 18500
+    assert lim(_lib.BF16, 32, 32, 128, 64, 64) == lim(_lib.F16, 32, 32, 128, 64, 64)
+    assert 10000 < lim(_lib.F32, 32, 8, 128, 16, 16) < 12000
+    assert lim(_lib.F16, 32, 8, 128, 16, 16, kernel=1) == lim(_lib.F32, 32, 8, 128, 16, 16)
+    assert 10000 < lim(_lib.F16, 32, 32, 64, 64, 64) < 12000
+    assert lim(_lib.F16, 32, 32, 128, 1, 1) > lim(_lib.F16, 64, 8, 128, 1, 1) > 30000
+    assert lim(_lib.F16, 32, 8, 128, 16, 0) == 2 ** 31 - 1
+
+
+def test_check_schedule_fails_before_the_first_forward(ekv_lib):
+    """A schedule whose evicting strided chunks would hold more entries per head than the chunk tail can select among is
+    refused up front (the reference has no such ceiling; here it is EKV_ERR_UNSUPPORTED, never a mid-prompt surprise):
+    Mistral layout, 32 K prompt, stride 16 — budget 0.5 (16 K retained) passes, 0.6 (19.7 K) is refused; kv_policy
+    'full' (nothing evicted) always passes."""
+    import torch
+    from easykv_b200 import plan as P
+    from easykv_b200.cache import BudgetedKVCache
+    c = object.__new__(BudgetedKVCache)                       # no device memory: only the shape arithmetic is exercised
+    c.lib, c.dtype, c.B, c.H, c.Hkv, c.d, c.cap, c.n, c.n_phys = ekv_lib, torch.float16, 1, 32, 8, 128, 0, [0], [0]
+    def run(budget, policy):
+        pl = P.resolve_plan("encoding", 32768, budget, 16, 0.1, 4)
+        return c.check_schedule(pl.r_idx, list(P.schedule(pl, policy, 4, False)))
+    assert run(0.5, "roco")
+    assert run(0.6, "full")
+    with pytest.raises(NotImplementedError, match="ekv_chunk_entry_limit"):
+        run(0.6, "roco")
 
 
 def test_product_never_imports_the_oracle():

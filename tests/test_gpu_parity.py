@@ -277,6 +277,42 @@ def test_head_dim_64_96_vs_oracle(engines, d, dtype, H, Hkv, stride, policy, n0)
     assert torch.equal(Kc, orc.export(0)[0]) and torch.equal(Vc, orc.export(0)[1])
 
 
+@pytest.mark.parametrize("dtype,q_len,kernel", [
+    (torch.float16, 16, 0),       # strided chunk, tensor-core path: the per-unit tail's ceiling
+    (torch.float32, 16, 0),       # fp32 chunk: the exact kernel
+    (torch.float16, 16, 1),       # exact kernel forced
+    (torch.float16, 1, 0),        # decode step: a unit split over a cluster of 8
+])
+def test_entry_limit_matches_the_kernels(ekv_lib, dtype, q_len, kernel):
+    """ekv_chunk_entry_limit is the kernels' real ceiling: an evicting forward at exactly the limit runs, one entry more is
+    refused with EKV_ERR_UNSUPPORTED (NotImplementedError) — never a wrong result or a crash."""
+    from easykv_b200.cache import BudgetedKVCache
+    from easykv_b200.plan import StepParams
+    H = Hkv = 1
+    d, dev = 128, "cuda"
+    probe = BudgetedKVCache(1, 1, H, Hkv, d, 64, dtype=dtype)
+    limit = probe.entry_limit(q_len, q_len, kernel)
+    assert 10000 < limit < 200000
+    torch.manual_seed(3)
+    for extra, ok in ((0, True), (1, False)):
+        n = limit - q_len + extra
+        c = BudgetedKVCache(1, 1, H, Hkv, d, n + q_len, dtype=dtype)
+        c.load_prefill(0, torch.randn(1, Hkv, n, d, device=dev).to(dtype), torch.randn(1, Hkv, n, d, device=dev).to(dtype), n,
+                       [float(n - i) for i in range(n)])
+        sp = StepParams(policy="roco", accumulate=True, evict=q_len, counter_add=float(q_len), c_new_step=1.0 if q_len > 1 else 0.0,
+                        k_feasible=n - n // 4)
+        q = torch.randn(1, H, q_len, d, device=dev).to(dtype) * 0.3
+        k = torch.randn(1, Hkv, q_len, d, device=dev).to(dtype); v = torch.randn(1, Hkv, q_len, d, device=dev).to(dtype)
+        if ok:
+            out, vl = c.step(0, sp, q, k, v, kernel=kernel)
+            torch.cuda.synchronize()
+            assert torch.isfinite(out.float()).all() and vl.shape[-1] == q_len and int(vl.min()) >= 0 and int(vl.max()) < n + q_len
+            assert len(set(vl.flatten().tolist())) == q_len
+        else:
+            with pytest.raises(NotImplementedError):
+                c.step(0, sp, q, k, v, kernel=kernel)
+
+
 def test_chunk_one_pass_denominator_falls_back_when_logits_run_away(engines):
     """The tcgen05 chunk kernel sums softmax denominators in one pass against per-warp reference points (the row
     maximum over the first 128-key tile) and must detect rows whose later logits exceed that reference by more than
