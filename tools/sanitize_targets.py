@@ -39,7 +39,7 @@ def oracle_step(orcs, st, q, k, v):
     return torch.stack(outs), (None if vics[0] is None else torch.stack(vics))
 
 
-def decode_case(label, B, H, Hkv, n, steps, variant, cluster, dtype=torch.float16, steady=False, d=128, kernel=0):
+def decode_case(label, B, H, Hkv, n, steps, variant, cluster, dtype=torch.float16, steady=False, d=128, kernel=0, hard_select=False):
     g = torch.Generator().manual_seed(3)
     rnd = lambda *s: torch.randn(*s, generator=g).to(dtype)
     lib.ekv_debug_set_dispatch(variant, cluster)
@@ -52,7 +52,19 @@ def decode_case(label, B, H, Hkv, n, steps, variant, cluster, dtype=torch.float1
         o = restate.LayerOracle(Hkv, d, dtype)
         o.load_prefill(K0[b], V0[b], n, torch.tensor(C0))
         orcs.append(o)
-    st = restate.Step(policy="roco", accumulate=True, evict=1, counter_add=1.0, k_feasible=n - int(n * 0.3))
+    if hard_select:
+        # the lowest-mean slots carry the LARGEST standard deviations: the candidate attempt is rejected and the victim comes
+        # from the bucket select (histograms, classify pass, listed entries ranked exactly) — the path racecheck should see
+        gs = torch.Generator().manual_seed(9)
+        Cc = torch.tensor(C0)
+        S0 = torch.rand(B, Hkv, n, generator=gs) * 0.5 + 0.5
+        S0[:, :, ::3] *= 0.01                                       # a third of the slots: tiny mean ...
+        SQ0 = S0 * S0 / Cc * (1.0 + torch.rand(B, Hkv, n, generator=gs) * 0.2)
+        SQ0[:, :, ::3] = 4.0 + torch.rand(B, Hkv, (n + 2) // 3, generator=gs)    # ... and a huge second moment
+        cache.S[0][:, :, :n] = S0.cuda(); cache.SQ[0][:, :, :n] = SQ0.cuda()
+        for b, o in enumerate(orcs):
+            o.S, o.SQ = S0[b].clone(), SQ0[b].clone()
+    st = restate.Step(policy="roco", accumulate=True, evict=1, counter_add=1.0, k_feasible=n - int(n * 0.3) if not hard_select else n // 2)
     sp = StepParams.from_fields(st)
     sd = None
     qb = torch.zeros(1, B, H, 1, d, dtype=dtype, device=dev)
@@ -117,6 +129,12 @@ if run("cluster"):
     decode_case("cluster decode C=2 (FMA)", 1, 8, 8, 200, 3, variant=0, cluster=2)
     decode_case("cluster decode C=4, g=4 (FMA)", 1, 8, 2, 300, 3, variant=3, cluster=4)
     decode_case("cluster decode C=2, g=8 (tensor-core variant)", 1, 16, 2, 300, 3, variant=4, cluster=2)
+if run("bucket"):
+    # the bucket select itself (ekv_bucket.cuh) in both kernels that use it, on a state built to reject the candidate walk
+    decode_case("cluster decode C=2 (FMA), bucket select", 1, 8, 8, 400, 2, variant=0, cluster=2, hard_select=True)
+    decode_case("cluster decode C=4, g=4 (FMA), bucket select", 1, 8, 2, 600, 2, variant=3, cluster=4, hard_select=True)
+if run("bucket_umma"):
+    decode_case("tcgen05 GQA decode, g=4, CTA pairs, bucket select", 1, 8, 2, 700, 2, variant=5, cluster=2, hard_select=True)
 if run("decode_umma"):
     decode_case("tcgen05 GQA decode, g=4, one CTA per unit", 2, 8, 2, 300, 3, variant=5, cluster=1)
     decode_case("tcgen05 GQA decode, g=8, CTA pairs", 1, 16, 2, 700, 3, variant=5, cluster=2)
